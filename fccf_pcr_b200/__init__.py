@@ -1,0 +1,237 @@
+"""fccf_pcr_b200 — B200-native FCCF-PCR registration path behind the reference's drop-in surface.
+
+The product is `libfccf.so` (C-ABI in include/fccf.h, hand-written sm_100a CUDA kernels) and the
+`FCCF {src} {tar} {voxel}` program; this Python module is only the ctypes binding the tests and
+bench.py use, mirroring the reference's operator `computer_transform_guess` (FCCF.cpp:1370) and
+its stages.  There is no CPU fallback: without the CUDA library and a GPU every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfccf.so")
+CLI_PATH = os.path.join(_HERE, "FCCF")
+_DT = {0: np.float32, 1: np.float64, 2: np.int32, 3: np.int64}
+
+PARAM_FIELDS = [
+    "parameter_l1", "parameter_l2", "parameter_k1", "parameter_k2", "normal_vector_threshold1",
+    "normal_vector_threshold2", "face_voxel_size", "voxel_point_threshold", "curvature_threshold",
+    "select_plane_number", "quick_verify_angel_threshold", "quick_verify_distance_threshold",
+    "required_optimize_plane", "fine_verify_voxel_size", "fine_verify_number",
+    "included_angle_same_threshold", "included_angle_min_threshold", "included_angle_max_threshold",
+    "third_plane_threshold", "third_plane_normal_threshold", "cluster_number_threshold",
+    "cluster_angel_threshold", "cluster_distance_threshold", "seclct_cluster_number", "rough_threshold_gl",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_float) for n in PARAM_FIELDS] + [("emulate_pcl_overflow", C.c_int), ("reserved", C.c_int * 3)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("downsample_ms", C.c_float), ("pipeline_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("n_launches", C.c_int)]
+
+
+EXPORTS = [
+    "fccf_default_params", "fccf_create", "fccf_destroy", "fccf_last_error", "fccf_set_params", "fccf_register",
+    "fccf_register_device", "fccf_register_batch", "fccf_voxelgrid", "fccf_extract_planes", "fccf_score_hypotheses",
+    "fccf_score_hypotheses_bench", "fccf_score_counts", "fccf_quick_verify", "fccf_debug_blob", "fccf_launch_count",
+]
+
+
+def build(force=False):
+    """Compile libfccf.so and the FCCF CLI for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcdir = os.path.join(_HERE, "csrc")
+    args = ["make", "-C", srcdir, "-j8"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libfccf.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        fp, ip, vp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p
+        L.fccf_default_params.argtypes = [C.POINTER(Params)]
+        L.fccf_create.argtypes = [C.c_int, C.POINTER(Params)]
+        L.fccf_create.restype = vp
+        L.fccf_destroy.argtypes = [vp]
+        L.fccf_last_error.argtypes = [vp]
+        L.fccf_last_error.restype = C.c_char_p
+        L.fccf_set_params.argtypes = [vp, C.POINTER(Params)]
+        L.fccf_register.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, C.c_float, fp, C.POINTER(Timing)]
+        L.fccf_register_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_float, fp, C.POINTER(Timing)]
+        L.fccf_register_batch.argtypes = [vp, C.c_int, C.POINTER(fp), C.POINTER(C.c_size_t), C.POINTER(fp), C.POINTER(C.c_size_t), C.c_float, fp, C.POINTER(Timing)]
+        L.fccf_voxelgrid.argtypes = [vp, fp, C.c_size_t, C.c_float, fp, C.POINTER(C.c_int64), ip, C.POINTER(C.c_size_t)]
+        L.fccf_extract_planes.argtypes = [vp, fp, C.c_size_t, ip]
+        L.fccf_score_hypotheses.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t, fp]
+        L.fccf_score_hypotheses_bench.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t, C.c_int, fp, fp]
+        L.fccf_score_counts.argtypes = [vp, C.c_size_t, ip, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.fccf_quick_verify.argtypes = [vp, fp, C.c_size_t, fp, C.c_int, fp, C.c_int, fp, ip, ip, ip]
+        L.fccf_debug_blob.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t), ip]
+        L.fccf_launch_count.argtypes = [vp]
+        L.fccf_launch_count.restype = C.c_uint64
+        _LIB = L
+    return _LIB
+
+
+class FccfError(RuntimeError):
+    pass
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def default_params(**over):
+    p = Params()
+    lib().fccf_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+class Context:
+    """One registration context on one GPU (fccf_ctx)."""
+
+    def __init__(self, device=0, **params):
+        self.L = lib()
+        self.params = default_params(**params)
+        h = self.L.fccf_create(int(device), C.byref(self.params))
+        if not h:
+            raise FccfError("fccf_create failed: no usable CUDA device (libfccf has no CPU fallback)")
+        self.h = C.c_void_p(h)
+        self.timing = Timing()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fccf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, soft=False):
+        if rc != 0:
+            msg = self.L.fccf_last_error(self.h).decode()
+            if soft and rc == 3:
+                self.warning = msg
+                return
+            raise FccfError("libfccf error %d: %s" % (rc, msg))
+
+    def set_params(self, **over):
+        for k, v in over.items():
+            setattr(self.params, k, v)
+        self._check(self.L.fccf_set_params(self.h, C.byref(self.params)))
+
+    # computer_transform_guess + main()'s downsampling: src = argv[1], tar = argv[2]
+    def register(self, src, tar, leaf):
+        src = np.ascontiguousarray(src, np.float32)
+        tar = np.ascontiguousarray(tar, np.float32)
+        T = np.zeros(16, np.float32)
+        self._check(self.L.fccf_register(self.h, _f(src), len(src), _f(tar), len(tar), C.c_float(leaf), _f(T), C.byref(self.timing)))
+        return T.reshape(4, 4)
+
+    def register_device(self, d_src_ptr, n_src, d_tar_ptr, n_tar, leaf):
+        T = np.zeros(16, np.float32)
+        self._check(self.L.fccf_register_device(self.h, C.c_void_p(d_src_ptr), n_src, C.c_void_p(d_tar_ptr), n_tar, C.c_float(leaf), _f(T), C.byref(self.timing)))
+        return T.reshape(4, 4)
+
+    def register_batch(self, srcs, tars, leaf):
+        n = len(srcs)
+        srcs = [np.ascontiguousarray(a, np.float32) for a in srcs]
+        tars = [np.ascontiguousarray(a, np.float32) for a in tars]
+        fp = C.POINTER(C.c_float)
+        sp = (fp * n)(*[_f(a) for a in srcs])
+        tp = (fp * n)(*[_f(a) for a in tars])
+        ns = (C.c_size_t * n)(*[len(a) for a in srcs])
+        nt = (C.c_size_t * n)(*[len(a) for a in tars])
+        T = np.zeros((n, 16), np.float32)
+        self._check(self.L.fccf_register_batch(self.h, n, sp, ns, tp, nt, C.c_float(leaf), _f(T), C.byref(self.timing)))
+        return T.reshape(n, 4, 4)
+
+    def voxelgrid(self, xyz, leaf):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        n = len(xyz)
+        out = np.zeros((max(n, 1), 3), np.float32)
+        cell = np.zeros(max(n, 1), np.int64)
+        cnt = np.zeros(max(n, 1), np.int32)
+        m = C.c_size_t(0)
+        self._check(self.L.fccf_voxelgrid(self.h, _f(xyz), n, C.c_float(leaf), _f(out), cell.ctypes.data_as(C.POINTER(C.c_int64)), _i(cnt), C.byref(m)))
+        return out[:m.value].copy(), cell[:m.value].copy(), cnt[:m.value].copy()
+
+    def extract_planes(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        nf = C.c_int(0)
+        self._check(self.L.fccf_extract_planes(self.h, _f(xyz), len(xyz), C.byref(nf)))
+        return nf.value
+
+    def score_hypotheses(self, Ts, s1, s2):
+        Ts = np.ascontiguousarray(Ts, np.float32).reshape(-1, 16)
+        s1 = np.ascontiguousarray(s1, np.float32)
+        s2 = np.ascontiguousarray(s2, np.float32)
+        sc = np.zeros(max(len(Ts), 1), np.float32)
+        self._check(self.L.fccf_score_hypotheses(self.h, _f(Ts), len(Ts), _f(s1), len(s1), _f(s2), len(s2), _f(sc)))
+        return sc[:len(Ts)]
+
+    def score_hypotheses_bench(self, Ts, s1, s2, repeat):
+        Ts = np.ascontiguousarray(Ts, np.float32).reshape(-1, 16)
+        s1 = np.ascontiguousarray(s1, np.float32)
+        s2 = np.ascontiguousarray(s2, np.float32)
+        sc = np.zeros(max(len(Ts), 1), np.float32)
+        ms = C.c_float(0)
+        self._check(self.L.fccf_score_hypotheses_bench(self.h, _f(Ts), len(Ts), _f(s1), len(s1), _f(s2), len(s2), int(repeat), _f(sc), C.byref(ms)))
+        return sc[:len(Ts)], ms.value
+
+    def score_counts(self, hyp, cap_rows=1 << 20):
+        rows = np.zeros((cap_rows, 5), np.int32)
+        n = C.c_size_t(0)
+        self._check(self.L.fccf_score_counts(self.h, int(hyp), _i(rows), cap_rows, C.byref(n)))
+        r = rows[:min(n.value, cap_rows)]
+        order = np.lexsort((r[:, 2], r[:, 1], r[:, 0]))
+        return r[order].copy()
+
+    def quick_verify(self, Ts, planes1, planes2):
+        Ts = np.ascontiguousarray(Ts, np.float32).reshape(-1, 16).copy()
+        p1 = np.ascontiguousarray(planes1, np.float32).reshape(-1, 7)
+        p2 = np.ascontiguousarray(planes2, np.float32).reshape(-1, 7)
+        n = len(Ts)
+        sc = np.zeros(n, np.float32)
+        npair = np.zeros(n, np.int32)
+        pairs = np.zeros((n, 16, 2), np.int32)
+        iters = np.zeros(n, np.int32)
+        self._check(self.L.fccf_quick_verify(self.h, _f(Ts), n, _f(p1), len(p1), _f(p2), len(p2), _f(sc), _i(npair), _i(pairs), _i(iters)))
+        return sc, Ts.reshape(-1, 4, 4), npair, pairs, iters
+
+    def blob(self, name):
+        nb = C.c_size_t(0)
+        dt = C.c_int(0)
+        self._check(self.L.fccf_debug_blob(self.h, name.encode(), None, 0, C.byref(nb), C.byref(dt)))
+        out = np.zeros(nb.value // np.dtype(_DT[dt.value]).itemsize, _DT[dt.value])
+        if nb.value:
+            self._check(self.L.fccf_debug_blob(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), nb.value, C.byref(nb), C.byref(dt)))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self.L.fccf_launch_count(self.h))

@@ -1,0 +1,314 @@
+// cluster.cu — transform_cluster (FCCF.cpp:1040-1231) for the three roughness pools.
+//
+// The reference seeds clusters greedily in index order (the last hypothesis never seeds,
+// FCCF.cpp:1084), gathers with pcl::KdTreeFLANN::radiusSearch (squared L2 < r^2, sorted by
+// (distance, index)) plus a 2-degree test on the rotated x axis, sorts clusters by size with an
+// exchange sort (range_cluster, 1020-1038) and emits averaged centres with an adaptive size
+// cut-off (1123-1229).  Here:
+//   cluster_prep    rotated x axis per hypothesis and a (type, x) sort key
+//   radix sort      (sort.cu) -> hypotheses ordered by translation x inside each pool, so the
+//                   exact radius test only visits an x-window
+//   cluster_kernel  one CTA per pool: the greedy seeding is the lexicographically-first
+//                   independent set of the neighbour relation, resolved in parallel rounds
+//                   (a hypothesis is a seed once all earlier neighbours are known non-seeds);
+//                   then cluster sizes, the exact exchange sort (warp_exchange_sort), the
+//                   cut-off walk, and one warp per emitted cluster for the (distance,index)
+//                   ordered float32 averaging.
+#include "fccf_dev.cuh"
+#include "fccf_internal.h"
+
+namespace fccf {
+
+struct ClArgs {
+  PipeState* st;
+  const float* hyp_qt; float* hyp_ax;
+  u64* keys; const u32* order;     // order: sorted position -> global hypothesis index
+  float* xs;                        // x in sorted order (global index space)
+  int *state, *size, *seeds, *perm, *key, *members;
+  float* mdist;
+  float* centre;
+  float thr_n, ang_thr, rad, sel_num;
+  int* nbits;                       // device word: key width for the sort
+  int cap_hyp;
+};
+
+__global__ void __launch_bounds__(256) cluster_prep_kernel(const __grid_constant__ ClArgs A) {
+  PipeState* st = A.st;
+  const int n = st->hyp_off[3];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *A.nbits = 34;
+  if (i >= n) return;
+  const float* q = A.hyp_qt + (size_t)i * 8;
+  q4 Q; Q.w = q[0]; Q.x = q[1]; Q.y = q[2]; Q.z = q[3];
+  f3 ax = quat_rotate(Q, mk3(1, 0, 0));
+  float* o = A.hyp_ax + (size_t)i * 4;
+  o[0] = ax.x; o[1] = ax.y; o[2] = ax.z; o[3] = 0.f;
+  int ty = (i >= st->hyp_off[2]) ? 2 : ((i >= st->hyp_off[1]) ? 1 : 0);
+  float x = q[4];
+  u32 k;
+  if (x != x) k = 0xffffffffu;
+  else { u32 b = __float_as_uint(x); k = (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+  A.keys[i] = ((u64)ty << 32) | (u64)k;
+}
+
+__global__ void __launch_bounds__(256) cluster_xs_kernel(const __grid_constant__ ClArgs A) {
+  const int n = A.st->hyp_off[3];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float x = A.hyp_qt[(size_t)A.order[k] * 8 + 4];
+  A.xs[k] = (x != x) ? CUDART_INF_F : x;
+}
+
+__device__ __forceinline__ bool cl_neigh(const float* qi, const float* ai, const float* qj, const float* aj, float r2, float ang_thr, float* dist) {
+  float d0 = qi[4] - qj[4], d1 = qi[5] - qj[5], d2 = qi[6] - qj[6];
+  float d = 0.f; d += d0 * d0; d += d1 * d1; d += d2 * d2;    // flann::L2_Simple
+  if (!(d < r2)) return false;
+  float a = normal_angle(ai[0], ai[1], ai[2], aj[0], aj[1], aj[2]);
+  if (dist) *dist = d;
+  return a < ang_thr;
+}
+__device__ __forceinline__ void cl_window(const float* xs, int n, float x, double rr, int& lo, int& hi) {
+  if (!isfinite(x)) { lo = 0; hi = 0; return; }   // a non-finite translation has no neighbour (d is NaN/inf)
+  double a = (double)x - rr, b = (double)x + rr;
+  int l = 0, h = n;
+  while (l < h) { int m = (l + h) >> 1; if ((double)xs[m] < a) l = m + 1; else h = m; }
+  lo = l; h = n;
+  while (l < h) { int m = (l + h) >> 1; if ((double)xs[m] <= b) l = m + 1; else h = m; }
+  hi = l;
+}
+
+#define CL_WSCR 128   // per-warp member scratch (clusters up to this size are averaged by one warp)
+
+// ordered float32 averaging of one cluster whose members (local indices) are sorted by (dist, index)
+__device__ void cl_emit_centre(const float* qt, const int* mem, int m, float* out, int lane) {
+  float acc = 0.f;
+  if (lane < 9) {
+    for (int k = 0; k < m; k++) {
+      const float* q = qt + (size_t)mem[k] * 8;
+      float v;
+      if (lane < 3) v = q[4 + lane];
+      else {
+        q4 Q; Q.w = q[0]; Q.x = q[1]; Q.y = q[2]; Q.z = q[3];
+        f3 r = quat_rotate(Q, lane < 6 ? mk3(1, 0, 0) : mk3(0, 1, 0));
+        v = get(r, (lane - 3) % 3);
+      }
+      acc = acc + v;
+    }
+    acc = acc / (float)m;
+  }
+  float s[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) s[k] = __shfl_sync(0xffffffffu, acc, k);
+  if (lane == 0) {
+    f3 a1 = mk3(s[3], s[4], s[5]), a2 = mk3(s[6], s[7], s[8]);
+    normalize(a1); normalize(a2);
+    m3 R = rotation_from_axes(a1, a2);
+    q4 q = quat_from_matrix(R);
+    out[0] = q.w; out[1] = q.x; out[2] = q.y; out[3] = q.z; out[4] = s[0]; out[5] = s[1]; out[6] = s[2]; out[7] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ ClArgs A) {
+  PipeState* st = A.st;
+  const int ty = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n = st->n_hyp[ty], base = st->hyp_off[ty], tnum = st->hyp_off[3];
+  const float* qt = A.hyp_qt + (size_t)base * 8;
+  const float* ax = A.hyp_ax + (size_t)base * 4;
+  float* centre = A.centre + (size_t)ty * FCCF_MAXCENTRE * 8;
+  __shared__ int s_flag, s_K, s_E;
+  __shared__ int s_emit[FCCF_MAXCENTRE];
+  __shared__ int s_mem[32][CL_WSCR];
+  __shared__ float s_md[32][CL_WSCR];
+  // cluster_num (FCCF.cpp:1465): int(200.0f * size / total); NaN (0/0) casts to INT_MIN on x86
+  float cnf = A.sel_num * (float)n / (float)tnum;
+  int cluster_num = (cnf == cnf) ? (int)cnf : (int)0x80000000;
+  if (t == 0) st->cluster_num[ty] = cluster_num;
+  if ((float)n <= A.thr_n) {   // FCCF.cpp:1043-1063
+    if (n == 0) {
+      if (t == 0) { centre[0] = 1.f; for (int k = 1; k < 8; k++) centre[k] = 0.f; st->n_centre[ty] = 1; st->n_seeds[ty] = 0; }
+    } else {
+      for (int k = t; k < n * 8; k += 1024) centre[k] = qt[k];
+      if (t == 0) { st->n_centre[ty] = n; st->n_seeds[ty] = 0; }
+    }
+    return;
+  }
+  const float* xs = A.xs + base;
+  const u32* order = A.order + base;   // values are global indices; local = value - base
+  int* state = A.state + base; int* size = A.size + base; int* seeds = A.seeds + base; int* perm = A.perm + base; int* key = A.key + base;
+  const double rad = (double)A.rad;
+  const float r2 = (float)(rad * rad);
+  const double rr = rad * 1.0001 + 1e-6;
+  for (int i = t; i < n; i += 1024) state[i] = (i == n - 1) ? 2 : 0;
+  __syncthreads();
+  // ---- greedy seeding as parallel rounds ----
+  while (true) {
+    if (t == 0) s_flag = 0;
+    __syncthreads();
+    for (int i = t; i < n; i += 1024) {
+      if (((volatile int*)state)[i] != 0) continue;
+      int lo, hi; cl_window(xs, n, qt[(size_t)i * 8 + 4], rr, lo, hi);
+      bool found_seed = false, all_dec = true;
+      for (int k = lo; k < hi; k++) {
+        int j = (int)order[k] - base;
+        if (j >= i) continue;
+        int sj = ((volatile int*)state)[j];
+        if (sj == 2) continue;
+        if (cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, qt + (size_t)j * 8, ax + (size_t)j * 4, r2, A.ang_thr, nullptr)) {
+          if (sj == 1) { found_seed = true; break; }
+          all_dec = false;
+        }
+      }
+      if (found_seed) state[i] = 2;
+      else if (all_dec) state[i] = 1;
+      else s_flag = 1;
+    }
+    __syncthreads();
+    if (!s_flag) break;
+    __syncthreads();
+  }
+  // ---- seeds in index order + cluster sizes ----
+  if (t == 0) s_K = 0;
+  __syncthreads();
+  {
+    __shared__ int s_w[32];
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+      int i = i0 + t;
+      bool is = (i < n) && state[i] == 1;
+      unsigned b = __ballot_sync(0xffffffffu, is);
+      if (lane == 0) s_w[warp] = __popc(b);
+      __syncthreads();
+      int off = s_K;
+      for (int w2 = 0; w2 < warp; w2++) off += s_w[w2];
+      if (is) seeds[off + __popc(b & ((1u << lane) - 1u))] = i;
+      __syncthreads();
+      if (t == 0) { int tot = 0; for (int w2 = 0; w2 < 32; w2++) tot += s_w[w2]; s_K += tot; }
+      __syncthreads();
+    }
+  }
+  const int K = s_K;
+  if (t == 0) st->n_seeds[ty] = K;
+  for (int k = t; k < K; k += 1024) {
+    int i = seeds[k];
+    int lo, hi; cl_window(xs, n, qt[(size_t)i * 8 + 4], rr, lo, hi);
+    int cnt = 0;
+    for (int kk = lo; kk < hi; kk++) {
+      int j = (int)order[kk] - base;
+      if (cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, qt + (size_t)j * 8, ax + (size_t)j * 4, r2, A.ang_thr, nullptr)) cnt++;
+    }
+    size[k] = cnt; key[k] = cnt; perm[k] = k;
+  }
+  __syncthreads();
+  // ---- range_cluster: exchange sort by size ----
+  if (t < 32) warp_exchange_sort(key, perm, K, [](int a, int b) { return a < b; });
+  __syncthreads();
+  // ---- adaptive cut-off walk (FCCF.cpp:1123-1229) ----
+  if (t == 0) {
+    int clusternum = key[0];
+    int emitted = 0;
+    for (int ci = 0; ci < K; ci++) {
+      if (key[ci] >= clusternum) {
+        if (emitted >= FCCF_MAXCENTRE) { atomicOr(&st->status, ST_CENTRE_OVERFLOW); break; }
+        s_emit[emitted++] = perm[ci];
+        if (cluster_num >= 0 && emitted > cluster_num) break;
+      } else {
+        if ((double)emitted < (cluster_num / 2.0)) { clusternum--; if (clusternum < 2) break; }
+        else break;   // stop = true: nothing further is emitted
+      }
+    }
+    s_E = emitted;
+    st->n_centre[ty] = emitted;
+  }
+  __syncthreads();
+  const int E = s_E;
+  // ---- centres: small clusters by one warp each ----
+  for (int e = warp; e < E; e += 32) {
+    int k = s_emit[e]; int i = seeds[k]; int m = size[k];
+    if (m > CL_WSCR || m == 0) continue;
+    int lo, hi; cl_window(xs, n, qt[(size_t)i * 8 + 4], rr, lo, hi);
+    int cntw = 0;
+    for (int k0 = lo; k0 < hi; k0 += 32) {
+      int kk = k0 + lane; bool ok = false; float d = 0.f; int j = -1;
+      if (kk < hi) { j = (int)order[kk] - base; ok = cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, qt + (size_t)j * 8, ax + (size_t)j * 4, r2, A.ang_thr, &d); }
+      unsigned b = __ballot_sync(0xffffffffu, ok);
+      if (ok) { int p = cntw + __popc(b & ((1u << lane) - 1u)); s_mem[warp][p] = j; s_md[warp][p] = d; }
+      cntw += __popc(b);
+    }
+    __syncwarp();
+    // rank sort by (dist, index)
+    int myj[CL_WSCR / 32]; int myr[CL_WSCR / 32];
+#pragma unroll
+    for (int u = 0; u < CL_WSCR / 32; u++) {
+      int p = u * 32 + lane; myj[u] = -1; myr[u] = 0;
+      if (p < m) {
+        float d = s_md[warp][p]; int j = s_mem[warp][p]; int r = 0;
+        for (int o = 0; o < m; o++) { float d2 = s_md[warp][o]; int j2 = s_mem[warp][o]; if (d2 < d || (d2 == d && j2 < j)) r++; }
+        myj[u] = j; myr[u] = r;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < CL_WSCR / 32; u++) if (myj[u] >= 0) s_mem[warp][myr[u]] = myj[u];
+    __syncwarp();
+    cl_emit_centre(qt, s_mem[warp], m, centre + (size_t)e * 8, lane);
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- big clusters: whole block gathers into global scratch, rank sort, warp 0 averages ----
+  int* gmem = A.members + base; float* gmd = A.mdist + base;
+  int* gsorted = A.members + A.cap_hyp + base;   // second half of the member scratch
+  __shared__ int s_cnt, s_w2[32];
+  for (int e = 0; e < E; e++) {
+    int k = s_emit[e]; int i = seeds[k]; int m = size[k];
+    if (m == 0) { if (t == 0) { float* o = centre + (size_t)e * 8; float nanv = CUDART_NAN_F; for (int u = 0; u < 8; u++) o[u] = nanv; } continue; }
+    if (m <= CL_WSCR) continue;
+    int lo, hi; cl_window(xs, n, qt[(size_t)i * 8 + 4], rr, lo, hi);
+    if (t == 0) s_cnt = 0;
+    __syncthreads();
+    for (int k0 = lo; k0 < hi; k0 += 1024) {
+      int kk = k0 + t; bool ok = false; float d = 0.f; int j = -1;
+      if (kk < hi) { j = (int)order[kk] - base; ok = cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, qt + (size_t)j * 8, ax + (size_t)j * 4, r2, A.ang_thr, &d); }
+      unsigned b = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) s_w2[warp] = __popc(b);
+      __syncthreads();
+      int off = s_cnt;
+      for (int w2 = 0; w2 < warp; w2++) off += s_w2[w2];
+      if (ok) { int p = off + __popc(b & ((1u << lane) - 1u)); gmem[p] = j; gmd[p] = d; }
+      __syncthreads();
+      if (t == 0) { int tot = 0; for (int w2 = 0; w2 < 32; w2++) tot += s_w2[w2]; s_cnt += tot; }
+      __syncthreads();
+    }
+    for (int p = t; p < m; p += 1024) {
+      float d = gmd[p]; int j = gmem[p]; int r = 0;
+      for (int o = 0; o < m; o++) { float d2 = gmd[o]; int j2 = gmem[o]; if (d2 < d || (d2 == d && j2 < j)) r++; }
+      gsorted[r] = j;
+    }
+    __syncthreads();
+    if (warp == 0) cl_emit_centre(qt, gsorted, m, centre + (size_t)e * 8, lane);
+    __syncthreads();
+  }
+}
+
+void launch_cluster(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
+  ClArgs A;
+  PipeState* st = w.st;
+  A.st = st; A.hyp_qt = h.hyp_qt; A.hyp_ax = h.hyp_ax; A.keys = h.ckeyA; A.order = h.cidxA; A.xs = (float*)h.c_mdist + h.cap_hyp;
+  A.state = h.c_state; A.size = h.c_size; A.seeds = h.c_seeds; A.perm = h.c_perm; A.key = h.c_key; A.members = h.c_members; A.mdist = h.c_mdist;
+  A.centre = h.centre;
+  A.thr_n = w.p.cluster_number_threshold; A.ang_thr = w.p.cluster_angel_threshold; A.rad = w.p.cluster_distance_threshold; A.sel_num = w.p.seclct_cluster_number;
+  A.nbits = &st->tickets[20]; A.cap_hyp = h.cap_hyp;
+  int cap = h.cap_hyp;
+  cluster_prep_kernel<<<(cap + 255) / 256, 256, 0, s>>>(A);
+  if (launches) *launches += 1;
+  SortJobs ab, ba;
+  SortJob j; j.kin = h.ckeyA; j.kout = h.ckeyB; j.vin = h.cidxA; j.vout = h.cidxB; j.n = &st->hyp_off[3]; j.nbits = &st->tickets[20]; j.hist = h.chist; j.ticket = &st->tickets[21];
+  ab.j[0] = j;
+  SortJob k = j; k.kin = h.ckeyB; k.kout = h.ckeyA; k.vin = h.cidxB; k.vout = h.cidxA; ba.j[0] = k;
+  // 34-bit keys: 6 passes of 6 bits (even pass count: result back in ckeyA / cidxA)
+  launch_sort(s, ab, ba, 1, cap, 6, launches);
+  cluster_xs_kernel<<<(cap + 255) / 256, 256, 0, s>>>(A);
+  cluster_kernel<<<3, 1024, 0, s>>>(A);
+  if (launches) *launches += 2;
+}
+
+}  // namespace fccf

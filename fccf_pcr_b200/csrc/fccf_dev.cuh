@@ -1,0 +1,207 @@
+// fccf_dev.cuh — device-side arithmetic shared by the kernels.
+//
+// Everything here is compiled with -fmad=false: the reference is built for baseline x86-64
+// (CMakeLists.txt:5-10: -O3, no -march=native), i.e. IEEE single/double without FMA contraction,
+// and the parity contract (BASELINE.json) is bit-exact decisions against that arithmetic.
+// Evaluation orders follow Eigen 3.3's fixed-size kernels (3-term reductions are a0 + (a1 + a2))
+// and PCL 1.10's SSE transform helper (x*c0 + (y*c1 + (z*c2 + c3))).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace fccf {
+
+struct f3 { float x, y, z; };
+struct d3 { double x, y, z; };
+struct m3 { float m[3][3]; };
+struct q4 { float w, x, y, z; };
+
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ float get(const f3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+__device__ __forceinline__ float sum3(float a, float b, float c) { return a + (b + c); }
+__device__ __forceinline__ double sum3d(double a, double b, double c) { return a + (b + c); }
+__device__ __forceinline__ float dot(const f3& a, const f3& b) { return sum3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ f3 cross(const f3& a, const f3& b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ void normalize(f3& v) {  // Eigen normalize(): only if squaredNorm > 0
+  float z = dot(v, v);
+  if (z > 0.0f) { float n = sqrtf(z); v.x = v.x / n; v.y = v.y / n; v.z = v.z / n; }
+}
+
+// FCCF.cpp:369-377 compute_normal_angel: double dot/norms, quotient rounded to float, acos in
+// double, degrees, rounded to float.
+__device__ __forceinline__ float normal_angle(float x1, float y1, float z1, float x2, float y2, float z2) {
+  double a0 = x1, a1 = y1, a2 = z1, b0 = x2, b1 = y2, b2 = z2;
+  float n1n3 = (float)sum3d(a0 * b0, a1 * b1, a2 * b2);
+  double na = sqrt(sum3d(a0 * a0, a1 * a1, a2 * a2)), nb = sqrt(sum3d(b0 * b0, b1 * b1, b2 * b2));
+  float cos_theta = (float)((double)n1n3 / (na * nb));
+  return (float)(acos((double)cos_theta) * 180 / 3.14159265358979323846);
+}
+// FCCF.cpp:379-389
+__device__ __forceinline__ bool compare_normal(float x1, float y1, float z1, float x2, float y2, float z2, float thr) {
+  float th = normal_angle(x1, y1, z1, x2, y2, z2);
+  return !(th > thr);
+}
+// FCCF.cpp:391-407
+__device__ __forceinline__ bool compare_plane(float nx1, float ny1, float nz1, float cx1, float cy1, float cz1,
+                                              float nx2, float ny2, float nz2, float cx2, float cy2, float cz2, float l, float k) {
+  float dx = cx1 - cx2, dy = cy1 - cy2, dz = cz1 - cz2;
+  float vl = sqrtf(dx * dx + dy * dy + dz * dz);
+  double e0 = (double)(dx / vl), e1 = (double)(dy / vl), e2 = (double)(dz / vl);
+  float n1n3 = (float)fabs(sum3d((double)nx1 * e0, (double)ny1 * e1, (double)nz1 * e2));
+  float n2n3 = (float)fabs(sum3d((double)nx2 * e0, (double)ny2 * e1, (double)nz2 * e2));
+  float thr = l / (k * vl + 1);
+  return (n1n3 < thr && n2n3 < thr);
+}
+
+__device__ __forceinline__ m3 mul33(const m3& a, const m3& b) {
+  m3 r;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) r.m[i][j] = sum3(a.m[i][0] * b.m[0][j], a.m[i][1] * b.m[1][j], a.m[i][2] * b.m[2][j]);
+  return r;
+}
+__device__ __forceinline__ f3 mul3v(const m3& a, const f3& v) {
+  return mk3(sum3(a.m[0][0] * v.x, a.m[0][1] * v.y, a.m[0][2] * v.z), sum3(a.m[1][0] * v.x, a.m[1][1] * v.y, a.m[1][2] * v.z),
+             sum3(a.m[2][0] * v.x, a.m[2][1] * v.y, a.m[2][2] * v.z));
+}
+// cos*I + (1-cos)*r r^T + sin*[r]x   (FCCF.cpp:850-868)
+__device__ __forceinline__ m3 rodrigues(float c, float s, const f3& r) {
+  m3 R;
+  float rv[3] = {r.x, r.y, r.z};
+  float rx[3][3] = {{0.f, -r.z, r.y}, {r.z, 0.f, -r.x}, {-r.y, r.x, 0.f}};
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) R.m[i][j] = (c * ((i == j) ? 1.f : 0.f) + (1 - c) * (rv[i] * rv[j])) + s * rx[i][j];
+  return R;
+}
+// Eigen compute_inverse<Matrix3f>
+__device__ __forceinline__ float cof33(const m3& m, int i, int j) {
+  int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return m.m[i1][j1] * m.m[i2][j2] - m.m[i1][j2] * m.m[i2][j1];
+}
+__device__ __forceinline__ m3 inverse33(const m3& m) {
+  float c0 = cof33(m, 0, 0), c1 = cof33(m, 1, 0), c2 = cof33(m, 2, 0);
+  float det = sum3(c0 * m.m[0][0], c1 * m.m[1][0], c2 * m.m[2][0]);
+  float invdet = 1.0f / det;
+  m3 r;
+  r.m[0][0] = c0 * invdet; r.m[0][1] = c1 * invdet; r.m[0][2] = c2 * invdet;
+  r.m[1][0] = cof33(m, 0, 1) * invdet; r.m[1][1] = cof33(m, 1, 1) * invdet; r.m[1][2] = cof33(m, 2, 1) * invdet;
+  r.m[2][0] = cof33(m, 0, 2) * invdet; r.m[2][1] = cof33(m, 1, 2) * invdet; r.m[2][2] = cof33(m, 2, 2) * invdet;
+  return r;
+}
+// Eigen Quaternionf(Matrix3f)
+__device__ __forceinline__ q4 quat_from_matrix(const m3& mat) {
+  float c[4];
+  float t = sum3(mat.m[0][0], mat.m[1][1], mat.m[2][2]);
+  if (t > 0.0f) {
+    t = sqrtf(t + 1.0f);
+    c[3] = 0.5f * t;
+    t = 0.5f / t;
+    c[0] = (mat.m[2][1] - mat.m[1][2]) * t;
+    c[1] = (mat.m[0][2] - mat.m[2][0]) * t;
+    c[2] = (mat.m[1][0] - mat.m[0][1]) * t;
+  } else {
+    int i = 0;
+    if (mat.m[1][1] > mat.m[0][0]) i = 1;
+    if (mat.m[2][2] > mat.m[i][i]) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrtf(mat.m[i][i] - mat.m[j][j] - mat.m[k][k] + 1.0f);
+    c[i] = 0.5f * t;
+    t = 0.5f / t;
+    c[3] = (mat.m[k][j] - mat.m[j][k]) * t;
+    c[j] = (mat.m[j][i] + mat.m[i][j]) * t;
+    c[k] = (mat.m[k][i] + mat.m[i][k]) * t;
+  }
+  q4 q; q.x = c[0]; q.y = c[1]; q.z = c[2]; q.w = c[3];
+  return q;
+}
+// Eigen toRotationMatrix (no normalisation)
+__device__ __forceinline__ m3 quat_to_matrix(const q4& q) {
+  float tx = 2.f * q.x, ty = 2.f * q.y, tz = 2.f * q.z;
+  float twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  float txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  float tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  m3 r;
+  r.m[0][0] = 1.f - (tyy + tzz); r.m[0][1] = txy - twz; r.m[0][2] = txz + twy;
+  r.m[1][0] = txy + twz; r.m[1][1] = 1.f - (txx + tzz); r.m[1][2] = tyz - twx;
+  r.m[2][0] = txz - twy; r.m[2][1] = tyz + twx; r.m[2][2] = 1.f - (txx + tyy);
+  return r;
+}
+// Eigen _transformVector
+__device__ __forceinline__ f3 quat_rotate(const q4& q, const f3& v) {
+  f3 qv = mk3(q.x, q.y, q.z);
+  f3 uv = cross(qv, v);
+  uv.x += uv.x; uv.y += uv.y; uv.z += uv.z;
+  f3 c2 = cross(qv, uv);
+  return mk3((v.x + q.w * uv.x) + c2.x, (v.y + q.w * uv.y) + c2.y, (v.z + q.w * uv.z) + c2.z);
+}
+// pcl::detail::Transformer<float>::se3 / so3 on a row-major 3x4 (first 12 floats of a 4x4)
+__device__ __forceinline__ f3 tf_se3(const float* T, const f3& p) {
+  return mk3(p.x * T[0] + (p.y * T[1] + (p.z * T[2] + T[3])), p.x * T[4] + (p.y * T[5] + (p.z * T[6] + T[7])),
+             p.x * T[8] + (p.y * T[9] + (p.z * T[10] + T[11])));
+}
+__device__ __forceinline__ f3 tf_so3(const float* T, const f3& n) {
+  return mk3(n.x * T[0] + (n.y * T[1] + n.z * T[2]), n.x * T[4] + (n.y * T[5] + n.z * T[6]), n.x * T[8] + (n.y * T[9] + n.z * T[10]));
+}
+// two-axis rotation construction shared by FCCF.cpp:1148-1196 and 1306-1354
+__device__ __forceinline__ m3 rotation_from_axes(f3 nt1, f3 nt2) {
+  f3 ns1 = mk3(1, 0, 0), ns2 = mk3(0, 1, 0);
+  f3 r1 = cross(ns1, nt1); normalize(r1);
+  float c1 = dot(nt1, ns1);
+  float s1 = dot(nt1, cross(r1, ns1));
+  m3 R1 = rodrigues(c1, s1, r1);
+  ns2 = mul3v(R1, ns2);
+  f3 r2 = nt1;
+  float ns2dnt2 = dot(ns2, nt2), ns2dr2 = dot(ns2, r2), nt2dr2 = dot(nt2, r2);
+  f3 r2cns2 = cross(r2, ns2);
+  float r2cns2dnt2 = dot(r2cns2, nt2);
+  float c2 = (ns2dnt2 - (ns2dr2 * nt2dr2)) / (1 - (ns2dr2 * nt2dr2));
+  float s2 = (r2cns2dnt2) / (1 - (ns2dr2 * nt2dr2));
+  m3 R2 = rodrigues(c2, s2, r2);
+  return mul33(R2, R1);
+}
+
+// ordered-int encoding of finite floats for atomicMin/atomicMax
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : (i ^ 0x7fffffff); }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : (i ^ 0x7fffffff)); }
+
+// Warp-cooperative emulation of the reference's exchange sorts (range_face FCCF.cpp:409-427,
+// range_cluster 1020-1038, score_range 1233-1251):  for i: for j>i: if key[i] < key[j] swap.
+// Pass i moves the first maximum of the suffix to position i and shifts every strict
+// left-to-right record of the suffix to the next record's position.  Called by one full warp;
+// key[]/perm[] live in shared or global memory.  `less(a,b)` is the reference's comparison.
+template <typename K, typename Less>
+__device__ void warp_exchange_sort(K* key, int* perm, int n, Less less) {
+  const unsigned full = 0xffffffffu;
+  int lane = threadIdx.x & 31;
+  for (int i = 0; i + 1 < n; i++) {
+    K cur = key[i]; int curp = perm[i];
+    bool moved = false;
+    for (int base = i + 1; base < n; base += 32) {
+      int j = base + lane;
+      bool in = j < n;
+      K v = in ? key[j] : cur; int vp = in ? perm[j] : 0;
+      // records inside this window, resolved in lane order
+      unsigned todo = __ballot_sync(full, in && less(cur, v));
+      K wcur = cur; int wcurp = curp;
+      while (todo) {
+        int l = __ffs(todo) - 1;
+        K lv = __shfl_sync(full, v, l); int lvp = __shfl_sync(full, vp, l);
+        if (lane == l) { key[j] = wcur; perm[j] = wcurp; }
+        wcur = lv; wcurp = lvp; moved = true;
+        unsigned above = (l == 31) ? 0u : (full << (l + 1));
+        todo = __ballot_sync(full, in && less(wcur, v)) & above;
+      }
+      cur = wcur; curp = wcurp;
+    }
+    if (moved && lane == 0) { key[i] = cur; perm[i] = curp; }
+    __syncwarp();
+  }
+}
+
+}  // namespace fccf

@@ -1,0 +1,173 @@
+// fccf_internal.h — device workspace layout and kernel launchers of libfccf (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/fccf.h"
+
+namespace fccf {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define FCCF_MAXF 16          // planes kept per cloud (FCCF.cpp:141,670: 16)
+#define FCCF_MAXBASE 120      // C(16,2)
+#define FCCF_MAXMATCH (FCCF_MAXBASE * FCCF_MAXBASE)
+#define FCCF_MAXCENTRE 256    // per roughness type
+#define FCCF_TOPK 16          // fine-verified hypotheses per type (reference: 4)
+
+// radix sort tile
+#define RS_T 256
+#define RS_I 8
+#define RS_TILE (RS_T * RS_I)
+
+// status bits written by kernels (checked by the host after the final synchronise)
+enum { ST_OCT_DEPTH = 1, ST_HYP_OVERFLOW = 2, ST_KEYBITS = 4, ST_CENTRE_OVERFLOW = 8, ST_HASH_FULL = 16, ST_CLUSTER_MEMBERS = 32 };
+
+struct VGState {
+  int n_in, n_finite;
+  int mn[3], mx[3];          // ordered-int encoded float bounds
+  int bail;                  // pcl::VoxelGrid int32 overflow bail-out (output = input)
+  int minb[3];
+  long long div[3];
+  long long total;           // number of cells (or n_in when bailing out) = key of non-finite points
+  int nbits;
+  float inv;
+  int n_out;                 // number of output points
+  int pad;
+};
+struct OctState {
+  double mn[3], mx[3];
+  int depth, nbits;
+  int n;                     // points
+  int V, Vp, S, F1;
+  float cc[3];               // whole-cloud centroid (FCCF.cpp:473)
+  int pad;
+};
+struct FaceTable {
+  int F, pad;
+  float plane[FCCF_MAXF][8]; // cx cy cz nx ny nz size nvox
+  double theta[FCCF_MAXF];
+  int id[FCCF_MAXF];         // stage-1 face id
+};
+struct BaseTable {
+  int B;
+  int i[FCCF_MAXBASE], j[FCCF_MAXBASE], type[FCCF_MAXBASE];
+  float angle[FCCF_MAXBASE];
+};
+struct ScoreState {          // fine-verify lattice + hash set-up (device)
+  double mn[3];              // lattice origin: voxel faces lie at mn + k*res (mn = first static point - res)
+  int n1, n2, cap_eff, used;
+};
+struct PipeState {
+  VGState vg[2][2];          // [stage: 0 main(), 1 computer_transform_guess][cloud: 0 = "1" (TAR file), 1 = "2" (SRC file)]
+  OctState oct[2];
+  FaceTable ft[2];
+  BaseTable base[2];
+  int n_match;
+  int n_hyp[3], hyp_off[4];
+  int cluster_num[3];
+  int n_centre[3];
+  int n_seeds[3];
+  int n_top[3];
+  int tickets[64];
+  int status;
+  ScoreState fv;
+  float type_best[3][13];    // per type: best score + 3x4
+  float T_final[16];
+};
+
+struct SortJob {
+  const u64* kin; u64* kout; const u32* vin; u32* vout;   // pass 0 uses the element index as value
+  const int* n; const int* nbits;
+  u32* hist;     // [(nblocks_cap + 1) * 256]
+  int* ticket;
+};
+struct SortJobs { SortJob j[3]; };
+struct SegJob {
+  const u64* keys; const int* n; int* seg_start; int* nseg; u32* blk; int* ticket;
+};
+struct SegJobs { SegJob j[3]; };
+
+// Stable LSD radix sort of (key,value) pairs with a device-side element count and key width;
+// `np` passes of ceil(nbits/np) <= 8 bits.  Result ends in (kout,vout) of the last pass; the
+// launcher ping-pongs between the two buffer sets given in `a` and `b` (np even: result in a).
+void launch_sort(cudaStream_t s, SortJobs jobs_ab, SortJobs jobs_ba, int njobs, int cap, int np, uint64_t* launches);
+// segment heads of a sorted key array: seg_start[0..nseg], nseg
+void launch_segments(cudaStream_t s, SegJobs jobs, int njobs, int cap, uint64_t* launches);
+
+// per-cloud device buffers
+struct CloudWS {
+  int cap;                   // capacity in points
+  const float* raw;          // raw cloud (device)
+  u64 *keyA, *keyB; u32 *idxA, *idxB; u32 *hist, *segblk;
+  float* vg_xyz[2]; long long* vg_cell[2]; int* vg_cnt[2];
+  int* seg_start;
+  int* vox_start;            // V+1
+  float* vox_rec;            // V x 12: cx cy cz nx ny nz curv count flag kx ky kz
+  int* vox_aux;              // V: planar rank / leftover offset
+  float* pvox;               // Vp x 8: cx cy cz nx ny nz size voxel-index
+  float* sub;                // S x 3 leftover cloud
+  int *grow_label, *merge_label, *next, *fhead, *ftail, *fnvox, *falloc, *fperm, *fkey;
+  float* fstat;              // F1 x 16: avg(7) + sums(7)
+  int* face_vox;             // member lists of the selected faces (debug)
+  int* face_off;
+};
+struct Work {
+  CloudWS c[2];
+  PipeState* st;
+  fccf_params p;
+  float leaf;
+};
+
+void launch_init_state(cudaStream_t s, PipeState* st, int n0, int n1, uint64_t* launches);
+// VoxelGrid stage `stage` (0: on raw clouds, 1: on the stage-0 output) for both clouds
+void launch_voxelgrid(cudaStream_t s, const Work& w, int stage, int ncloud, uint64_t* launches);
+// face_extrate for both clouds (input: vg_xyz[1] with st->vg[1][c].n_out points)
+void launch_planes(cudaStream_t s, const Work& w, int ncloud, int src_stage, uint64_t* launches);
+
+// hypotheses / clustering / verification workspace
+struct HypWS {
+  int cap_hyp;
+  int* match_cnt;            // FCCF_MAXMATCH: hypotheses of (b1,b2), 0 if no match
+  int* match_off;            // offset inside its type pool
+  float* hyp_T;              // cap_hyp x 12 (3x4 row-major), pools concatenated: type0, type1, type2
+  float* hyp_qt;             // cap_hyp x 8: qw qx qy qz tx ty tz pad
+  float* hyp_ax;             // cap_hyp x 4: rotated x axis
+  u64 *ckeyA, *ckeyB; u32 *cidxA, *cidxB; u32* chist;
+  int* c_state;              // per hypothesis: seed state
+  int* c_size;               // per hypothesis: cluster size if seed
+  int* c_seeds;              // compacted seed ids (per type region)
+  int* c_perm; int* c_key;
+  int* c_members; float* c_mdist;   // scratch for emitted clusters
+  float* centre;             // 3 x FCCF_MAXCENTRE x 8 (qw qx qy qz tx ty tz pad)
+  float* qv_T;               // 3 x FCCF_MAXCENTRE x 16 refined
+  float* qv_score;           // 3 x FCCF_MAXCENTRE
+  int* qv_npair; int* qv_pairs; int* qv_iters;   // per centre: count, 16 x 2, iterations
+  int* rank_perm;            // 3 x FCCF_MAXCENTRE
+  float* top_T;              // 3 x FCCF_TOPK x 16
+  float* top_s1; float* top_s2; int* top_centre;
+  // fine verify
+  u64* fv_keys; int* fv_s; int* fv_t;   // hash: cap_hash slots; fv_t: [3*FCCF_TOPK][cap_hash] (used when the table exceeds shared memory)
+  int cap_hash;
+};
+void launch_hypotheses(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
+void launch_cluster(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
+void launch_quick_verify(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
+void launch_fine_verify_fuse(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
+
+// stand-alone stage entry points (C-ABI helpers)
+void launch_quick_verify_list(cudaStream_t s, const fccf_params& p, float* d_T16, int n, const float* d_planes1, int f1,
+                              const float* d_planes2, int f2, float* d_score, int* d_npair, int* d_pairs, int* d_iters, uint64_t* launches);
+struct ScoreWS {
+  u64* keys; int* s_cnt; int* t_cnt;   // t_cnt: n_rows x cap_hash global counters (fallback when the table exceeds shared memory)
+  int cap_hash; int t_rows;
+  ScoreState* ss; int* status;
+};
+// lattice + static hash of the static leftover cloud (n1/n2 are device-side counts)
+void launch_score_build(cudaStream_t s, const fccf_params& p, const float* d_s1, const int* d_n1, const int* d_n2, int cap_points, const ScoreWS& ws, uint64_t* launches);
+// scores n_hyp hypotheses (row-major 4x4 each) -> d_scores
+void launch_score_list(cudaStream_t s, const fccf_params& p, const float* d_T16, int n_hyp, const float* d_s2, const ScoreWS& ws, float* d_scores, uint64_t* launches);
+// per-voxel (s,t) rows of one hypothesis: rows of 5 ints, *d_nrows rows
+void launch_score_dump(cudaStream_t s, const fccf_params& p, const float* d_T16, const float* d_s2, const ScoreWS& ws, int* d_rows, int cap_rows, int* d_nrows, uint64_t* launches);
+
+}  // namespace fccf

@@ -1,0 +1,217 @@
+// hypotheses.cu — coplane-pair construction, pair-descriptor matching and closed-form hypothesis
+// generation (FCCF.cpp:429-468 select_base, 1412-1427 match loop, 841-1018 computer_transform,
+// 1439-1462 matrix -> quaternion), as count -> scan -> emit so that every pool keeps the
+// reference's push_back order:
+//   pairs_match   one CTA: base pairs of both clouds (ordered ballot compaction of the 16x16
+//                 upper triangle), the B1 x B2 descriptor test, per-match hypothesis counts, and an
+//                 ordered scan of the counts per roughness type (three 21-bit fields of a u64)
+//   emit_hyp      one thread per matched (pair,pair): recomputes the two-Rodrigues rotation and
+//                 writes its hypotheses (3x4 + quaternion/translation) at their pool offsets
+#include "fccf_dev.cuh"
+#include "fccf_internal.h"
+
+namespace fccf {
+
+struct HypArgs {
+  PipeState* st;
+  int* match_cnt; int* match_off;
+  float* hyp_T; float* hyp_qt;
+  int cap_hyp;
+  float tmin, tmax, rough, same_thr, third_thr, third_ang;
+};
+
+struct Plane { f3 c, n; float size; };
+__device__ __forceinline__ Plane load_plane(const FaceTable& f, int i) {
+  Plane p; p.c = mk3(f.plane[i][0], f.plane[i][1], f.plane[i][2]); p.n = mk3(f.plane[i][3], f.plane[i][4], f.plane[i][5]); p.size = f.plane[i][6];
+  return p;
+}
+
+// FCCF.cpp:841-1018.  EMIT=false: only count the hypotheses this match pushes.
+template <bool EMIT>
+__device__ int hyp_generate(const FaceTable& f1, const FaceTable& f2, int i11, int i12, int i21, int i22,
+                            float third_thr, float third_ang, float* outT, float* outQ) {
+  Plane P11 = load_plane(f1, i11), P12 = load_plane(f1, i12), P21 = load_plane(f2, i21), P22 = load_plane(f2, i22);
+  f3 n1 = P11.n, m1 = P12.n, n2 = P21.n, m2 = P22.n;
+  f3 r1 = cross(n2, n1); normalize(r1);
+  float n2dn1 = dot(n2, n1);
+  f3 r1cn2 = cross(r1, n2);
+  float r1cn2dn1 = dot(r1cn2, n1);
+  m3 R1 = rodrigues(n2dn1, r1cn2dn1, r1);
+  m2 = mul3v(R1, m2);
+  f3 r2 = n1;
+  float m2dm1 = dot(m2, m1), m2dr2 = dot(m2, r2), m1dr2 = dot(m1, r2);
+  f3 r2cm2 = cross(r2, m2);
+  float r2cm2dm1 = dot(r2cm2, m1);
+  float cos2 = (m2dm1 - (m2dr2 * m1dr2)) / (1 - (m2dr2 * m1dr2));
+  float sin2 = (r2cm2dm1) / (1 - (m2dr2 * m1dr2));
+  m3 R2 = rodrigues(cos2, sin2, r2);
+  m3 rot = mul33(R2, R1);
+  float T[12];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { T[4 * i] = rot.m[i][0]; T[4 * i + 1] = rot.m[i][1]; T[4 * i + 2] = rot.m[i][2]; T[4 * i + 3] = 0.f; }
+  q4 q;
+  if (EMIT) q = quat_from_matrix(rot);
+  f3 n1cm1 = cross(n1, m1); normalize(n1cm1);
+  f3 n2cm2 = cross(n2, m2); normalize(n2cm2);
+  int count = 0;
+  const int F1 = f1.F, F2 = f2.F;
+  for (int k3 = 0; k3 < F1; k3++) {
+    if (k3 == i11 || k3 == i12) continue;
+    Plane P13 = load_plane(f1, k3);
+    if (!(fabsf(dot(n1cm1, P13.n)) > third_thr)) continue;
+    for (int k2 = 0; k2 < F2; k2++) {
+      if (k2 == i21 || k2 == i22) continue;
+      Plane P2 = load_plane(f2, k2);
+      f3 cn = tf_so3(T, P2.n);     // transformPointCloudWithNormals (FCCF.cpp:948), translation still 0
+      float a3 = normal_angle(P13.n.x, P13.n.y, P13.n.z, cn.x, cn.y, cn.z);
+      if (a3 < third_ang && fabsf(dot(n2cm2, cn)) > third_thr) {
+        if (EMIT) {
+          f3 c23 = tf_se3(T, P2.c);
+          f3 k1 = P13.n, kk2 = cn;
+          float d11 = dot(P11.c, n1), d12 = dot(P12.c, m1), d13 = dot(P13.c, k1);
+          float d21 = dot(P21.c, n2), d22 = dot(P22.c, m2), d23 = dot(c23, kk2);
+          f3 D = mk3(d11 - d21, d12 - d22, d13 - d23);
+          m3 Am; Am.m[0][0] = n1.x; Am.m[0][1] = n1.y; Am.m[0][2] = n1.z; Am.m[1][0] = m1.x; Am.m[1][1] = m1.y; Am.m[1][2] = m1.z;
+          Am.m[2][0] = k1.x; Am.m[2][1] = k1.y; Am.m[2][2] = k1.z;
+          m3 AT;
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) AT.m[i][j] = Am.m[j][i];
+          f3 Tt = mul3v(mul33(inverse33(mul33(AT, Am)), AT), D);
+          float* o = outT + (size_t)count * 12;
+#pragma unroll
+          for (int i = 0; i < 12; i++) o[i] = T[i];
+          o[3] = Tt.x; o[7] = Tt.y; o[11] = Tt.z;
+          float* oq = outQ + (size_t)count * 8;
+          oq[0] = q.w; oq[1] = q.x; oq[2] = q.y; oq[3] = q.z; oq[4] = Tt.x; oq[5] = Tt.y; oq[6] = Tt.z; oq[7] = 0.f;
+        }
+        count++;
+      }
+    }
+  }
+  if (count == 0) {
+    if (EMIT) {
+      float sa = P11.size, sb = P12.size, sc = P21.size, sd = P22.size;
+      float sx = (P11.c.x * sa + P12.c.x * sb) / (sa + sb);
+      float sy = (P11.c.y * sa + P12.c.y * sb) / (sa + sb);
+      float sz = (P11.c.z * sa + P12.c.z * sb) / (sa + sb);
+      float tx = (P21.c.x * sc + P22.c.x * sd) / (sc + sd);
+      float ty = (P21.c.y * sc + P22.c.y * sd) / (sc + sd);
+      float tz = (P21.c.z * sc + P22.c.z * sd) / (sc + sd);
+      f3 tc = mul3v(rot, mk3(tx, ty, tz));
+#pragma unroll
+      for (int i = 0; i < 12; i++) outT[i] = T[i];
+      outT[3] = sx - tc.x; outT[7] = sy - tc.y; outT[11] = sz - tc.z;
+      outQ[0] = q.w; outQ[1] = q.x; outQ[2] = q.y; outQ[3] = q.z; outQ[4] = outT[3]; outQ[5] = outT[7]; outQ[6] = outT[11]; outQ[7] = 0.f;
+    }
+    count = 1;
+  }
+  return count;
+}
+
+__global__ void __launch_bounds__(1024) pairs_match_kernel(const __grid_constant__ HypArgs A) {
+  PipeState* st = A.st;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ int s_w[32];
+  __shared__ u64 s_w64[32];
+  __shared__ u64 s_carry;
+  // ---- select_base for both clouds (FCCF.cpp:429-468) ----
+  for (int c = 0; c < 2; c++) {
+    const FaceTable& f = st->ft[c];
+    BaseTable& B = st->base[c];
+    const int F = f.F;
+    bool ok = false; float angel = 0.f; int a = t >> 4, b = t & 15;
+    if (t < 256 && a < b && b < F) {
+      angel = normal_angle(f.plane[a][3], f.plane[a][4], f.plane[a][5], f.plane[b][3], f.plane[b][4], f.plane[b][5]);
+      ok = (A.tmin < angel && angel < A.tmax);
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0;
+    for (int w2 = 0; w2 < warp; w2++) off += s_w[w2];
+    if (ok) {
+      int k = off + __popc(bal & ((1u << lane) - 1u));
+      B.i[k] = a; B.j[k] = b; B.angle[k] = angel;
+      double th1 = (double)A.rough, ta = f.theta[a], tb = f.theta[b];
+      int ty = 3;
+      if (ta <= th1 && tb <= th1) ty = 0;
+      else if (ta > th1 && tb > th1) ty = 1;
+      else if (ta <= th1 && tb > th1) ty = 2;
+      else if (ta > th1 && tb <= th1) ty = 2;
+      B.type[k] = ty;
+    }
+    if (t == 0) { int tot = 0; for (int w2 = 0; w2 < 32; w2++) tot += s_w[w2]; B.B = tot; }
+    __syncthreads();
+  }
+  // ---- match loop (FCCF.cpp:1415-1427): counts ----
+  const int B1 = st->base[0].B, B2 = st->base[1].B;
+  const int NM = B1 * B2;
+  for (int idx = t; idx < NM; idx += 1024) {
+    int i1 = idx / B2, i2 = idx - i1 * B2;
+    const BaseTable &b1 = st->base[0], &b2 = st->base[1];
+    int cnt = 0;
+    if (fabsf(b1.angle[i1] - b2.angle[i2]) < A.same_thr && b1.type[i1] == b2.type[i2] && b1.type[i1] < 3)
+      cnt = hyp_generate<false>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_ang, nullptr, nullptr);
+    A.match_cnt[idx] = cnt;
+  }
+  if (t == 0) s_carry = 0;
+  __syncthreads();
+  // ---- ordered scan of the counts per type ----
+  for (int i0 = 0; i0 < NM; i0 += 1024) {
+    int idx = i0 + t;
+    u64 x = 0;
+    if (idx < NM) { int cnt = A.match_cnt[idx]; if (cnt > 0) { int ty = st->base[0].type[idx / B2]; x = (u64)cnt << (21 * ty); } }
+    u64 inc = x;
+    for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+    if (lane == 31) s_w64[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      u64 w = s_w64[lane], wi = w;
+      for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += y; }
+      s_w64[lane] = wi - w;
+    }
+    __syncthreads();
+    u64 excl = s_carry + s_w64[warp] + inc - x;
+    if (idx < NM && x) { int ty = st->base[0].type[idx / B2]; A.match_off[idx] = (int)((excl >> (21 * ty)) & 0x1fffffull); }
+    __syncthreads();
+    if (t == 1023) s_carry = excl + x;
+    __syncthreads();
+  }
+  if (t == 0) {
+    int n0 = (int)(s_carry & 0x1fffffull), n1 = (int)((s_carry >> 21) & 0x1fffffull), n2 = (int)((s_carry >> 42) & 0x1fffffull);
+    if (n0 + n1 + n2 > A.cap_hyp) { atomicOr(&st->status, ST_HYP_OVERFLOW); n0 = n1 = n2 = 0; }
+    st->n_hyp[0] = n0; st->n_hyp[1] = n1; st->n_hyp[2] = n2;
+    st->hyp_off[0] = 0; st->hyp_off[1] = n0; st->hyp_off[2] = n0 + n1; st->hyp_off[3] = n0 + n1 + n2;
+    st->n_match = NM;
+  }
+}
+
+__global__ void __launch_bounds__(128) emit_hyp_kernel(const __grid_constant__ HypArgs A) {
+  PipeState* st = A.st;
+  const int B2 = st->base[1].B;
+  const int NM = st->n_match;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NM) return;
+  if (st->hyp_off[3] == 0) return;
+  int cnt = A.match_cnt[idx];
+  if (cnt <= 0) return;
+  int i1 = idx / B2, i2 = idx - i1 * B2;
+  const BaseTable &b1 = st->base[0], &b2 = st->base[1];
+  int ty = b1.type[i1];
+  size_t off = (size_t)st->hyp_off[ty] + A.match_off[idx];
+  hyp_generate<true>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_ang, A.hyp_T + off * 12, A.hyp_qt + off * 8);
+}
+
+void launch_hypotheses(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
+  HypArgs A;
+  A.st = w.st; A.match_cnt = h.match_cnt; A.match_off = h.match_off; A.hyp_T = h.hyp_T; A.hyp_qt = h.hyp_qt; A.cap_hyp = h.cap_hyp;
+  A.tmin = w.p.included_angle_min_threshold; A.tmax = w.p.included_angle_max_threshold; A.rough = w.p.rough_threshold_gl;
+  A.same_thr = w.p.included_angle_same_threshold; A.third_thr = w.p.third_plane_threshold; A.third_ang = w.p.third_plane_normal_threshold;
+  pairs_match_kernel<<<1, 1024, 0, s>>>(A);
+  emit_hyp_kernel<<<(FCCF_MAXMATCH + 127) / 128, 128, 0, s>>>(A);
+  if (launches) *launches += 2;
+}
+
+}  // namespace fccf

@@ -1,0 +1,370 @@
+// verify.cu — quick_verify (FCCF.cpp:680-783) with the Ceres plane-to-plane refinement
+// (LidarPlaneFactor FCCF.cpp:178-208, ceres_refine 210-249), score_range (1233-1251) and the
+// top-k selection (1499-1544), one WARP per hypothesis.
+//
+// Plane association: lane a < F1 tests source plane a against all target planes (<= 16 x 16).
+// Refinement: Ceres 1.14's trust-region Levenberg-Marquardt restated (DENSE_QR, Jacobi scaling,
+// EigenQuaternionParameterization, <= 50 iterations; App. A.5 of SURVEY.md).  Lane l owns residual
+// row l (pair l/2, residual l%2) and, for l < 6, the l-th damping row of the augmented system
+// [J; sqrt(D)] y = [r; 0]; every "sum over rows" is one xor-butterfly over the warp (all lanes end
+// with the same bits), the Householder QR runs column by column on those register rows.  FP64
+// throughout — this is the FP64-pipe stage of the path.
+#include "fccf_dev.cuh"
+#include "fccf_internal.h"
+
+namespace fccf {
+
+__device__ __forceinline__ double bfly(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void crossd(const double a[3], const double b[3], double o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3d(const double a[3], const double b[3]) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
+
+// f(q,a) = a + w*uv + u x uv, uv = 2 (u x a); Jacobian wrt (x,y,z,w)
+__device__ void rot_with_jac(const double q[4], const double a[3], double f[3], double J[3][4], bool want) {
+  const double* u = q; double w = q[3];
+  double uv[3]; crossd(u, a, uv); uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+  double c2[3]; crossd(u, uv, c2);
+  for (int i = 0; i < 3; i++) f[i] = (a[i] + w * uv[i]) + c2[i];
+  if (!want) return;
+  for (int k = 0; k < 3; k++) {
+    double e[3] = {0, 0, 0}; e[k] = 1.0;
+    double Av[3]; crossd(e, a, Av); Av[0] *= 2; Av[1] *= 2; Av[2] *= 2;
+    double t1[3], t2[3]; crossd(e, uv, t1); crossd(u, Av, t2);
+    for (int i = 0; i < 3; i++) J[i][k] = w * Av[i] + t1[i] + t2[i];
+  }
+  for (int i = 0; i < 3; i++) J[i][3] = uv[i];
+}
+
+struct LmRow { double n1[3], p1[3], n2[3], p2[3], w; bool active; int odd; };
+
+// residual of this lane's row and (optionally) its 6 local Jacobian entries; warp-uniform return
+__device__ bool lm_eval(const LmRow& R, const double x[7], double& r, double J[6], bool want) {
+  bool fin = true;
+  r = 0.0;
+  if (want) for (int c = 0; c < 6; c++) J[c] = 0.0;
+  if (R.active) {
+    const double* q = x; const double* t = x + 4;
+    double n2r[3], p2r[3], Jn[3][4], Jp[3][4];
+    rot_with_jac(q, R.n2, n2r, Jn, want);
+    rot_with_jac(q, R.p2, p2r, Jp, want);
+    for (int i = 0; i < 3; i++) p2r[i] += t[i];
+    double cv[3]; crossd(R.n1, n2r, cv);
+    double nc = sqrt(dot3d(cv, cv));
+    double d = dot3d(R.n1, R.p1) - dot3d(n2r, p2r);
+    double sd = sqrt(d * d);
+    r = R.odd ? R.w * sd : R.w * nc;
+    fin = isfinite(r);
+    if (want) {
+      double Ja[7];
+      for (int col = 0; col < 4; col++) {
+        double dn[3] = {Jn[0][col], Jn[1][col], Jn[2][col]}, dp[3] = {Jp[0][col], Jp[1][col], Jp[2][col]};
+        if (!R.odd) { double dc[3]; crossd(R.n1, dn, dc); Ja[col] = R.w * (dot3d(cv, dc) / nc); }
+        else { double dd = -(dot3d(dn, p2r) + dot3d(n2r, dp)); Ja[col] = R.w * (d * dd / sd); }
+      }
+      for (int col = 0; col < 3; col++) Ja[4 + col] = R.odd ? R.w * (d * (-n2r[col]) / sd) : 0.0;
+      // EigenQuaternionParameterization::ComputeJacobian (4x3)
+      double Pm[4][3] = {{q[3], q[2], -q[1]}, {-q[2], q[3], q[0]}, {q[1], -q[0], q[3]}, {-q[0], -q[1], -q[2]}};
+      for (int lc = 0; lc < 3; lc++) { double s = 0; for (int a = 0; a < 4; a++) s += Ja[a] * Pm[a][lc]; J[lc] = s; }
+      for (int lc = 0; lc < 3; lc++) J[3 + lc] = Ja[4 + lc];
+      for (int lc = 0; lc < 6; lc++) fin = fin && isfinite(J[lc]);
+    }
+  }
+  return __all_sync(0xffffffffu, fin);
+}
+__device__ void lm_plus(const double x[7], const double delta[6], double out[7]) {
+  double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+  if (nd > 0.0) {
+    double s = sin(nd) / nd;
+    double dq[4] = {s * delta[0], s * delta[1], s * delta[2], cos(nd)};
+    const double* b = x;
+    out[3] = dq[3] * b[3] - dq[0] * b[0] - dq[1] * b[1] - dq[2] * b[2];
+    out[0] = dq[3] * b[0] + dq[0] * b[3] + dq[1] * b[2] - dq[2] * b[1];
+    out[1] = dq[3] * b[1] + dq[1] * b[3] + dq[2] * b[0] - dq[0] * b[2];
+    out[2] = dq[3] * b[2] + dq[2] * b[3] + dq[0] * b[1] - dq[1] * b[0];
+  } else { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; }
+  for (int i = 0; i < 3; i++) out[4 + i] = x[4 + i] + delta[3 + i];
+}
+// min || [A; B] y - [b; 0] || by Householder QR.  Lane l holds main row l (A, b) and, for l < 6,
+// augmented row l (B = diag(lmd)).  Returns false on a zero column / non-finite solution.
+__device__ bool lm_qr_solve(double A[6], double b, double B[6], int lane, double y[6]) {
+  double bb = 0.0;   // rhs of the augmented row
+  const bool aug = lane < 6;
+  for (int k = 0; k < 6; k++) {
+    double mk = (lane >= k) ? A[k] : 0.0;
+    double ak = aug ? B[k] : 0.0;
+    double nrm = sqrt(bfly(mk * mk + ak * ak));
+    if (nrm == 0.0) return false;
+    double akk = __shfl_sync(0xffffffffu, A[k], k);
+    double alpha = (akk > 0) ? -nrm : nrm;
+    double v0 = akk - alpha;
+    double vm = (lane == k) ? v0 : mk;     // Householder vector entries of this lane's rows
+    double va = ak;
+    double vtv = bfly(vm * vm + va * va);
+    if (vtv == 0.0) return false;
+    double beta = 2.0 / vtv;
+    for (int j = k + 1; j < 6; j++) {
+      double s = bfly(vm * A[j] + va * (aug ? B[j] : 0.0));
+      s *= beta;
+      A[j] -= s * vm;
+      if (aug) B[j] -= s * va;
+    }
+    {
+      double s = bfly(vm * b + va * bb);
+      s *= beta;
+      b -= s * vm;
+      if (aug) bb -= s * va;
+    }
+    if (lane == k) A[k] = alpha;
+  }
+  bool ok = true;
+  for (int k = 5; k >= 0; k--) {
+    double s = b;
+    for (int j = k + 1; j < 6; j++) s -= A[j] * y[j];
+    s = s / A[k];
+    y[k] = __shfl_sync(0xffffffffu, s, k);
+    ok = ok && isfinite(y[k]);
+  }
+  return ok;
+}
+
+// ceres::Solve for one hypothesis (whole warp).  x = (qx,qy,qz,qw,tx,ty,tz)
+__device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
+  const int max_iter = 50;
+  const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+  const double min_relative_decrease = 1e-3, min_radius = 1e-32, max_radius = 1e16, min_diag = 1e-6, max_diag = 1e32;
+  x[0] = 0; x[1] = 0; x[2] = 0; x[3] = 1; x[4] = 0; x[5] = 0; x[6] = 0;
+  double r, J[6];
+  double radius = 1e4, decrease_factor = 2.0; bool reuse_diag = false;
+  double scale[6], diag[6], g[6];
+  int iter = 0;
+  if (!lm_eval(R, x, r, J, true)) return 0;
+  double cost = 0.5 * bfly(r * r);
+  for (int c = 0; c < 6; c++) g[c] = bfly(J[c] * r);
+  for (int c = 0; c < 6; c++) scale[c] = 1.0 / (1.0 + sqrt(bfly(J[c] * J[c])));
+  for (int c = 0; c < 6; c++) J[c] *= scale[c];
+  double gmax;
+  {
+    double ng[6], xp[7]; for (int c = 0; c < 6; c++) ng[c] = -g[c];
+    lm_plus(x, ng, xp);
+    gmax = 0; for (int i = 0; i < 7; i++) gmax = fmax(gmax, fabs(x[i] - xp[i]));
+  }
+  double x_norm = 0; for (int i = 0; i < 7; i++) x_norm += x[i] * x[i]; x_norm = sqrt(x_norm);
+  int invalid = 0; bool step_successful = true;
+  while (true) {
+    if (iter >= max_iter) break;
+    if (step_successful && gmax <= gradient_tolerance) break;
+    if (radius < min_radius) break;
+    iter++;
+    step_successful = false;
+    if (!reuse_diag) for (int c = 0; c < 6; c++) diag[c] = fmin(fmax(bfly(J[c] * J[c]), min_diag), max_diag);
+    double Aq[6], Bq[6], step[6];
+    for (int c = 0; c < 6; c++) { Aq[c] = J[c]; Bq[c] = (lane == c) ? sqrt(diag[c] / radius) : 0.0; }
+    bool solved = lm_qr_solve(Aq, r, Bq, lane, step);
+    reuse_diag = true;
+    bool valid = false; double model_change = 0;
+    if (solved) {
+      for (int c = 0; c < 6; c++) step[c] = -step[c];
+      double mr = 0; for (int c = 0; c < 6; c++) mr += J[c] * step[c];
+      model_change = -bfly(mr * (r + mr / 2.0));
+      valid = (model_change > 0.0);
+    }
+    if (!valid) {
+      invalid++;
+      if (invalid >= 5) break;
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diag = true;
+      continue;
+    }
+    invalid = 0;
+    double delta[6]; for (int c = 0; c < 6; c++) delta[c] = step[c] * scale[c];
+    double xc[7]; lm_plus(x, delta, xc);
+    double rc, Jd[6];
+    double cand_cost;
+    if (lm_eval(R, xc, rc, Jd, false)) cand_cost = 0.5 * bfly(rc * rc);
+    else cand_cost = 1.7976931348623157e308;
+    double sn = 0; for (int i = 0; i < 7; i++) sn += (x[i] - xc[i]) * (x[i] - xc[i]); sn = sqrt(sn);
+    if (sn <= parameter_tolerance * (x_norm + parameter_tolerance)) break;
+    double cost_change = cost - cand_cost;
+    if (fabs(cost_change) <= function_tolerance * cost) break;
+    double rel = cost_change / model_change;
+    if (rel > min_relative_decrease) {
+      for (int i = 0; i < 7; i++) x[i] = xc[i];
+      x_norm = 0; for (int i = 0; i < 7; i++) x_norm += x[i] * x[i]; x_norm = sqrt(x_norm);
+      cost = cand_cost;
+      if (!lm_eval(R, x, r, J, true)) break;
+      for (int c = 0; c < 6; c++) g[c] = bfly(J[c] * r);
+      for (int c = 0; c < 6; c++) J[c] *= scale[c];
+      {
+        double ng[6], xp[7]; for (int c = 0; c < 6; c++) ng[c] = -g[c];
+        lm_plus(x, ng, xp);
+        gmax = 0; for (int i = 0; i < 7; i++) gmax = fmax(gmax, fabs(x[i] - xp[i]));
+      }
+      step_successful = true;
+      radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+      radius = fmin(max_radius, radius);
+      decrease_factor = 2.0; reuse_diag = false;
+    } else {
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diag = true;
+    }
+  }
+  return iter;
+}
+
+// quick_verify for one hypothesis by one warp.  planes: stride 8 floats (c, n, size, -).
+__device__ float quick_verify_warp(float T[16], const float* pl1, int F1, const float* pl2, int F2, float ang_thr, float dist_thr,
+                                   float required, int lane, int* npair_out, int* pairs_out, int* iters_out) {
+  // integer-truncating size sums (FCCF.cpp:693,707)
+  int fs1 = 0, fs2 = 0;
+  for (int k = 0; k < F1; k++) fs1 = (int)((float)fs1 + pl1[k * 8 + 6]);
+  for (int k = 0; k < F2; k++) fs2 = (int)((float)fs2 + pl2[k * 8 + 6]);
+  bool find = false; int best = 0; float best_imp = 0.f, best_score = 0.f;
+  f3 p1 = mk3(0, 0, 0), n1 = mk3(0, 0, 0);
+  if (lane < F1) {
+    p1 = mk3(pl1[lane * 8], pl1[lane * 8 + 1], pl1[lane * 8 + 2]); n1 = mk3(pl1[lane * 8 + 3], pl1[lane * 8 + 4], pl1[lane * 8 + 5]);
+    float size1 = pl1[lane * 8 + 6];
+    double d1d = sum3d((double)n1.x * (double)p1.x, (double)n1.y * (double)p1.y, (double)n1.z * (double)p1.z);
+    float d1 = (float)d1d;
+    for (int b = 0; b < F2; b++) {
+      f3 p2 = tf_se3(T, mk3(pl2[b * 8], pl2[b * 8 + 1], pl2[b * 8 + 2]));
+      f3 n2 = tf_so3(T, mk3(pl2[b * 8 + 3], pl2[b * 8 + 4], pl2[b * 8 + 5]));
+      float angel = normal_angle(n1.x, n1.y, n1.z, n2.x, n2.y, n2.z);
+      float d2 = (float)sum3d((double)n2.x * (double)p2.x, (double)n2.y * (double)p2.y, (double)n2.z * (double)p2.z);
+      float dist = (float)fabs((double)(d1 - d2));
+      if (angel < ang_thr && dist < dist_thr) {
+        find = true;
+        float size2 = pl2[b * 8 + 6];
+        float mn = size1 < size2 ? size1 : size2, mx = size1 > size2 ? size1 : size2;
+        float cs = mn / mx;
+        float ci = (2 * mn) / (float)(fs1 + fs2);
+        if (cs > best_score) { best_imp = ci; best_score = cs; best = b; }
+      }
+    }
+  }
+  unsigned fm = __ballot_sync(0xffffffffu, find);
+  int np = __popc(fm);
+  // row layout: lane l -> pair l/2
+  int k = lane >> 1;
+  int src = (k < np) ? (int)__fns(fm, 0, k + 1) : 0;
+  f3 bp2 = mk3(0, 0, 0), bn2 = mk3(0, 0, 0);
+  if (find) {
+    bp2 = tf_se3(T, mk3(pl2[best * 8], pl2[best * 8 + 1], pl2[best * 8 + 2]));
+    bn2 = tf_so3(T, mk3(pl2[best * 8 + 3], pl2[best * 8 + 4], pl2[best * 8 + 5]));
+  }
+  LmRow R;
+  R.n1[0] = __shfl_sync(0xffffffffu, n1.x, src); R.n1[1] = __shfl_sync(0xffffffffu, n1.y, src); R.n1[2] = __shfl_sync(0xffffffffu, n1.z, src);
+  R.p1[0] = __shfl_sync(0xffffffffu, p1.x, src); R.p1[1] = __shfl_sync(0xffffffffu, p1.y, src); R.p1[2] = __shfl_sync(0xffffffffu, p1.z, src);
+  R.n2[0] = __shfl_sync(0xffffffffu, bn2.x, src); R.n2[1] = __shfl_sync(0xffffffffu, bn2.y, src); R.n2[2] = __shfl_sync(0xffffffffu, bn2.z, src);
+  R.p2[0] = __shfl_sync(0xffffffffu, bp2.x, src); R.p2[1] = __shfl_sync(0xffffffffu, bp2.y, src); R.p2[2] = __shfl_sync(0xffffffffu, bp2.z, src);
+  float wimp = __shfl_sync(0xffffffffu, best_imp, src);
+  int bsel = __shfl_sync(0xffffffffu, best, src);
+  R.w = (double)wimp; R.active = (k < np); R.odd = lane & 1;
+  if (pairs_out && R.active && !(lane & 1)) { pairs_out[2 * k] = src; pairs_out[2 * k + 1] = bsel; }
+  if (npair_out && lane == 0) *npair_out = np;
+  int iters = -1;
+  if ((float)np >= required) {
+    double x[7];
+    iters = lm_refine_warp(R, lane, x);
+    q4 q; q.w = (float)x[3]; q.x = (float)x[0]; q.y = (float)x[1]; q.z = (float)x[2];   // FCCF.cpp:231-236
+    m3 Rm = quat_to_matrix(q);
+    float N[16] = {Rm.m[0][0], Rm.m[0][1], Rm.m[0][2], (float)x[4], Rm.m[1][0], Rm.m[1][1], Rm.m[1][2], (float)x[5],
+                   Rm.m[2][0], Rm.m[2][1], Rm.m[2][2], (float)x[6], 0.f, 0.f, 0.f, 1.f};
+    float O[16];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {   // Eigen 4x4 packet product: sequential k
+      float s = N[4 * i] * T[j];
+      s = N[4 * i + 1] * T[4 + j] + s;
+      s = N[4 * i + 2] * T[8 + j] + s;
+      s = N[4 * i + 3] * T[12 + j] + s;
+      O[4 * i + j] = s;
+    }
+    for (int i = 0; i < 16; i++) T[i] = O[i];
+  }
+  if (iters_out && lane == 0) *iters_out = iters;
+  float score = 0.f;
+  for (int kk = 0; kk < np; kk++) score = score + __shfl_sync(0xffffffffu, wimp, 2 * kk);
+  return score;
+}
+
+struct QvArgs {
+  PipeState* st;
+  const float* centre; float* qv_T; float* qv_score; int* qv_npair; int* qv_pairs; int* qv_iters;
+  int* rank_perm; float* top_T; float* top_s1; int* top_centre;
+  float ang_thr, dist_thr, required, fine_number;
+};
+
+__global__ void __launch_bounds__(128) quick_verify_kernel(const __grid_constant__ QvArgs A) {
+  PipeState* st = A.st;
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int ty = wid / FCCF_MAXCENTRE, ci = wid - ty * FCCF_MAXCENTRE;
+  if (ty >= 3 || ci >= st->n_centre[ty]) return;
+  const float* c = A.centre + (size_t)wid * 8;
+  q4 q; q.w = c[0]; q.x = c[1]; q.y = c[2]; q.z = c[3];
+  m3 Rm = quat_to_matrix(q);   // FCCF.cpp:1470-1489
+  float T[16] = {Rm.m[0][0], Rm.m[0][1], Rm.m[0][2], c[4], Rm.m[1][0], Rm.m[1][1], Rm.m[1][2], c[5], Rm.m[2][0], Rm.m[2][1], Rm.m[2][2], c[6], 0.f, 0.f, 0.f, 1.f};
+  float s = quick_verify_warp(T, &st->ft[0].plane[0][0], st->ft[0].F, &st->ft[1].plane[0][0], st->ft[1].F, A.ang_thr, A.dist_thr, A.required, lane,
+                              A.qv_npair + wid, A.qv_pairs + (size_t)wid * 32, A.qv_iters + wid);
+  if (lane < 16) A.qv_T[(size_t)wid * 16 + lane] = T[lane];
+  if (lane == 0) A.qv_score[wid] = s;
+}
+
+// score_range + top-k (FCCF.cpp:1494-1544): one warp per type
+__global__ void __launch_bounds__(96) rank_top_kernel(const __grid_constant__ QvArgs A) {
+  PipeState* st = A.st;
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ float s_key[3][FCCF_MAXCENTRE];
+  __shared__ int s_perm[3][FCCF_MAXCENTRE];
+  const int C = st->n_centre[ty];
+  for (int k = lane; k < C; k += 32) { s_key[ty][k] = A.qv_score[ty * FCCF_MAXCENTRE + k]; s_perm[ty][k] = k; }
+  __syncwarp();
+  warp_exchange_sort(s_key[ty], s_perm[ty], C, [](float a, float b) { return a < b; });
+  __syncwarp();
+  int amax = (int)A.fine_number;
+  if (amax > FCCF_TOPK) amax = FCCF_TOPK;
+  int nt = C < amax ? C : amax;
+  for (int k = lane; k < C; k += 32) A.rank_perm[ty * FCCF_MAXCENTRE + k] = s_perm[ty][k];
+  for (int k = 0; k < nt; k++) {
+    int ci = s_perm[ty][k];
+    if (lane < 16) A.top_T[((size_t)ty * FCCF_TOPK + k) * 16 + lane] = A.qv_T[((size_t)ty * FCCF_MAXCENTRE + ci) * 16 + lane];
+    if (lane == 0) { A.top_s1[ty * FCCF_TOPK + k] = s_key[ty][k]; A.top_centre[ty * FCCF_TOPK + k] = ci; }
+  }
+  if (lane == 0) st->n_top[ty] = nt;
+}
+
+void launch_quick_verify(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
+  QvArgs A;
+  A.st = w.st; A.centre = h.centre; A.qv_T = h.qv_T; A.qv_score = h.qv_score; A.qv_npair = h.qv_npair; A.qv_pairs = h.qv_pairs; A.qv_iters = h.qv_iters;
+  A.rank_perm = h.rank_perm; A.top_T = h.top_T; A.top_s1 = h.top_s1; A.top_centre = h.top_centre;
+  A.ang_thr = w.p.quick_verify_angel_threshold; A.dist_thr = w.p.quick_verify_distance_threshold; A.required = w.p.required_optimize_plane; A.fine_number = w.p.fine_verify_number;
+  quick_verify_kernel<<<(3 * FCCF_MAXCENTRE + 3) / 4, 128, 0, s>>>(A);
+  rank_top_kernel<<<1, 96, 0, s>>>(A);
+  if (launches) *launches += 2;
+}
+
+// stand-alone: n hypotheses (row-major 4x4, updated in place) against two plane tables (F x 8)
+struct QvListArgs { float* T; int n; const float* pl1; int f1; const float* pl2; int f2; float* score; int* npair; int* pairs; int* iters; float ang_thr, dist_thr, required; };
+__global__ void __launch_bounds__(128) quick_verify_list_kernel(const __grid_constant__ QvListArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (wid >= A.n) return;
+  float T[16];
+  for (int i = 0; i < 16; i++) T[i] = A.T[(size_t)wid * 16 + i];
+  float s = quick_verify_warp(T, A.pl1, A.f1, A.pl2, A.f2, A.ang_thr, A.dist_thr, A.required, lane, A.npair ? A.npair + wid : nullptr,
+                              A.pairs ? A.pairs + (size_t)wid * 32 : nullptr, A.iters ? A.iters + wid : nullptr);
+  if (lane < 16) A.T[(size_t)wid * 16 + lane] = T[lane];
+  if (lane == 0) A.score[wid] = s;
+}
+void launch_quick_verify_list(cudaStream_t s, const fccf_params& p, float* d_T16, int n, const float* d_planes1, int f1,
+                              const float* d_planes2, int f2, float* d_score, int* d_npair, int* d_pairs, int* d_iters, uint64_t* launches) {
+  QvListArgs A;
+  A.T = d_T16; A.n = n; A.pl1 = d_planes1; A.f1 = f1; A.pl2 = d_planes2; A.f2 = f2; A.score = d_score; A.npair = d_npair; A.pairs = d_pairs; A.iters = d_iters;
+  A.ang_thr = p.quick_verify_angel_threshold; A.dist_thr = p.quick_verify_distance_threshold; A.required = p.required_optimize_plane;
+  if (n <= 0) return;
+  quick_verify_list_kernel<<<(n + 3) / 4, 128, 0, s>>>(A);
+  if (launches) *launches += 1;
+}
+
+}  // namespace fccf

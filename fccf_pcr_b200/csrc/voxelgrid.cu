@@ -1,0 +1,202 @@
+// voxelgrid.cu — pcl::VoxelGrid<PointXYZ>::filter as called at FCCF.cpp:1668-1678 (main) and
+// FCCF.cpp:1377-1387 (computer_transform_guess), restated for the GPU:
+//   vg_minmax   bounding box of the finite points (getMinMax3D) + grid set-up by the last block
+//               (inverse leaf, int32-overflow bail-out, min_b/div_b, key width)
+//   vg_keys     one 64-bit cell key per point: ijk = (int)(floor(p*inv) - (float)min_b),
+//               key = ix + dx*(iy + dy*iz)  (PCL's idx, widened to 64 bit); bail-out: key = index
+//   radix sort  (sort.cu) by key, stable => ascending original index inside a cell
+//   segments    one segment per occupied cell
+//   vg_centroid per cell, float32 running sum in sorted order then / n (pcl::CentroidPoint)
+// HBM traffic per launch is 12 B/point read (+8 B key write); everything else is key traffic.
+#include "fccf_dev.cuh"
+#include "fccf_internal.h"
+
+namespace fccf {
+
+struct VGArgs {
+  const float* in[2];        // packed xyz
+  const int* n_in[2];        // device-side input count
+  VGState* st[2];
+  u64* keys[2];
+  int* ticket[2];
+  float leaf;
+  int emulate;
+};
+
+__global__ void __launch_bounds__(256) vg_minmax_kernel(const __grid_constant__ VGArgs A) {
+  const int c = blockIdx.y;
+  const int n = *A.n_in[c];
+  const float* p = A.in[c];
+  int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+  int nf = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+      nf++;
+      int ox = f2ord(x), oy = f2ord(y), oz = f2ord(z);
+      mn[0] = min(mn[0], ox); mn[1] = min(mn[1], oy); mn[2] = min(mn[2], oz);
+      mx[0] = max(mx[0], ox); mx[1] = max(mx[1], oy); mx[2] = max(mx[2], oz);
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    nf += __shfl_xor_sync(0xffffffffu, nf, o);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  }
+  VGState* st = A.st[c];
+  if ((threadIdx.x & 31) == 0 && nf > 0) {
+    atomicAdd(&st->n_finite, nf);
+#pragma unroll
+    for (int a = 0; a < 3; a++) { atomicMin(&st->mn[a], mn[a]); atomicMax(&st->mx[a], mx[a]); }
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(A.ticket[c], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  // grid set-up (PCL 1.10 voxel_grid.hpp applyFilter)
+  *A.ticket[c] = 0;
+  st->n_in = n;
+  int nfin = atomicAdd(&st->n_finite, 0);
+  float inv = 1.0f / A.leaf;
+  st->inv = inv;
+  if (nfin == 0) { st->bail = 0; st->total = 0; st->nbits = 1; st->n_finite = 0; return; }
+  float fmn[3], fmx[3];
+  for (int a = 0; a < 3; a++) { fmn[a] = ord2f(atomicAdd(&st->mn[a], 0)); fmx[a] = ord2f(atomicAdd(&st->mx[a], 0)); }
+  long long dx = (long long)((fmx[0] - fmn[0]) * inv) + 1;
+  long long dy = (long long)((fmx[1] - fmn[1]) * inv) + 1;
+  long long dz = (long long)((fmx[2] - fmn[2]) * inv) + 1;
+  int bail = (A.emulate && (dx * dy * dz) > 2147483647LL) ? 1 : 0;
+  st->bail = bail;
+  long long total;
+  if (bail) total = n;
+  else {
+    for (int a = 0; a < 3; a++) {
+      int lo = (int)floorf(fmn[a] * inv), hi = (int)floorf(fmx[a] * inv);
+      st->minb[a] = lo;
+      st->div[a] = (long long)hi - lo + 1;
+    }
+    total = st->div[0] * st->div[1] * st->div[2];
+  }
+  st->total = total;
+  int nbits = 64 - __clzll(total);   // non-finite points get key = total
+  st->nbits = nbits < 1 ? 1 : nbits;
+}
+
+__global__ void __launch_bounds__(256) vg_keys_kernel(const __grid_constant__ VGArgs A) {
+  const int c = blockIdx.y;
+  const VGState* st = A.st[c];
+  const int n = st->n_in;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = A.in[c];
+  float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+  u64 key;
+  if (!(isfinite(x) && isfinite(y) && isfinite(z))) key = (u64)st->total;
+  else if (st->bail) key = (u64)i;
+  else {
+    float inv = st->inv;
+    int i0 = (int)(floorf(x * inv) - (float)st->minb[0]);
+    int i1 = (int)(floorf(y * inv) - (float)st->minb[1]);
+    int i2 = (int)(floorf(z * inv) - (float)st->minb[2]);
+    key = (u64)((long long)i0 + (long long)i1 * st->div[0] + (long long)i2 * st->div[0] * st->div[1]);
+  }
+  A.keys[c][i] = key;
+}
+
+struct VGOut {
+  const float* in[2];
+  const u64* keys[2];
+  const u32* idx[2];
+  const int* seg_start[2];
+  VGState* st[2];
+  float* out[2];
+  long long* cell[2];
+  int* cnt[2];
+};
+
+// one thread per occupied cell: in-order float32 running sum (pcl::CentroidPoint<PointXYZ>)
+__global__ void __launch_bounds__(128) vg_centroid_kernel(const __grid_constant__ VGOut A) {
+  const int c = blockIdx.y;
+  VGState* st = A.st[c];
+  const int nseg = st->n_out;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const int b = A.seg_start[c][s], e = A.seg_start[c][s + 1];
+  const float* p = A.in[c];
+  const u32* idx = A.idx[c];
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int k = b; k < e; k++) {
+    u32 i = idx[k];
+    sx += p[3 * i]; sy += p[3 * i + 1]; sz += p[3 * i + 2];
+  }
+  float fn = (float)(e - b);
+  A.out[c][3 * s] = sx / fn; A.out[c][3 * s + 1] = sy / fn; A.out[c][3 * s + 2] = sz / fn;
+  A.cell[c][s] = (long long)A.keys[c][b];
+  A.cnt[c][s] = e - b;
+}
+
+__global__ void init_state_kernel(PipeState* st, int n0, int n1) {
+  int t = threadIdx.x;
+  if (t == 0) {
+    for (int s = 0; s < 2; s++) for (int c = 0; c < 2; c++) {
+      VGState& v = st->vg[s][c];
+      v.n_in = 0; v.n_finite = 0; v.n_out = 0; v.bail = 0; v.total = 0; v.nbits = 1;
+      for (int a = 0; a < 3; a++) { v.mn[a] = 0x7fffffff; v.mx[a] = (int)0x80000000; v.minb[a] = 0; v.div[a] = 1; }
+    }
+    st->vg[0][0].n_in = n0; st->vg[0][1].n_in = n1;
+    st->status = 0;
+    st->n_match = 0;
+    for (int i = 0; i < 3; i++) { st->n_hyp[i] = 0; st->n_centre[i] = 0; st->n_top[i] = 0; st->cluster_num[i] = 0; }
+  }
+  if (t < 64) st->tickets[t] = 0;
+}
+
+void launch_init_state(cudaStream_t s, PipeState* st, int n0, int n1, uint64_t* launches) {
+  init_state_kernel<<<1, 64, 0, s>>>(st, n0, n1);
+  if (launches) *launches += 1;
+}
+
+// stage 0: raw -> vg_xyz[0]; stage 1: vg_xyz[0] -> vg_xyz[1]
+void launch_voxelgrid(cudaStream_t s, const Work& w, int stage, int ncloud, uint64_t* launches) {
+  VGArgs A; VGOut O; SortJobs ab, ba; SegJobs sj;
+  int cap = 1;
+  for (int c = 0; c < ncloud; c++) {
+    const CloudWS& cw = w.c[c];
+    PipeState* st = w.st;
+    A.in[c] = (stage == 0) ? cw.raw : cw.vg_xyz[0];
+    A.n_in[c] = (stage == 0) ? &st->vg[0][c].n_in : &st->vg[0][c].n_out;
+    A.st[c] = &st->vg[stage][c];
+    A.keys[c] = cw.keyA;
+    A.ticket[c] = &st->tickets[0 + c];
+    SortJob j; j.kin = cw.keyA; j.kout = cw.keyB; j.vin = cw.idxA; j.vout = cw.idxB; j.n = &st->vg[stage][c].n_in; j.nbits = &st->vg[stage][c].nbits;
+    j.hist = cw.hist; j.ticket = &st->tickets[2 + c];
+    ab.j[c] = j;
+    SortJob k = j; k.kin = cw.keyB; k.kout = cw.keyA; k.vin = cw.idxB; k.vout = cw.idxA;
+    ba.j[c] = k;
+    SegJob g; g.keys = cw.keyA; g.n = &st->vg[stage][c].n_finite; g.seg_start = cw.seg_start; g.nseg = &st->vg[stage][c].n_out; g.blk = cw.segblk; g.ticket = &st->tickets[4 + c];
+    sj.j[c] = g;
+    O.in[c] = A.in[c]; O.keys[c] = cw.keyA; O.idx[c] = cw.idxA; O.seg_start[c] = cw.seg_start; O.st[c] = &st->vg[stage][c];
+    O.out[c] = cw.vg_xyz[stage]; O.cell[c] = cw.vg_cell[stage]; O.cnt[c] = cw.vg_cnt[stage];
+    if (cw.cap > cap) cap = cw.cap;
+  }
+  for (int c = ncloud; c < 2; c++) { A.in[c] = A.in[0]; A.n_in[c] = A.n_in[0]; A.st[c] = A.st[0]; A.keys[c] = A.keys[0]; A.ticket[c] = A.ticket[0]; }
+  A.leaf = w.leaf; A.emulate = w.p.emulate_pcl_overflow;
+  int nb_mm = (cap + 256 * 8 - 1) / (256 * 8);
+  if (nb_mm > 592) nb_mm = 592;
+  if (nb_mm < 1) nb_mm = 1;
+  vg_minmax_kernel<<<dim3(nb_mm, ncloud), 256, 0, s>>>(A);
+  vg_keys_kernel<<<dim3((cap + 255) / 256, ncloud), 256, 0, s>>>(A);
+  if (launches) *launches += 2;
+  launch_sort(s, ab, ba, ncloud, cap, 4, launches);   // result back in keyA / idxA
+  launch_segments(s, sj, ncloud, cap, launches);
+  vg_centroid_kernel<<<dim3((cap + 127) / 128, ncloud), 128, 0, s>>>(O);
+  if (launches) *launches += 1;
+}
+
+}  // namespace fccf

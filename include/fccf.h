@@ -1,0 +1,125 @@
+/* fccf.h — C-ABI of libfccf, the B200-native FCCF-PCR registration path.
+ *
+ * Drop-in boundary for the reference's operator
+ *     void computer_transform_guess(PointCloud<PointXYZ>::Ptr source, Ptr target, Matrix4f& best)
+ * (/root/reference/FCCF.cpp:1370) and for the program around it, main() (FCCF.cpp:1646-1690).
+ * Plain pointers and sizes only; no C++/torch types cross this boundary.  All compute runs in
+ * hand-written sm_100a CUDA kernels; there is no CPU fallback: every entry point fails with a
+ * non-zero status when no CUDA device is usable.
+ *
+ * Ownership: the caller owns every host pointer; a context owns its device memory, stream and
+ * CUDA graph.  Threading: one context per host thread per GPU; a context is not thread-safe.
+ * Errors: int status (0 = ok), text via fccf_last_error().
+ */
+#ifndef FCCF_H_
+#define FCCF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fccf_ctx fccf_ctx;
+
+/* Every file-scope tunable of the reference (FCCF.cpp:126-176) with its default. */
+typedef struct fccf_params {
+  float parameter_l1, parameter_l2, parameter_k1, parameter_k2;      /* FCCF.cpp:126-129 */
+  float normal_vector_threshold1, normal_vector_threshold2;          /* :131-132 */
+  float face_voxel_size;                                              /* :134 */
+  float voxel_point_threshold;                                        /* :136 */
+  float curvature_threshold;                                          /* :138 */
+  float select_plane_number;                                          /* :141 */
+  float quick_verify_angel_threshold, quick_verify_distance_threshold; /* :145-146 */
+  float required_optimize_plane;                                      /* :147 */
+  float fine_verify_voxel_size;                                       /* :150 */
+  float fine_verify_number;                                           /* :151 */
+  float included_angle_same_threshold;                                /* :156 */
+  float included_angle_min_threshold, included_angle_max_threshold;   /* :157-158 */
+  float third_plane_threshold;                                        /* :160 */
+  float third_plane_normal_threshold;                                 /* :162 */
+  float cluster_number_threshold;                                     /* :166 */
+  float cluster_angel_threshold, cluster_distance_threshold;          /* :167-168 */
+  float seclct_cluster_number;                                        /* :171 */
+  float rough_threshold_gl;                                           /* :175 */
+  int emulate_pcl_overflow; /* 1: reproduce pcl::VoxelGrid's int32 bail-out (output = input) */
+  int reserved[3];
+} fccf_params;
+
+typedef struct fccf_timing {
+  float h2d_ms;       /* host->device copies of both raw clouds */
+  float downsample_ms;/* main()'s two VoxelGrid filters, FCCF.cpp:1668-1678 (outside the reference's clock) */
+  float pipeline_ms;  /* computer_transform_guess, the reference's clock() region FCCF.cpp:1682-1684 */
+  float d2h_ms;       /* result read-back */
+  float total_ms;     /* end to end, host pointers in -> matrix out */
+  int n_launches;     /* kernels launched for this registration */
+} fccf_timing;
+
+enum { FCCF_OK = 0, FCCF_ERR_CUDA = 1, FCCF_ERR_ARG = 2, FCCF_ERR_CAPACITY = 3, FCCF_ERR_NO_DEVICE = 4 };
+enum { FCCF_F32 = 0, FCCF_F64 = 1, FCCF_I32 = 2, FCCF_I64 = 3 };
+
+/* replaces: the global initialisers FCCF.cpp:126-176 */
+void fccf_default_params(fccf_params* p);
+
+/* Creates a context on CUDA device `device`.  NULL if there is no usable device (no fallback). */
+fccf_ctx* fccf_create(int device, const fccf_params* params);
+void fccf_destroy(fccf_ctx* ctx);
+const char* fccf_last_error(const fccf_ctx* ctx);
+int fccf_set_params(fccf_ctx* ctx, const fccf_params* params);
+
+/* replaces: main() from the loaded clouds on (FCCF.cpp:1667-1687): VoxelGrid(leaf) on each cloud,
+ * then computer_transform_guess(cloud_tar, cloud_src, T) — note the reference's swapped argument
+ * order (FCCF.cpp:1683).  src = argv[1], tar = argv[2]; xyz are packed float32 triples in host
+ * memory.  T_out: row-major 4x4 mapping src into tar's frame.  timing may be NULL. */
+int fccf_register(fccf_ctx* ctx, const float* src_xyz, size_t n_src, const float* tar_xyz, size_t n_tar,
+                  float leaf, float T_out[16], fccf_timing* timing);
+
+/* Same, with both raw clouds already resident in device memory (device pointers). */
+int fccf_register_device(fccf_ctx* ctx, const float* d_src_xyz, size_t n_src, const float* d_tar_xyz, size_t n_tar,
+                         float leaf, float T_out[16], fccf_timing* timing);
+
+/* Batch of independent pairs (BASELINE config 4): pair b uses src[b]/tar[b]; T_out is B x 16. */
+int fccf_register_batch(fccf_ctx* ctx, int n_pairs, const float* const* src_xyz, const size_t* n_src,
+                        const float* const* tar_xyz, const size_t* n_tar, float leaf, float* T_out, fccf_timing* timing);
+
+/* replaces: pcl::VoxelGrid<PointXYZ>::filter as called at FCCF.cpp:1668-1678 / 1377-1387.
+ * out_xyz: capacity n points; out_cell (int64 linear cell index) / out_cnt may be NULL. */
+int fccf_voxelgrid(fccf_ctx* ctx, const float* xyz, size_t n, float leaf, float* out_xyz, int64_t* out_cell,
+                   int32_t* out_cnt, size_t* n_out);
+
+/* replaces: face_extrate (FCCF.cpp:470-678) on one already-downsampled cloud; results are read
+ * through fccf_debug_blob with the tag "1" (vox_key1, vox_cnt1, vox_plane1, face_plane1, ...). */
+int fccf_extract_planes(fccf_ctx* ctx, const float* xyz, size_t n, int32_t* n_faces);
+
+/* replaces: fine_verify (FCCF.cpp:785-839) for H hypotheses at once ("hypotheses scored"): static
+ * leftover cloud s1, moving leftover cloud s2, T = H row-major 4x4.  scores: H floats.
+ * counts (optional): per hypothesis the per-voxel overlap table is kept on the device and can be
+ * read with fccf_score_counts. */
+int fccf_score_hypotheses(fccf_ctx* ctx, const float* T, size_t n_hyp, const float* s1_xyz, size_t n1,
+                          const float* s2_xyz, size_t n2, float* scores);
+/* Device-resident variant used for throughput measurement: uploads once, then scores `repeat`
+ * times; returns the average kernel milliseconds per launch in *kernel_ms. */
+int fccf_score_hypotheses_bench(fccf_ctx* ctx, const float* T, size_t n_hyp, const float* s1_xyz, size_t n1,
+                                const float* s2_xyz, size_t n2, int repeat, float* scores, float* kernel_ms);
+/* Per-voxel overlap counts of hypothesis `hyp` of the last fccf_score_hypotheses call: rows of
+ * (Lx, Ly, Lz, s, t) for voxels holding both static and moving points; returns rows in *n_rows. */
+int fccf_score_counts(fccf_ctx* ctx, size_t hyp, int32_t* rows, size_t cap_rows, size_t* n_rows);
+
+/* replaces: quick_verify + ceres_refine (FCCF.cpp:680-783, 210-249) for H hypotheses given two plane
+ * tables (F x 7 floats: centroid, normal, point size).  T is updated in place (refined);
+ * scores: H floats; pair_count/pairs (optional): per hypothesis up to 16 (i1,i2) pairs; iters optional. */
+int fccf_quick_verify(fccf_ctx* ctx, float* T, size_t n_hyp, const float* planes1, int f1, const float* planes2, int f2,
+                      float* scores, int32_t* pair_count, int32_t* pairs, int32_t* iters);
+
+/* Stage intermediates of the last fccf_register / fccf_extract_planes call, copied to host memory.
+ * Returns FCCF_ERR_ARG for an unknown name; *bytes = size needed (also when dst is NULL). */
+int fccf_debug_blob(fccf_ctx* ctx, const char* name, void* dst, size_t cap_bytes, size_t* bytes, int* dtype);
+
+/* Number of kernels this library has launched in the context so far. */
+uint64_t fccf_launch_count(const fccf_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCCF_H_ */

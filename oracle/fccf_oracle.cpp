@@ -842,13 +842,25 @@ static void rot_with_jac(const double q[4], const double a[3], double f[3], doub
   }
   for (int i = 0; i < 3; i++) J[i][3] = uv[i];
 }
-// residuals (2 per pair) and, optionally, the local (tangent-space) Jacobian rows (6 columns)
-static bool lm_evaluate(const std::vector<PairFace>& pf, const double x[7], double* r, double* J /* (2n) x 6 row-major or null */) {
+// Row layout used for every reduction below: 32 rows (row l = pair l/2, residual l%2; rows past
+// 2*npairs are zero) plus 6 damping rows of the augmented system held "under" rows 0..5.  Every
+// sum over rows is the xor-butterfly order  v[l] += v[l^16], v[l^8], ... v[l^1]  — Ceres/Eigen's
+// own blocked summation order is unknowable here, so the oracle fixes this one (it is the order a
+// 32-lane warp reduction produces, which lets the CUDA path agree to the last bit of the sums).
+static double bfly32(const double* v) {
+  double a[16];   // lane 0 of the butterfly only needs the halving tree
+  for (int l = 0; l < 16; l++) a[l] = v[l] + v[l + 16];
+  for (int o = 8; o; o >>= 1) for (int l = 0; l < o; l++) a[l] = a[l] + a[l + o];
+  return a[0];
+}
+// residual rows and, optionally, the local (tangent-space) Jacobian rows (6 columns)
+static bool lm_evaluate(const std::vector<PairFace>& pf, const double x[7], double r[32], double (*J)[6]) {
   int n = (int)pf.size();
   const double* q = x; const double* t = x + 4;
   // EigenQuaternionParameterization::ComputeJacobian (4x3 row-major)
   double Pm[4][3] = {{q[3], q[2], -q[1]}, {-q[2], q[3], q[0]}, {q[1], -q[0], q[3]}, {-q[0], -q[1], -q[2]}};
-  for (int k = 0; k < n; k++) {
+  for (int l = 0; l < 32; l++) { r[l] = 0.0; if (J) for (int c = 0; c < 6; c++) J[l][c] = 0.0; }
+  for (int k = 0; k < n && k < 16; k++) {
     double n1[3] = {pf[k].n1.x, pf[k].n1.y, pf[k].n1.z}, n2[3] = {pf[k].n2.x, pf[k].n2.y, pf[k].n2.z};
     double p1[3] = {pf[k].p1.x, pf[k].p1.y, pf[k].p1.z}, p2[3] = {pf[k].p2.x, pf[k].p2.y, pf[k].p2.z};
     double w = (double)pf[k].w;
@@ -872,7 +884,7 @@ static bool lm_evaluate(const std::vector<PairFace>& pf, const double x[7], doub
         Ja1[col] = w * (d * dd / sd);
       }
       for (int col = 0; col < 3; col++) { Ja0[4 + col] = 0.0; Ja1[4 + col] = w * (d * (-n2r[col]) / sd); }
-      double* j0 = J + (size_t)(2 * k) * 6; double* j1 = j0 + 6;
+      double* j0 = J[2 * k]; double* j1 = J[2 * k + 1];
       for (int lc = 0; lc < 3; lc++) {
         double s0 = 0, s1 = 0;
         for (int a = 0; a < 4; a++) { s0 += Ja0[a] * Pm[a][lc]; s1 += Ja1[a] * Pm[a][lc]; }
@@ -897,34 +909,42 @@ static void lm_plus(const double x[7], const double delta[6], double out[7]) {
   } else { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; }
   for (int i = 0; i < 3; i++) out[4 + i] = x[4 + i] + delta[3 + i];
 }
-// least squares min ||A y - b|| by Householder QR, A is m x 6 row-major (destroyed)
-static bool qr_solve6(double* A, double* b, int m, double y[6]) {
-  const int nc = 6;
-  for (int k = 0; k < nc; k++) {
-    double nrm = 0; for (int i = k; i < m; i++) nrm += A[i * nc + k] * A[i * nc + k];
-    nrm = std::sqrt(nrm);
+// min || [A; B] y - [b; 0] || by Householder QR (DENSE_QR).  A: 32 main rows, B: 6 damping rows.
+static bool qr_solve6(double A[32][6], double b[32], double B[6][6], double y[6]) {
+  double bb[6] = {0, 0, 0, 0, 0, 0};
+  double tmp[32];
+  for (int k = 0; k < 6; k++) {
+    double mk[32], ak[32];
+    for (int l = 0; l < 32; l++) { mk[l] = (l >= k) ? A[l][k] : 0.0; ak[l] = (l < 6) ? B[l][k] : 0.0; }
+    for (int l = 0; l < 32; l++) tmp[l] = mk[l] * mk[l] + ak[l] * ak[l];
+    double nrm = std::sqrt(bfly32(tmp));
     if (nrm == 0.0) return false;
-    double alpha = (A[k * nc + k] > 0) ? -nrm : nrm;
-    double v0 = A[k * nc + k] - alpha;
-    // v = (v0, A[k+1..m,k]); beta = 2/(v^T v)
-    double vtv = v0 * v0; for (int i = k + 1; i < m; i++) vtv += A[i * nc + k] * A[i * nc + k];
+    double akk = A[k][k];
+    double alpha = (akk > 0) ? -nrm : nrm;
+    double v0 = akk - alpha;
+    double vm[32];
+    for (int l = 0; l < 32; l++) vm[l] = (l == k) ? v0 : mk[l];
+    for (int l = 0; l < 32; l++) tmp[l] = vm[l] * vm[l] + ak[l] * ak[l];
+    double vtv = bfly32(tmp);
     if (vtv == 0.0) return false;
     double beta = 2.0 / vtv;
-    for (int j = k + 1; j < nc; j++) {
-      double s = v0 * A[k * nc + j]; for (int i = k + 1; i < m; i++) s += A[i * nc + k] * A[i * nc + j];
-      s *= beta;
-      A[k * nc + j] -= s * v0; for (int i = k + 1; i < m; i++) A[i * nc + j] -= s * A[i * nc + k];
+    for (int j = k + 1; j < 6; j++) {
+      for (int l = 0; l < 32; l++) tmp[l] = vm[l] * A[l][j] + ak[l] * ((l < 6) ? B[l][j] : 0.0);
+      double s = bfly32(tmp); s *= beta;
+      for (int l = 0; l < 32; l++) A[l][j] -= s * vm[l];
+      for (int l = 0; l < 6; l++) B[l][j] -= s * ak[l];
     }
     {
-      double s = v0 * b[k]; for (int i = k + 1; i < m; i++) s += A[i * nc + k] * b[i];
-      s *= beta;
-      b[k] -= s * v0; for (int i = k + 1; i < m; i++) b[i] -= s * A[i * nc + k];
+      for (int l = 0; l < 32; l++) tmp[l] = vm[l] * b[l] + ak[l] * ((l < 6) ? bb[l] : 0.0);
+      double s = bfly32(tmp); s *= beta;
+      for (int l = 0; l < 32; l++) b[l] -= s * vm[l];
+      for (int l = 0; l < 6; l++) bb[l] -= s * ak[l];
     }
-    A[k * nc + k] = alpha;
+    A[k][k] = alpha;
   }
-  for (int k = nc - 1; k >= 0; k--) {
-    double s = b[k]; for (int j = k + 1; j < nc; j++) s -= A[k * nc + j] * y[j];
-    y[k] = s / A[k * nc + k];
+  for (int k = 5; k >= 0; k--) {
+    double s = b[k]; for (int j = k + 1; j < 6; j++) s -= A[k][j] * y[j];
+    y[k] = s / A[k][k];
     if (!std::isfinite(y[k])) return false;
   }
   return true;
@@ -934,25 +954,26 @@ static void ceres_refine(M4f& newT, const std::vector<PairFace>& pf, int* iters_
   const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
   const double min_relative_decrease = 1e-3, min_radius = 1e-32, max_radius = 1e16;
   const double min_diag = 1e-6, max_diag = 1e32;
-  int n = (int)pf.size(), m = 2 * n;
   double x[7] = {0, 0, 0, 1, 0, 0, 0};
-  std::vector<double> r(m), J(m * 6), rc(m), A((m + 6) * 6), bb(m + 6), mr(m);
+  double r[32], J[32][6], rc[32], A[32][6], B[6][6], bb[32], tmp[32];
   double radius = 1e4, decrease_factor = 2.0; bool reuse_diag = false;
   double scale[6], diag[6];
   int iter = 0;
-  bool ok = lm_evaluate(pf, x, r.data(), J.data());
+  auto colsum = [&](int c, bool with_r) { for (int l = 0; l < 32; l++) tmp[l] = with_r ? J[l][c] * r[l] : J[l][c] * J[l][c]; return bfly32(tmp); };
+  auto half_sq = [&](const double* v) { for (int l = 0; l < 32; l++) tmp[l] = v[l] * v[l]; return 0.5 * bfly32(tmp); };
+  bool ok = lm_evaluate(pf, x, r, J);
   if (ok) {
-    double cost = 0; for (int i = 0; i < m; i++) cost += r[i] * r[i]; cost *= 0.5;
+    double cost = half_sq(r);
     double g[6];
     auto grad_and_scale = [&](bool first) {
-      for (int c = 0; c < 6; c++) { double s = 0; for (int i = 0; i < m; i++) s += J[i * 6 + c] * r[i]; g[c] = s; }
-      if (first) for (int c = 0; c < 6; c++) { double s = 0; for (int i = 0; i < m; i++) s += J[i * 6 + c] * J[i * 6 + c]; scale[c] = 1.0 / (1.0 + std::sqrt(s)); }
-      for (int i = 0; i < m; i++) for (int c = 0; c < 6; c++) J[i * 6 + c] *= scale[c];
+      for (int c = 0; c < 6; c++) g[c] = colsum(c, true);
+      if (first) for (int c = 0; c < 6; c++) scale[c] = 1.0 / (1.0 + std::sqrt(colsum(c, false)));
+      for (int l = 0; l < 32; l++) for (int c = 0; c < 6; c++) J[l][c] *= scale[c];
     };
     auto grad_max_norm = [&]() {
       double ng[6], xp[7]; for (int c = 0; c < 6; c++) ng[c] = -g[c];
       lm_plus(x, ng, xp);
-      double mxn = 0; for (int i = 0; i < 7; i++) mxn = std::max(mxn, std::fabs(x[i] - xp[i]));
+      double mxn = 0; for (int i = 0; i < 7; i++) mxn = std::fmax(mxn, std::fabs(x[i] - xp[i]));
       return mxn;
     };
     grad_and_scale(true);
@@ -967,21 +988,17 @@ static void ceres_refine(M4f& newT, const std::vector<PairFace>& pf, int* iters_
       iter++;
       step_successful = false;
       // LevenbergMarquardtStrategy::ComputeStep
-      if (!reuse_diag) {
-        for (int c = 0; c < 6; c++) { double s = 0; for (int i = 0; i < m; i++) s += J[i * 6 + c] * J[i * 6 + c]; diag[c] = std::min(std::max(s, min_diag), max_diag); }
-      }
-      double lmd[6]; for (int c = 0; c < 6; c++) lmd[c] = std::sqrt(diag[c] / radius);
-      for (int i = 0; i < m; i++) { for (int c = 0; c < 6; c++) A[i * 6 + c] = J[i * 6 + c]; bb[i] = r[i]; }
-      for (int i = 0; i < 6; i++) { for (int c = 0; c < 6; c++) A[(m + i) * 6 + c] = (i == c) ? lmd[c] : 0.0; bb[m + i] = 0.0; }
+      if (!reuse_diag) for (int c = 0; c < 6; c++) diag[c] = std::fmin(std::fmax(colsum(c, false), min_diag), max_diag);
+      for (int l = 0; l < 32; l++) { for (int c = 0; c < 6; c++) A[l][c] = J[l][c]; bb[l] = r[l]; }
+      for (int i = 0; i < 6; i++) for (int c = 0; c < 6; c++) B[i][c] = (i == c) ? std::sqrt(diag[c] / radius) : 0.0;
       double step[6];
-      bool solved = qr_solve6(A.data(), bb.data(), m + 6, step);
+      bool solved = qr_solve6(A, bb, B, step);
       reuse_diag = true;
       bool valid = false; double model_change = 0;
       if (solved) {
         for (int c = 0; c < 6; c++) step[c] = -step[c];
-        for (int i = 0; i < m; i++) { double s = 0; for (int c = 0; c < 6; c++) s += J[i * 6 + c] * step[c]; mr[i] = s; }
-        double mc = 0; for (int i = 0; i < m; i++) mc += mr[i] * (r[i] + mr[i] / 2.0);
-        model_change = -mc;
+        for (int l = 0; l < 32; l++) { double mr = 0; for (int c = 0; c < 6; c++) mr += J[l][c] * step[c]; tmp[l] = mr * (r[l] + mr / 2.0); }
+        model_change = -bfly32(tmp);
         valid = (model_change > 0.0);
       }
       if (!valid) {
@@ -994,7 +1011,7 @@ static void ceres_refine(M4f& newT, const std::vector<PairFace>& pf, int* iters_
       double delta[6]; for (int c = 0; c < 6; c++) delta[c] = step[c] * scale[c];
       double xc[7]; lm_plus(x, delta, xc);
       double cand_cost;
-      if (lm_evaluate(pf, xc, rc.data(), nullptr)) { cand_cost = 0; for (int i = 0; i < m; i++) cand_cost += rc[i] * rc[i]; cand_cost *= 0.5; }
+      if (lm_evaluate(pf, xc, rc, nullptr)) cand_cost = half_sq(rc);
       else cand_cost = DBL_MAX;
       double sn = 0; for (int i = 0; i < 7; i++) sn += (x[i] - xc[i]) * (x[i] - xc[i]); sn = std::sqrt(sn);
       if (sn <= parameter_tolerance * (x_norm + parameter_tolerance)) break;
@@ -1005,12 +1022,12 @@ static void ceres_refine(M4f& newT, const std::vector<PairFace>& pf, int* iters_
         for (int i = 0; i < 7; i++) x[i] = xc[i];
         x_norm = 0; for (int i = 0; i < 7; i++) x_norm += x[i] * x[i]; x_norm = std::sqrt(x_norm);
         cost = cand_cost;
-        if (!lm_evaluate(pf, x, r.data(), J.data())) break;
+        if (!lm_evaluate(pf, x, r, J)) break;
         grad_and_scale(false);
         gmax = grad_max_norm();
         step_successful = true;
-        radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
-        radius = std::min(max_radius, radius);
+        radius = radius / std::fmax(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+        radius = std::fmin(max_radius, radius);
         decrease_factor = 2.0; reuse_diag = false;
       } else {
         radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diag = true;
