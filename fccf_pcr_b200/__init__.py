@@ -35,7 +35,8 @@ class Params(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("downsample_ms", C.c_float), ("pipeline_ms", C.c_float),
-                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("n_launches", C.c_int)]
+                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("n_launches", C.c_int),
+                ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong), ("stage_ms", C.c_float * 8)]
 
 
 EXPORTS = [

@@ -46,6 +46,8 @@ struct fccf_ctx {
   HypWS h;
   int cap_hyp = 1 << 18;
   cudaEvent_t ev[6];
+  cudaEvent_t sev[8];
+  size_t last_h2d = 0;
   bool have_run = false;
   float leaf = 0.f;
   // stand-alone scoring
@@ -161,6 +163,7 @@ fccf_ctx* fccf_create(int device, const fccf_params* params) {
   if (cudaMalloc(&ctx->d_st, sizeof(PipeState)) != cudaSuccess || cudaMallocHost(&ctx->h_st, sizeof(PipeState)) != cudaSuccess) { delete ctx; return nullptr; }
   cudaMemset(ctx->d_st, 0, sizeof(PipeState));
   for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->sev[i]);
   return ctx;
 }
 
@@ -180,6 +183,7 @@ void fccf_destroy(fccf_ctx* ctx) {
   if (ctx->d_st) cudaFree(ctx->d_st);
   if (ctx->h_st) cudaFreeHost(ctx->h_st);
   for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->sev[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -215,10 +219,15 @@ static int run_pipeline(fccf_ctx* ctx, int n_tar, int n_src, float leaf, float T
   launch_voxelgrid(s, w, 0, 2, &ctx->launches);            // main(): FCCF.cpp:1668-1678
   CK(cudaEventRecord(ctx->ev[2], s));
   launch_voxelgrid(s, w, 1, 2, &ctx->launches);            // FCCF.cpp:1377-1387
+  cudaEventRecord(ctx->sev[0], s);
   launch_planes(s, w, 2, 1, &ctx->launches);               // FCCF.cpp:1400-1401
+  cudaEventRecord(ctx->sev[1], s);
   launch_hypotheses(s, w, ctx->h, &ctx->launches);         // FCCF.cpp:1406-1427, 1439-1462
+  cudaEventRecord(ctx->sev[2], s);
   launch_cluster(s, w, ctx->h, &ctx->launches);            // FCCF.cpp:1464-1466
+  cudaEventRecord(ctx->sev[3], s);
   launch_quick_verify(s, w, ctx->h, &ctx->launches);       // FCCF.cpp:1468-1494
+  cudaEventRecord(ctx->sev[4], s);
   launch_fine_verify_fuse(s, w, ctx->h, &ctx->launches);   // FCCF.cpp:1499-1606
   CK(cudaEventRecord(ctx->ev[3], s));
   CK(cudaMemcpyAsync(ctx->h_st, ctx->d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
@@ -235,6 +244,12 @@ static int run_pipeline(fccf_ctx* ctx, int n_tar, int n_src, float leaf, float T
     cudaEventElapsedTime(&tm->d2h_ms, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&tm->total_ms, ctx->ev[0], ctx->ev[4]);
     tm->n_launches = (int)(ctx->launches - l0);
+    tm->h2d_bytes = had_h2d ? (unsigned long long)ctx->last_h2d : 0ull;
+    tm->d2h_bytes = sizeof(PipeState);
+    tm->stage_ms[0] = tm->downsample_ms;
+    cudaEventElapsedTime(&tm->stage_ms[1], ctx->ev[2], ctx->sev[0]);
+    for (int k = 0; k < 4; k++) cudaEventElapsedTime(&tm->stage_ms[2 + k], ctx->sev[k], ctx->sev[k + 1]);
+    cudaEventElapsedTime(&tm->stage_ms[6], ctx->sev[4], ctx->ev[3]);
   }
   return check_status(ctx);
 }
@@ -252,6 +267,7 @@ int fccf_register(fccf_ctx* ctx, const float* src_xyz, size_t n_src, const float
   if (n_tar) CK(cudaMemcpyAsync(ctx->d_raw[0], tar_xyz, n_tar * 12, cudaMemcpyHostToDevice, s));
   if (n_src) CK(cudaMemcpyAsync(ctx->d_raw[1], src_xyz, n_src * 12, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(ctx->ev[1], s));
+  ctx->last_h2d = (n_tar + n_src) * 12;
   return run_pipeline(ctx, (int)n_tar, (int)n_src, leaf, T_out, timing, true);
 }
 
@@ -281,6 +297,7 @@ int fccf_register_batch(fccf_ctx* ctx, int n_pairs, const float* const* src_xyz,
     if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc;
     if (rc) worst = rc;
     acc.h2d_ms += t.h2d_ms; acc.downsample_ms += t.downsample_ms; acc.pipeline_ms += t.pipeline_ms; acc.d2h_ms += t.d2h_ms; acc.total_ms += t.total_ms; acc.n_launches += t.n_launches;
+    acc.h2d_bytes += t.h2d_bytes; acc.d2h_bytes += t.d2h_bytes; for (int k = 0; k < 8; k++) acc.stage_ms[k] += t.stage_ms[k];
   }
   if (timing) *timing = acc;
   return worst;

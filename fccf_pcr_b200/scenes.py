@@ -196,9 +196,22 @@ def write_ply(path, xyz, binary=True):
 
 
 def rotation_error_deg(Ta, Tb):
+    """Angle between two rotation blocks; the chord form stays accurate for tiny angles
+    (acos of a float32 trace bottoms out around 0.02 degrees)."""
     Ra, Rb = np.asarray(Ta, float)[:3, :3], np.asarray(Tb, float)[:3, :3]
-    c = (np.trace(Ra.T @ Rb) - 1.0) / 2.0
-    return math.degrees(math.acos(max(-1.0, min(1.0, c))))
+    chord = np.linalg.norm(Ra - Rb) / math.sqrt(2.0)      # = 2 sin(angle / 2) for rotations
+    return math.degrees(2.0 * math.asin(min(1.0, chord / 2.0)))
+
+
+def read_ply(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    end = data.index(b"end_header\n") + len(b"end_header\n")
+    hdr = data[:end].decode("ascii").split("\n")
+    n = [int(line.split()[2]) for line in hdr if line.startswith("element vertex")][0]
+    if any("binary_little_endian" in line for line in hdr):
+        return np.frombuffer(data[end:end + 12 * n], "<f4").reshape(n, 3).copy()
+    return np.array([[float(v) for v in line.split()[:3]] for line in data[end:].decode().split("\n")[:n]], np.float32)
 
 
 def translation_error(Ta, Tb):

@@ -54,6 +54,8 @@ typedef struct fccf_timing {
   float d2h_ms;       /* result read-back */
   float total_ms;     /* end to end, host pointers in -> matrix out */
   int n_launches;     /* kernels launched for this registration */
+  unsigned long long h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host */
+  float stage_ms[8];  /* voxelgrid(main), voxelgrid(pipeline), planes, hypotheses, cluster, quick_verify, fine_verify+fuse, - */
 } fccf_timing;
 
 enum { FCCF_OK = 0, FCCF_ERR_CUDA = 1, FCCF_ERR_ARG = 2, FCCF_ERR_CAPACITY = 3, FCCF_ERR_NO_DEVICE = 4 };

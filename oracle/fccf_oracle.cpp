@@ -1372,6 +1372,24 @@ float orc_quick_verify(void* c, float* T16, const float* planes1, int F1, const 
   if (iters) *iters = it;
   return s;
 }
+// stdout of main() (FCCF.cpp:1667, 1687): default ostream float formatting + Eigen's default IOFormat
+// (precision = stream's, every column right-aligned to the widest coefficient, " " and "\n" separators)
+int orc_format_output(float leaf, const float* T16, char* buf, int cap) {
+  // operator<<(float) with the default precision 6 and no flags is printf's %g
+  std::string s; char c[64];
+  snprintf(c, sizeof c, "Leaf size : %g\n", (double)leaf); s += c;
+  s += "Transformation: \n";
+  size_t width = 0;
+  for (int k = 0; k < 16; k++) { snprintf(c, sizeof c, "%g", (double)T16[k]); width = std::max(width, strlen(c)); }
+  for (int i = 0; i < 4; i++) {
+    if (i) s += "\n";
+    for (int j = 0; j < 4; j++) { if (j) s += " "; snprintf(c, sizeof c, "%*g", (int)width, (double)T16[4 * i + j]); s += c; }
+  }
+  s += "\n";
+  if ((int)s.size() + 1 > cap) return -1;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
 // blobs
 int64_t orc_blob_bytes(void* c, const char* name) { Ctx& C = *(Ctx*)c; auto it = C.blobs.find(name); return it == C.blobs.end() ? -1 : (int64_t)it->second.data.size(); }
 int orc_blob_dtype(void* c, const char* name) { Ctx& C = *(Ctx*)c; auto it = C.blobs.find(name); return it == C.blobs.end() ? -1 : it->second.dtype; }

@@ -55,6 +55,7 @@ def lib():
         L.orc_blob_dtype.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_blob_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.orc_blob_names.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.orc_format_output.argtypes = [C.c_float, fp, C.c_char_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -191,3 +192,12 @@ class Oracle:
         iters = C.c_int(0)
         s = self.L.orc_quick_verify(self.h, _f(T), _f(p1), len(p1), _f(p2), len(p2), _i(pairs), C.byref(npairs), C.byref(iters))
         return float(s), T.reshape(4, 4), pairs[:npairs.value].copy(), iters.value
+
+
+def format_output(leaf, T):
+    """stdout of the reference's main() for a leaf size and a 4x4 result."""
+    T = np.ascontiguousarray(T, np.float32).reshape(16)
+    buf = C.create_string_buffer(4096)
+    n = lib().orc_format_output(C.c_float(leaf), _f(T), buf, len(buf))
+    assert n >= 0
+    return buf.value.decode()
