@@ -55,6 +55,17 @@ struct Params {
   int emulate_pcl_overflow = 1;  // VoxelGrid int32 bail-out (App. A.1)
 };
 
+// float transcendentals inside pcl::eigen33 (atan2/cos/sin on float arguments).  The reference calls
+// the platform's glibc float routines, whose last-ulp behaviour depends on the glibc version and on
+// the CPU (ifunc FMA variants; <= 2.40: ~0.56 ulp polynomial kernels, >= 2.41: CORE-MATH, correctly
+// rounded).  Default 0: correctly rounded (evaluate in double, round once) — the limit every glibc
+// converges to and what the CUDA path computes, so the stages downstream compare bit for bit.
+// 1: this platform's atan2f/cosf/sinf (tests bound the effect of the switch on the final transform).
+static int g_libm_float = 0;
+static inline float f_atan2(float y, float x) { return g_libm_float ? std::atan2(y, x) : (float)std::atan2((double)y, (double)x); }
+static inline float f_cos(float x) { return g_libm_float ? std::cos(x) : (float)std::cos((double)x); }
+static inline float f_sin(float x) { return g_libm_float ? std::sin(x) : (float)std::sin((double)x); }
+
 struct P3 { float x, y, z; };
 struct V3f { float x, y, z; float& operator[](int i){ return (&x)[i]; } float operator[](int i) const { return (&x)[i]; } };
 struct V3d { double x, y, z; };
@@ -364,9 +375,9 @@ static void compute_roots(const float m[3][3], float roots[3]) {
   float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
   if (q > 0.f) q = 0.f;
   float rho = std::sqrt(-a_over_3);
-  float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
-  float cos_theta = std::cos(theta);
-  float sin_theta = std::sin(theta);
+  float theta = f_atan2(std::sqrt(-q), half_b) * s_inv3;
+  float cos_theta = f_cos(theta);
+  float sin_theta = f_sin(theta);
   roots[0] = c2_over_3 + 2.f * rho * cos_theta;
   roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
   roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
@@ -1294,6 +1305,7 @@ int orc_set_param(void* c, const char* name, double v) {
   SP(seclct_cluster_number) SP(rough_threshold_gl)
 #undef SP
   if (n == "emulate_pcl_overflow") { p.emulate_pcl_overflow = (int)v; return 0; }
+  if (n == "libm_float") { g_libm_float = (int)v; return 0; }   // process-wide (test switch)
   return -1;
 }
 // full program: src = argv[1], tar = argv[2]; T row-major 16 floats

@@ -68,12 +68,15 @@ def compare(ctx, o, verbose=True):
 
 def main():
     cases = [("indoor", 50000, 1, 0.1), ("indoor", 200000, 2, 0.2)]
+    prm = {}
     if len(sys.argv) > 1:
-        cases = [("indoor", int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3]))]
-    ctx = Context(0)
+        cases = [(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4]))]
+        for kv in sys.argv[5:]:
+            k, v = kv.split("="); prm[k] = float(v)
+    ctx = Context(0, **prm)
     for kind, n, seed, leaf in cases:
         src, tar, Tgt = scenes.make_pair(kind, n, seed)
-        o = Oracle()
+        o = Oracle(**prm)
         To = o.register(src, tar, leaf)
         t0 = time.time()
         try:
@@ -90,6 +93,17 @@ def main():
             scenes.rotation_error_deg(Tg, To), scenes.translation_error(Tg, To), scenes.rotation_error_deg(Tg, Tgt), scenes.translation_error(Tg, Tgt),
             scenes.rotation_error_deg(To, Tgt), scenes.translation_error(To, Tgt)))
         bad = compare(ctx, o)
+        # stage-wise inlier counts: the oracle's fine_verify fed with the GPU's own refined transforms
+        s1, s2 = ctx.blob("sub1").reshape(-1, 3), ctx.blob("sub2").reshape(-1, 3)
+        for t in range(3):
+            Tt = ctx.blob("top_T%d" % t).reshape(-1, 4, 4); To_ = o.blob("top_T%d" % t).reshape(-1, 4, 4)
+            cg = ctx.blob("fv_counts%d" % t).reshape(-1, 5); off = ctx.blob("fv_off%d" % t)
+            for k in range(len(Tt)):
+                so, rows = o.fine_verify(Tt[k], s1, s2)
+                rows = rows[np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))]
+                g = cg[off[k]:off[k + 1]]
+                print("  type %d top %d: rows gpu %d oracle(on gpu T) %d equal=%s | T diff vs oracle T: %.3e deg %.3e m" % (
+                    t, k, len(g), len(rows), np.array_equal(g, rows), scenes.rotation_error_deg(Tt[k], To_[k]) if k < len(To_) else -1, scenes.translation_error(Tt[k], To_[k]) if k < len(To_) else -1))
         print("=== blobs with differences: %d" % bad)
         # repeat timing
         for r in range(3):

@@ -1,0 +1,337 @@
+"""GPU parity tests: libfccf.so (C-ABI, sm_100a kernels) against the CPU oracle on the same seeded
+inputs.  Bars (BASELINE.json north_star): voxel keys, per-voxel counts, pair lists and inlier
+(per-voxel overlap) counts bit-exact; plane parameters within 1e-5 relative; final transform within
+0.01 degree and 1 mm.  Every call goes through the C-ABI; nothing here reads /root/reference."""
+import math
+
+import numpy as np
+import pytest
+
+from fccf_pcr_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("indoor", 20000, 7, 0.1), ("indoor", 50000, 1, 0.1), ("indoor", 200000, 2, 0.2)]
+
+INT_BLOBS = ["vg1_cell1", "vg1_cell2", "vg1_cnt1", "vg1_cnt2", "vg2_cell1", "vg2_cell2", "vg2_cnt1", "vg2_cnt2",
+             "oct_depth1", "oct_depth2", "vox_key1", "vox_key2", "vox_cnt1", "vox_cnt2", "vox_flag1", "vox_flag2",
+             "vox_pidx1", "vox_pidx2", "grow_label1", "grow_label2", "merge_label1", "merge_label2",
+             "n_stage1_faces1", "n_stage1_faces2", "face_id1", "face_id2", "face_nvox1", "face_nvox2", "face_vox1", "face_vox2",
+             "face_off1", "face_off2", "base1", "base2", "matches", "n_hyp", "n_centres", "cluster_num"]
+for _t in range(3):
+    INT_BLOBS += ["cluster_seed_sorted%d" % _t, "cluster_size_sorted%d" % _t, "qv_pairs%d" % _t, "qv_pair_off%d" % _t, "top_centre%d" % _t, "fv_off%d" % _t]
+# float32 data produced by in-order float32 sums: bit-exact as well
+EXACT_FLOAT_BLOBS = ["vg1_xyz1", "vg1_xyz2", "vg2_xyz1", "vg2_xyz2", "cloud_centroid1", "cloud_centroid2", "oct_min1", "oct_min2", "sub1", "sub2"]
+PLANE_TOL = 1e-5
+
+
+def _sorted_counts(o, t):
+    c = o.blob("fv_counts%d" % t).reshape(-1, 5)
+    off = o.blob("fv_off%d" % t)
+    out = []
+    for k in range(len(off) - 1):
+        r = c[off[k]:off[k + 1]]
+        out.append(r[np.lexsort((r[:, 2], r[:, 1], r[:, 0]))])
+    return np.concatenate(out, 0).reshape(-1) if out else np.zeros(0, np.int32)
+
+
+def _check_inlier_counts(c, o):
+    """Inlier counts = per-voxel (static, moving) point counts of every fine-verified hypothesis.  The
+    oracle's fine_verify is fed the GPU's own refined transforms (identical inputs):
+    a last-bit difference in a transform would otherwise move points across voxel faces."""
+    s1, s2 = c.blob("sub1").reshape(-1, 3), c.blob("sub2").reshape(-1, 3)
+    for t in range(3):
+        Tt = c.blob("top_T%d" % t).reshape(-1, 4, 4)
+        cg = c.blob("fv_counts%d" % t).reshape(-1, 5)
+        off = c.blob("fv_off%d" % t)
+        s2g = c.blob("top_s2%d" % t)
+        assert len(off) == len(Tt) + 1
+        for k in range(len(Tt)):
+            so, rows = o.fine_verify(Tt[k], s1, s2)
+            rows = rows[np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))]
+            assert np.array_equal(cg[off[k]:off[k + 1]], rows), "type %d hypothesis %d" % (t, k)
+            assert abs(s2g[k] - so) <= 1e-5 * abs(so) or (np.isnan(so) and np.isnan(s2g[k]))
+
+
+def _rel_rows(a, b, width, groups):
+    """max over rows of |a-b| / max(|b|) per group of columns (a vector's error relative to its norm)."""
+    a = a.reshape(-1, width).astype(np.float64)
+    b = b.reshape(-1, width).astype(np.float64)
+    worst = 0.0
+    for cols in groups:
+        d = np.abs(a[:, cols] - b[:, cols]).max(axis=1) if len(a) else np.zeros(0)
+        ref = np.maximum(np.abs(b[:, cols]).max(axis=1), 1e-3) if len(a) else np.ones(0)
+        if len(d):
+            worst = max(worst, float((d / ref).max()))
+    return worst
+
+
+@pytest.fixture(scope="module")
+def runs(ctx, oracle_mod):
+    cache = {}
+
+    def get(case):
+        if case not in cache:
+            kind, n, seed, leaf = case
+            src, tar, Tgt = scenes.make_pair(kind, n, seed)
+            o = oracle_mod.Oracle()
+            To = o.register(src, tar, leaf)
+            cache[case] = (src, tar, Tgt, o, To)
+        src, tar, Tgt, o, To = cache[case]
+        Tg = ctx.register(src, tar, case[3])      # re-run so the context's blobs belong to this case
+        return src, tar, Tgt, o, To, Tg
+
+    return get
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%d-seed%d-leaf%g" % c)
+def test_integer_stages_bit_exact(ctx, runs, case):
+    src, tar, Tgt, o, To, Tg = runs(case)
+    assert ctx.timing.n_launches > 0
+    names = set(o.blob_names())
+    for name in INT_BLOBS + EXACT_FLOAT_BLOBS:
+        if name not in names:
+            continue
+        a, b = ctx.blob(name), o.blob(name)
+        assert a.shape == b.shape, name
+        assert np.array_equal(a, b, equal_nan=(a.dtype.kind == "f")), "%s: %d of %d entries differ" % (name, int((a != b).sum()), a.size)
+    _check_inlier_counts(ctx, o)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%d-seed%d-leaf%g" % c)
+def test_plane_parameters_within_1e5(ctx, runs, case):
+    src, tar, Tgt, o, To, Tg = runs(case)
+    for tag in "12":
+        # per voxel: centroid (3), normal (3), curvature, count.  Centroids are in-order float32 sums:
+        # bit-exact.  Normals and curvature come out of pcl::eigen33's closed form, whose float
+        # atan2/cos/sin are glibc's in the oracle and correctly rounded on the GPU (last-ulp differences
+        # that the cancellation in the smallest root amplifies): normals of planar voxels within 1e-5 of
+        # the unit norm, curvature (a [0, 1/3] ratio compared against 0.05) within 2e-6 absolute.
+        a, b = ctx.blob("vox_plane" + tag).reshape(-1, 8), o.blob("vox_plane" + tag).reshape(-1, 8)
+        planar = o.blob("vox_flag" + tag) == 1
+        np.testing.assert_array_equal(a[:, :3], b[:, :3])
+        np.testing.assert_array_equal(a[:, 7], b[:, 7])
+        assert np.abs(a[planar, 3:6] - b[planar, 3:6]).max(initial=0) <= PLANE_TOL
+        assert np.abs(a[:, 6] - b[:, 6]).max(initial=0) <= 2e-6
+        assert _rel_rows(ctx.blob("pvox" + tag), o.blob("pvox" + tag), 7, [[0, 1, 2], [3, 4, 5], [6]]) <= PLANE_TOL
+        assert _rel_rows(ctx.blob("face_plane" + tag), o.blob("face_plane" + tag), 7, [[0, 1, 2], [3, 4, 5], [6]]) <= PLANE_TOL
+        # roughness = mean of |acos| angles of nearly parallel normals: absolute tolerance in degrees
+        # (one float ulp of cos(theta) at theta = 0 is 0.0198 degree: the formula's own resolution, Q9)
+        np.testing.assert_allclose(ctx.blob("face_theta" + tag), o.blob("face_theta" + tag), atol=0.02)
+        np.testing.assert_allclose(ctx.blob("base_angle" + tag), o.blob("base_angle" + tag), atol=1e-3)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%d-seed%d-leaf%g" % c)
+def test_hypotheses_clusters_and_scores(ctx, runs, case):
+    src, tar, Tgt, o, To, Tg = runs(case)
+    for t in range(3):
+        assert _rel_rows(ctx.blob("hyp%d" % t), o.blob("hyp%d" % t), 12, [[0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11]]) <= 1e-4
+        assert _rel_rows(ctx.blob("centre%d" % t), o.blob("centre%d" % t), 7, [[0, 1, 2, 3], [4, 5, 6]]) <= 1e-4
+        np.testing.assert_array_equal(ctx.blob("qv_score%d" % t), o.blob("qv_score%d" % t))      # plane-pair importance sums
+        np.testing.assert_array_equal(ctx.blob("top_s1%d" % t), o.blob("top_s1%d" % t))
+        np.testing.assert_allclose(ctx.blob("top_s2%d" % t), o.blob("top_s2%d" % t), rtol=1e-4)   # float32 sum over voxels, order differs
+        # the refined transforms that reach fine verification and fusion
+        a, b = ctx.blob("top_T%d" % t).reshape(-1, 4, 4), o.blob("top_T%d" % t).reshape(-1, 4, 4)
+        for Ta, Tb in zip(a, b):
+            assert scenes.rotation_error_deg(Ta, Tb) <= 0.01 and scenes.translation_error(Ta, Tb) <= 1e-3
+        # every refined cluster centre: the Levenberg-Marquardt trajectories are FP64 on both sides but
+        # libm (sin/cos/pow) differs in the last ulp, which ill-conditioned (wrong) hypotheses amplify
+        a, b = ctx.blob("qv_T%d" % t).reshape(-1, 4, 4), o.blob("qv_T%d" % t).reshape(-1, 4, 4)
+        ok = [scenes.rotation_error_deg(Ta, Tb) <= 0.01 and scenes.translation_error(Ta, Tb) <= 1e-3 for Ta, Tb in zip(a, b)]
+        assert len(ok) == 0 or sum(ok) >= 0.9 * len(ok), "type %d: only %d of %d refined centres agree" % (t, sum(ok), len(ok))
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%d-seed%d-leaf%g" % c)
+def test_final_transform(ctx, runs, case):
+    src, tar, Tgt, o, To, Tg = runs(case)
+    assert scenes.rotation_error_deg(Tg, To) <= 0.01          # degrees
+    assert scenes.translation_error(Tg, To) <= 1e-3           # metres
+    np.testing.assert_array_equal(Tg[3], [0, 0, 0, 1])
+    assert scenes.rotation_error_deg(Tg, Tgt) < 1.0 and scenes.translation_error(Tg, Tgt) < 0.08
+    # device-resident entry point gives the same bits as the host-pointer one
+    import torch
+
+    ds, dt = torch.from_numpy(src).cuda(), torch.from_numpy(tar).cuda()
+    torch.cuda.synchronize()
+    Td = ctx.register_device(ds.data_ptr(), len(src), dt.data_ptr(), len(tar), case[3])
+    np.testing.assert_array_equal(Td, Tg)
+    assert ctx.timing.h2d_bytes == 0
+
+
+# ---- stage entry points --------------------------------------------------------------------
+def test_voxelgrid_stage(ctx, orc):
+    rng = np.random.default_rng(4)
+    for n, leaf in [(0, 0.1), (1, 0.1), (7, 0.5), (5000, 0.25), (300000, 0.07)]:
+        pts = (rng.normal(size=(n, 3)) * [4, 3, 1]).astype(np.float32)
+        if n >= 5000:
+            pts[n // 3] = [np.nan, 1, 1]
+            pts[n // 2] = [1, -np.inf, 1]
+        a = ctx.voxelgrid(pts, leaf)
+        b = orc.voxelgrid(pts, leaf)
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and np.array_equal(x, y)
+    # hand-computed boundary case (tests/test_oracle_kat.py::test_voxelgrid_hand_computed)
+    pts = np.array([[0.1, 0.1, 0.1], [0.5, 0.1, 0.1], [-0.5, 0.1, 0.1], [-0.51, 0.1, 0.1], [0.4, 0.2, 0.3]], np.float32)
+    out, cell, cnt = ctx.voxelgrid(pts, 0.5)
+    assert cell.tolist() == [0, 1, 2, 3] and cnt.tolist() == [1, 1, 2, 1]
+    # pcl int32 overflow bail-out: output = input
+    pts = np.array([[0, 0, 0], [2000, 2000, 2000], [1, 1, 1]], np.float32)
+    out, cell, cnt = ctx.voxelgrid(pts, 0.5)
+    np.testing.assert_array_equal(out, pts)
+    # idempotence property at full size (2M points): a second pass keeps the cell set
+    pts = (rng.uniform(-1, 1, (2_000_000, 3)) * [100, 100, 10]).astype(np.float32)
+    out, cell, cnt = ctx.voxelgrid(pts, 0.5)
+    assert cnt.sum() == len(pts) and (np.diff(cell) > 0).all()
+    out2, cell2, cnt2 = ctx.voxelgrid(out, 0.5)
+    assert abs(len(out2) - len(out)) <= 1e-4 * len(out) and cnt2.sum() == len(out)
+
+
+def test_extract_planes_stage(ctx, orc):
+    src, tar, _ = scenes.make_pair("indoor", 30000, 11)
+    down, _, _ = orc.voxelgrid(tar, 0.1)
+    nf = ctx.extract_planes(down)
+    assert nf == orc.face_extract(down)
+    for name in ["vox_key1", "vox_cnt1", "vox_flag1", "vox_pidx1", "grow_label1", "merge_label1", "face_id1", "face_nvox1", "face_vox1", "sub1"]:
+        assert np.array_equal(ctx.blob(name), orc.blob(name)), name
+    assert _rel_rows(ctx.blob("face_plane1"), orc.blob("face_plane1"), 7, [[0, 1, 2], [3, 4, 5], [6]]) <= PLANE_TOL
+    # ragged / tiny inputs
+    for pts in [np.zeros((0, 3), np.float32), np.ones((1, 3), np.float32), down[:5], down[:37]]:
+        assert ctx.extract_planes(pts) == orc.face_extract(pts)
+
+
+def _moved(rng, s1, n2, deg, shift):
+    a = math.radians(deg)
+    R = np.array([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1]])
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = R
+    T[:3, 3] = shift
+    s2 = (s1[rng.permutation(len(s1))[:n2]] + rng.normal(scale=0.02, size=(n2, 3))).astype(np.float32)
+    return s2, T
+
+
+def test_score_hypotheses_inlier_counts_bit_exact(ctx, orc):
+    rng = np.random.default_rng(31)
+    s1 = (rng.uniform(-1, 1, (4000, 3)) * [5, 4, 1.5]).astype(np.float32)
+    s2, _ = _moved(rng, s1, 3500, 0, 0)
+    Ts = []
+    for k in range(40):
+        _, T = _moved(rng, s1, 1, rng.uniform(-8, 8), rng.uniform(-0.4, 0.4, 3))
+        Ts.append(T)
+    Ts = np.stack(Ts)
+    sc = ctx.score_hypotheses(Ts, s1, s2)
+    for k in range(40):
+        so, rows = orc.fine_verify(Ts[k], s1, s2)
+        assert abs(sc[k] - so) <= 1e-5 * max(so, 1e-3)     # float32 sum over voxels; the order differs (hash vs DFS)
+        if k % 8 == 0:
+            rows = rows[np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))]
+            assert np.array_equal(ctx.score_counts(k), rows)
+    # edge cases: no moving points, no static points (0/0 -> NaN, Q15), a hypothesis throwing everything out of range
+    assert ctx.score_hypotheses(Ts[:2], s1, np.zeros((0, 3), np.float32)).tolist() == [0.0, 0.0]
+    assert np.isnan(ctx.score_hypotheses(Ts[:1], np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))).all()
+    far = np.eye(4, dtype=np.float32); far[:3, 3] = 1e4
+    assert ctx.score_hypotheses(far[None], s1, s2)[0] == 0.0
+
+
+def test_score_hypotheses_full_size_properties(ctx):
+    """BASELINE config 3 size (hundreds of thousands of leftover points): checks that do not need the oracle."""
+    rng = np.random.default_rng(32)
+    n = 400_000
+    s1 = (rng.uniform(-1, 1, (n, 3)) * [90, 90, 8]).astype(np.float32)
+    I = np.eye(4, dtype=np.float32)
+    sc = ctx.score_hypotheses(np.stack([I, I]), s1, s1)
+    assert sc[0] == sc[1] and abs(sc[0] - 1.0) < 1e-6              # a cloud against itself: every voxel s == t
+    rows = ctx.score_counts(0)
+    assert (rows[:, 3] == rows[:, 4]).all() and rows[:, 3].sum() == n
+    # disjoint halves of one lattice voxel set score strictly less
+    sh = I.copy(); sh[:3, 3] = [0.5, 0.0, 0.0]
+    sc2 = ctx.score_hypotheses(sh[None], s1, s1)
+    assert 0.0 < sc2[0] < sc[0]
+    rows2 = ctx.score_counts(0)
+    assert rows2[:, 4].sum() <= n
+
+
+def test_quick_verify_stage(ctx, orc):
+    src, tar, _ = scenes.make_pair("indoor", 20000, 7)
+    o = orc
+    o.register(src, tar, 0.1)
+    p1 = o.blob("face_plane1").reshape(-1, 7)
+    p2 = o.blob("face_plane2").reshape(-1, 7)
+    cen = o.blob("centre0").reshape(-1, 7)[:24]
+    Ts = []
+    for c in cen:
+        T = np.eye(4, dtype=np.float32)
+        T[:3, :3] = o.quat_to_matrix(c[:4])
+        T[:3, 3] = c[4:7]
+        Ts.append(T)
+    Ts = np.stack(Ts)
+    sc, Tr, npair, pairs, iters = ctx.quick_verify(Ts, p1, p2)
+    agree = 0
+    for k in range(len(Ts)):
+        so, To, po, io = o.quick_verify(Ts[k], p1, p2)
+        assert sc[k] == np.float32(so)
+        assert npair[k] == len(po) and np.array_equal(pairs[k, :npair[k]], po)       # pair lists bit-exact
+        agree += scenes.rotation_error_deg(Tr[k], To) <= 0.01 and scenes.translation_error(Tr[k], To) <= 1e-3
+    assert agree >= 0.9 * len(Ts)
+
+
+def test_degenerate_inputs(ctx, oracle_mod):
+    src, tar, _ = scenes.make_pair("indoor", 20000, 7)
+    o = oracle_mod.Oracle()
+    # Q14: leaf 1.0 -> no planes -> three identity hypotheses -> zero / NaN matrix, reproduced not "fixed"
+    To = o.register(src, tar, 1.0)
+    Tg = ctx.register(src, tar, 1.0)
+    assert np.array_equal(np.isnan(Tg), np.isnan(To))
+    np.testing.assert_array_equal(np.nan_to_num(Tg), np.nan_to_num(To))
+    for name in ["n_hyp", "n_centres", "vg2_cnt1", "vox_cnt1"]:
+        assert np.array_equal(ctx.blob(name), o.blob(name)), name
+    # identical clouds
+    To = o.register(tar, tar, 0.1)
+    Tg = ctx.register(tar, tar, 0.1)
+    assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
+    # tiny clouds
+    To = o.register(src[:50], tar[:50], 0.1)
+    Tg = ctx.register(src[:50], tar[:50], 0.1)
+    assert np.array_equal(np.isnan(Tg), np.isnan(To))
+
+
+def test_outdoor_scaled_parameters(oracle_mod):
+    """BASELINE config 3 shape at reduced size: outdoor scene, leaf 0.5 with the plane / fine-verify voxels
+    scaled identically on both sides (face_voxel_size = max(1, 4*leaf))."""
+    import fccf_pcr_b200 as fccf
+
+    src, tar, Tgt = scenes.make_pair("outdoor", 300000, 3)
+    prm = dict(face_voxel_size=4.0, fine_verify_voxel_size=2.0)
+    o = oracle_mod.Oracle(**prm)
+    To = o.register(src, tar, 0.5)
+    c = fccf.Context(0, **prm)
+    Tg = c.register(src, tar, 0.5)
+    for name in ["vg2_cnt1", "vox_key1", "vox_cnt2", "merge_label1", "merge_label2", "base1", "base2", "matches", "n_hyp", "n_centres"]:
+        assert np.array_equal(c.blob(name), o.blob(name)), name
+    _check_inlier_counts(c, o)
+    assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
+    c.close()
+
+
+def test_batch_matches_single(ctx):
+    pairs = [scenes.make_pair("indoor", 20000, s) for s in (7, 8, 9)]
+    Tb = ctx.register_batch([p[0] for p in pairs], [p[1] for p in pairs], 0.1)
+    for k, p in enumerate(pairs):
+        np.testing.assert_array_equal(Tb[k], ctx.register(p[0], p[1], 0.1))
+
+
+def test_cli_output_is_the_reference_format(ctx, oracle_mod, tmp_path):
+    import subprocess
+
+    import fccf_pcr_b200 as fccf
+
+    src, tar, _ = scenes.make_pair("indoor", 20000, 7)
+    a, b = tmp_path / "src.ply", tmp_path / "tar.ply"
+    scenes.write_ply(str(a), src)
+    scenes.write_ply(str(b), tar, binary=False)      # ascii PLY, %.9g round-trips float32 exactly
+    r = subprocess.run([fccf.CLI_PATH, str(a), str(b), "0.1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    Tg = ctx.register(src, tar, 0.1)
+    expect = oracle_mod.format_output(0.1, Tg)        # formatter only: the matrix is the GPU's
+    assert r.stdout.startswith(expect), (r.stdout, expect)
+    extra = r.stdout[len(expect):]
+    assert extra.startswith("Time pipeline") and "kernel launches" in extra
