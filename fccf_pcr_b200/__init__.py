@@ -43,6 +43,7 @@ EXPORTS = [
     "fccf_default_params", "fccf_create", "fccf_destroy", "fccf_last_error", "fccf_set_params", "fccf_register",
     "fccf_register_device", "fccf_register_batch", "fccf_voxelgrid", "fccf_extract_planes", "fccf_score_hypotheses",
     "fccf_score_hypotheses_bench", "fccf_score_counts", "fccf_quick_verify", "fccf_debug_blob", "fccf_launch_count",
+    "fccf_stream_handle",
 ]
 
 
@@ -85,6 +86,8 @@ def lib():
         L.fccf_debug_blob.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t), ip]
         L.fccf_launch_count.argtypes = [vp]
         L.fccf_launch_count.restype = C.c_uint64
+        L.fccf_stream_handle.argtypes = [vp]
+        L.fccf_stream_handle.restype = vp
         _LIB = L
     return _LIB
 
@@ -232,6 +235,11 @@ class Context:
         if nb.value:
             self._check(self.L.fccf_debug_blob(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), nb.value, C.byref(nb), C.byref(dt)))
         return out
+
+    @property
+    def stream_handle(self):
+        """cudaStream_t of this context as an integer (e.g. for torch.cuda.ExternalStream)."""
+        return int(self.L.fccf_stream_handle(self.h) or 0)
 
     @property
     def launch_count(self):

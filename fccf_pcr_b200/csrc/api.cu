@@ -191,6 +191,7 @@ void fccf_destroy(fccf_ctx* ctx) {
 const char* fccf_last_error(const fccf_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no usable CUDA device)"; }
 int fccf_set_params(fccf_ctx* ctx, const fccf_params* params) { if (!ctx || !params) return FCCF_ERR_ARG; ctx->p = *params; return FCCF_OK; }
 uint64_t fccf_launch_count(const fccf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* fccf_stream_handle(const fccf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 }  // extern "C"
 

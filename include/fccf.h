@@ -118,6 +118,10 @@ int fccf_quick_verify(fccf_ctx* ctx, float* T, size_t n_hyp, const float* planes
  * Returns FCCF_ERR_ARG for an unknown name; *bytes = size needed (also when dst is NULL). */
 int fccf_debug_blob(fccf_ctx* ctx, const char* name, void* dst, size_t cap_bytes, size_t* bytes, int* dtype);
 
+/* The CUDA stream (cudaStream_t) every kernel of this context is launched on, so that a caller can
+ * bracket calls with its own events.  NULL without a context. */
+void* fccf_stream_handle(const fccf_ctx* ctx);
+
 /* Number of kernels this library has launched in the context so far. */
 uint64_t fccf_launch_count(const fccf_ctx* ctx);
 

@@ -1,0 +1,35 @@
+"""Per-stage device times of one registration (fccf_timing.stage_ms), for profiling runs."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+from fccf_pcr_b200 import Context, scenes
+
+STAGES = ["voxelgrid(main)", "voxelgrid(pipeline)", "planes", "hypotheses", "cluster", "quick_verify", "fine_verify+fuse"]
+
+
+def main():
+    kind = sys.argv[1] if len(sys.argv) > 1 else "indoor"
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
+    seed = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    leaf = float(sys.argv[4]) if len(sys.argv) > 4 else 0.2
+    reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+    prm = {}
+    for kv in sys.argv[6:]:
+        k, v = kv.split("=")
+        prm[k] = float(v)
+    src, tar, _ = scenes.make_pair(kind, n, seed)
+    ctx = Context(0, **prm)
+    for r in range(reps):
+        ctx.register(src, tar, leaf)
+        tm = ctx.timing
+        print("run %d: total %.3f ms (h2d %.3f, pipeline %.3f, d2h %.3f), %d launches | " % (r, tm.total_ms, tm.h2d_ms, tm.pipeline_ms, tm.d2h_ms, tm.n_launches) +
+              " ".join("%s %.3f" % (s, tm.stage_ms[i]) for i, s in enumerate(STAGES)))
+    print("n_hyp", ctx.blob("n_hyp"), "n_centres", ctx.blob("n_centres"), "P", len(ctx.blob("vg2_cnt1")), len(ctx.blob("vg2_cnt2")),
+          "V", len(ctx.blob("vox_cnt1")), "Vp", len(ctx.blob("pvox1")) // 7, "S", len(ctx.blob("sub1")) // 3, len(ctx.blob("sub2")) // 3)
+
+
+if __name__ == "__main__":
+    main()
