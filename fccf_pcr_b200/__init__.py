@@ -30,7 +30,7 @@ PARAM_FIELDS = [
 
 
 class Params(C.Structure):
-    _fields_ = [(n, C.c_float) for n in PARAM_FIELDS] + [("emulate_pcl_overflow", C.c_int), ("reserved", C.c_int * 3)]
+    _fields_ = [(n, C.c_float) for n in PARAM_FIELDS] + [("emulate_pcl_overflow", C.c_int), ("batch_lanes", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class Timing(C.Structure):
@@ -43,7 +43,7 @@ EXPORTS = [
     "fccf_default_params", "fccf_create", "fccf_destroy", "fccf_last_error", "fccf_set_params", "fccf_register",
     "fccf_register_device", "fccf_register_batch", "fccf_voxelgrid", "fccf_extract_planes", "fccf_score_hypotheses",
     "fccf_score_hypotheses_bench", "fccf_score_counts", "fccf_quick_verify", "fccf_debug_blob", "fccf_launch_count",
-    "fccf_stream_handle",
+    "fccf_stream_handle", "fccf_score_best", "fccf_register_batch_device",
 ]
 
 
@@ -77,10 +77,12 @@ def lib():
         L.fccf_register.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, C.c_float, fp, C.POINTER(Timing)]
         L.fccf_register_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_float, fp, C.POINTER(Timing)]
         L.fccf_register_batch.argtypes = [vp, C.c_int, C.POINTER(fp), C.POINTER(C.c_size_t), C.POINTER(fp), C.POINTER(C.c_size_t), C.c_float, fp, C.POINTER(Timing)]
+        L.fccf_register_batch_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t), C.c_float, fp, C.POINTER(Timing)]
         L.fccf_voxelgrid.argtypes = [vp, fp, C.c_size_t, C.c_float, fp, C.POINTER(C.c_int64), ip, C.POINTER(C.c_size_t)]
         L.fccf_extract_planes.argtypes = [vp, fp, C.c_size_t, ip]
         L.fccf_score_hypotheses.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t, fp]
         L.fccf_score_hypotheses_bench.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t, C.c_int, fp, fp]
+        L.fccf_score_best.argtypes = [vp, C.c_size_t, C.POINTER(C.c_int64), vp]
         L.fccf_score_counts.argtypes = [vp, C.c_size_t, ip, C.c_size_t, C.POINTER(C.c_size_t)]
         L.fccf_quick_verify.argtypes = [vp, fp, C.c_size_t, fp, C.c_int, fp, C.c_int, fp, ip, ip, ip]
         L.fccf_debug_blob.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t), ip]
@@ -174,6 +176,16 @@ class Context:
         self._check(self.L.fccf_register_batch(self.h, n, sp, ns, tp, nt, C.c_float(leaf), _f(T), C.byref(self.timing)))
         return T.reshape(n, 4, 4)
 
+    def register_batch_device(self, d_src_ptrs, n_srcs, d_tar_ptrs, n_tars, leaf):
+        n = len(d_src_ptrs)
+        sp = (C.c_void_p * n)(*[int(p) for p in d_src_ptrs])
+        tp = (C.c_void_p * n)(*[int(p) for p in d_tar_ptrs])
+        ns = (C.c_size_t * n)(*[int(v) for v in n_srcs])
+        nt = (C.c_size_t * n)(*[int(v) for v in n_tars])
+        T = np.zeros((n, 16), np.float32)
+        self._check(self.L.fccf_register_batch_device(self.h, n, sp, ns, tp, nt, C.c_float(leaf), _f(T), C.byref(self.timing)))
+        return T.reshape(n, 4, 4)
+
     def voxelgrid(self, xyz, leaf):
         xyz = np.ascontiguousarray(xyz, np.float32)
         n = len(xyz)
@@ -206,6 +218,12 @@ class Context:
         ms = C.c_float(0)
         self._check(self.L.fccf_score_hypotheses_bench(self.h, _f(Ts), len(Ts), _f(s1), len(s1), _f(s2), len(s2), int(repeat), _f(sc), C.byref(ms)))
         return sc[:len(Ts)], ms.value
+
+    def score_best(self, index_base=0, device_ptr=None):
+        """Packed (score, index) maximum of the last scored list (see fccf_score_best / dist.unpack_score_index)."""
+        out = C.c_int64(0)
+        self._check(self.L.fccf_score_best(self.h, int(index_base), C.byref(out), C.c_void_p(device_ptr) if device_ptr else None))
+        return np.int64(out.value)
 
     def score_counts(self, hyp, cap_rows=1 << 20):
         rows = np.zeros((cap_rows, 5), np.int32)

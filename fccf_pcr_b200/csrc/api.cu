@@ -4,7 +4,9 @@
 // parity tests, and read-back of stage intermediates ("debug blobs").
 // No CPU fallback: every entry point needs a CUDA device.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -30,12 +32,12 @@ struct Arena {
   }
 };
 
-struct fccf_ctx {
-  int device = 0;
+// One registration in flight: its own stream, workspaces and result block.  A context owns lane 0
+// (the single-pair entry points and the stage entry points) and creates further lanes on demand for
+// fccf_register_batch*, which keeps several independent pairs in flight at once: most kernels of one
+// registration are single-CTA (order-dependent greedy stages), so concurrent lanes fill the other SMs.
+struct Lane {
   cudaStream_t stream = nullptr;
-  fccf_params p;
-  std::string err;
-  uint64_t launches = 0;
   int cap_pts = 0;
   Arena cloud_arena[2];
   float* d_raw[2] = {nullptr, nullptr};
@@ -44,17 +46,32 @@ struct fccf_ctx {
   PipeState* h_st = nullptr;     // pinned
   Arena hyp_arena;
   HypWS h;
-  int cap_hyp = 1 << 18;
   cudaEvent_t ev[6];
   cudaEvent_t sev[8];
   size_t last_h2d = 0;
+  uint64_t launches = 0, l0 = 0;
+  bool busy = false; int pair = -1; bool had_h2d = false;
+};
+
+struct fccf_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;   // = lanes[0]->stream
+  fccf_params p;
+  std::string err;
+  uint64_t launches = 0;           // kernels launched outside the lanes (stand-alone stage entry points)
+  std::vector<Lane*> lanes;
+  int max_lanes = 8;
+  int cap_hyp = 1 << 18;
   bool have_run = false;
   float leaf = 0.f;
   // stand-alone scoring
   float *d_sc_s1 = nullptr, *d_sc_s2 = nullptr, *d_sc_T = nullptr, *d_sc_scores = nullptr;
   size_t sc_cap1 = 0, sc_cap2 = 0, sc_capT = 0;
   Arena sc_arena; ScoreWS sc_ws; int sc_cap_hash = 0; ScoreState* d_sc_ss = nullptr; int* d_sc_n = nullptr;
-  size_t sc_n2 = 0;
+  size_t sc_n2 = 0, sc_nhyp = 0;
+  long long* d_sc_best = nullptr;
+  // lane-0 aliases used by the stage entry points and the blob reader
+  Lane& L0() { return *lanes[0]; }
 };
 
 static size_t cloud_bytes(int cap) {
@@ -82,31 +99,53 @@ static void cloud_carve(Arena& a, CloudWS& w, int cap) {
   w.fstat = a.take<float>(16 * c); w.face_vox = a.take<int>(c); w.face_off = a.take<int>(64);
 }
 
-static int ensure_capacity(fccf_ctx* ctx, size_t n0, size_t n1) {
+static int lane_create(fccf_ctx* ctx, Lane** out) {
+  Lane* L = new Lane();
+  if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) { delete L; ctx->err = "cudaStreamCreate failed"; return FCCF_ERR_CUDA; }
+  if (cudaMalloc(&L->d_st, sizeof(PipeState)) != cudaSuccess || cudaMallocHost(&L->h_st, sizeof(PipeState)) != cudaSuccess) { delete L; ctx->err = "state allocation failed"; return FCCF_ERR_CUDA; }
+  cudaMemset(L->d_st, 0, sizeof(PipeState));
+  for (int i = 0; i < 6; i++) cudaEventCreate(&L->ev[i]);
+  for (int i = 0; i < 8; i++) cudaEventCreate(&L->sev[i]);
+  *out = L;
+  return FCCF_OK;
+}
+static void lane_destroy(Lane* L) {
+  if (!L) return;
+  if (L->stream) cudaStreamSynchronize(L->stream);
+  for (int c = 0; c < 2; c++) { if (L->cloud_arena[c].base) cudaFree(L->cloud_arena[c].base); if (L->d_raw[c]) cudaFree(L->d_raw[c]); }
+  if (L->hyp_arena.base) cudaFree(L->hyp_arena.base);
+  if (L->d_st) cudaFree(L->d_st);
+  if (L->h_st) cudaFreeHost(L->h_st);
+  for (int i = 0; i < 6; i++) cudaEventDestroy(L->ev[i]);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(L->sev[i]);
+  if (L->stream) cudaStreamDestroy(L->stream);
+  delete L;
+}
+
+static int ensure_capacity(fccf_ctx* ctx, Lane* L, size_t n0, size_t n1) {
   size_t need = std::max(n0, n1);
   if (need < 1024) need = 1024;
-  if ((size_t)ctx->cap_pts >= need) return FCCF_OK;
+  if ((size_t)L->cap_pts >= need) return FCCF_OK;
   if (need > (size_t)1 << 30) { ctx->err = "cloud too large"; return FCCF_ERR_ARG; }
   int cap = (int)((need + 4095) & ~(size_t)4095);
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(L->stream));
   for (int c = 0; c < 2; c++) {
-    if (ctx->cloud_arena[c].base) CK(cudaFree(ctx->cloud_arena[c].base));
-    if (ctx->d_raw[c]) CK(cudaFree(ctx->d_raw[c]));
-    ctx->cloud_arena[c] = Arena();
-    ctx->d_raw[c] = nullptr;
+    if (L->cloud_arena[c].base) CK(cudaFree(L->cloud_arena[c].base));
+    if (L->d_raw[c]) CK(cudaFree(L->d_raw[c]));
+    L->cloud_arena[c] = Arena();
+    L->d_raw[c] = nullptr;
     size_t bytes = cloud_bytes(cap);
-    CK(cudaMalloc(&ctx->cloud_arena[c].base, bytes));
-    ctx->cloud_arena[c].size = bytes;
-    CK(cudaMalloc(&ctx->d_raw[c], (size_t)cap * 12));
-    cloud_carve(ctx->cloud_arena[c], ctx->c[c], cap);
-    ctx->c[c].raw = ctx->d_raw[c];
+    CK(cudaMalloc(&L->cloud_arena[c].base, bytes));
+    L->cloud_arena[c].size = bytes;
+    CK(cudaMalloc(&L->d_raw[c], (size_t)cap * 12));
+    cloud_carve(L->cloud_arena[c], L->c[c], cap);
+    L->c[c].raw = L->d_raw[c];
   }
   // fine-verify hash sized for the leftover cloud (<= cap points)
-  if (ctx->hyp_arena.base) CK(cudaFree(ctx->hyp_arena.base));
-  ctx->hyp_arena = Arena();
-  HypWS& h = ctx->h;
+  if (L->hyp_arena.base) CK(cudaFree(L->hyp_arena.base));
+  L->hyp_arena = Arena();
+  HypWS& h = L->h;
   size_t ch = (size_t)ctx->cap_hyp, nbh = ch / RS_TILE + 2;
-  int cap_hash = 1024; while ((size_t)cap_hash < 2 * (size_t)cap) cap_hash <<= 1;
   size_t bytes = 0;
   auto add = [&](size_t x) { bytes += (x + 255) & ~(size_t)255; };
   add(4 * FCCF_MAXMATCH); add(4 * FCCF_MAXMATCH); add(48 * ch); add(32 * ch); add(16 * ch);
@@ -116,11 +155,12 @@ static int ensure_capacity(fccf_ctx* ctx, size_t n0, size_t n1) {
   size_t nc = 3 * FCCF_MAXCENTRE, ntop = 3 * FCCF_TOPK;
   add(nc * 32); add(nc * 64); add(nc * 4); add(nc * 4); add(nc * 128); add(nc * 4); add(nc * 4);
   add(ntop * 64); add(ntop * 4); add(ntop * 4); add(ntop * 4);
-  add((size_t)cap_hash * 8); add((size_t)cap_hash * 4); add((size_t)cap_hash * 4 * ntop);
+  size_t fv_bytes = score_ws_layout(nullptr, nullptr, cap, (int)ntop);
+  add(fv_bytes);
   bytes += 8192;
-  CK(cudaMalloc(&ctx->hyp_arena.base, bytes));
-  ctx->hyp_arena.size = bytes;
-  Arena& a = ctx->hyp_arena;
+  CK(cudaMalloc(&L->hyp_arena.base, bytes));
+  L->hyp_arena.size = bytes;
+  Arena& a = L->hyp_arena;
   h.cap_hyp = ctx->cap_hyp;
   h.match_cnt = a.take<int>(FCCF_MAXMATCH); h.match_off = a.take<int>(FCCF_MAXMATCH);
   h.hyp_T = a.take<float>(12 * ch); h.hyp_qt = a.take<float>(8 * ch); h.hyp_ax = a.take<float>(4 * ch);
@@ -130,9 +170,8 @@ static int ensure_capacity(fccf_ctx* ctx, size_t n0, size_t n1) {
   h.centre = a.take<float>(nc * 8); h.qv_T = a.take<float>(nc * 16); h.qv_score = a.take<float>(nc); h.qv_npair = a.take<int>(nc);
   h.qv_pairs = a.take<int>(nc * 32); h.qv_iters = a.take<int>(nc); h.rank_perm = a.take<int>(nc);
   h.top_T = a.take<float>(ntop * 16); h.top_s1 = a.take<float>(ntop); h.top_s2 = a.take<float>(ntop); h.top_centre = a.take<int>(ntop);
-  h.fv_keys = a.take<u64>(cap_hash); h.fv_s = a.take<int>(cap_hash); h.fv_t = a.take<int>((size_t)cap_hash * ntop);
-  h.cap_hash = cap_hash;
-  ctx->cap_pts = cap;
+  score_ws_layout(&h.fv, a.take<char>(fv_bytes), cap, (int)ntop);
+  L->cap_pts = cap;
   return FCCF_OK;
 }
 
@@ -153,26 +192,28 @@ void fccf_default_params(fccf_params* p) {
 }
 
 fccf_ctx* fccf_create(int device, const fccf_params* params) {
+  // Concurrent lanes need one hardware work queue each; the driver's default is 8 per device, which
+  // serialises lanes that share a queue (measured: 16 lanes 1.40 -> 0.63 ms/registration with 32).
+  // Only effective if the CUDA context of this process has not been created yet; never overrides.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return nullptr;
   if (cudaSetDevice(device) != cudaSuccess) return nullptr;
   fccf_ctx* ctx = new fccf_ctx();
   ctx->device = device;
   if (params) ctx->p = *params; else fccf_default_params(&ctx->p);
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
-  if (cudaMalloc(&ctx->d_st, sizeof(PipeState)) != cudaSuccess || cudaMallocHost(&ctx->h_st, sizeof(PipeState)) != cudaSuccess) { delete ctx; return nullptr; }
-  cudaMemset(ctx->d_st, 0, sizeof(PipeState));
-  for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
-  for (int i = 0; i < 8; i++) cudaEventCreate(&ctx->sev[i]);
+  if (ctx->p.batch_lanes > 0) ctx->max_lanes = ctx->p.batch_lanes > 64 ? 64 : ctx->p.batch_lanes;
+  Lane* L = nullptr;
+  if (lane_create(ctx, &L) != FCCF_OK) { delete ctx; return nullptr; }
+  ctx->lanes.push_back(L);
+  ctx->stream = L->stream;
   return ctx;
 }
 
 void fccf_destroy(fccf_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  for (int c = 0; c < 2; c++) { if (ctx->cloud_arena[c].base) cudaFree(ctx->cloud_arena[c].base); if (ctx->d_raw[c]) cudaFree(ctx->d_raw[c]); }
-  if (ctx->hyp_arena.base) cudaFree(ctx->hyp_arena.base);
+  for (Lane* L : ctx->lanes) lane_destroy(L);
   if (ctx->sc_arena.base) cudaFree(ctx->sc_arena.base);
   if (ctx->d_sc_s1) cudaFree(ctx->d_sc_s1);
   if (ctx->d_sc_s2) cudaFree(ctx->d_sc_s2);
@@ -180,28 +221,28 @@ void fccf_destroy(fccf_ctx* ctx) {
   if (ctx->d_sc_scores) cudaFree(ctx->d_sc_scores);
   if (ctx->d_sc_ss) cudaFree(ctx->d_sc_ss);
   if (ctx->d_sc_n) cudaFree(ctx->d_sc_n);
-  if (ctx->d_st) cudaFree(ctx->d_st);
-  if (ctx->h_st) cudaFreeHost(ctx->h_st);
-  for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->ev[i]);
-  for (int i = 0; i < 8; i++) cudaEventDestroy(ctx->sev[i]);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->d_sc_best) cudaFree(ctx->d_sc_best);
   delete ctx;
 }
 
 const char* fccf_last_error(const fccf_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no usable CUDA device)"; }
 int fccf_set_params(fccf_ctx* ctx, const fccf_params* params) { if (!ctx || !params) return FCCF_ERR_ARG; ctx->p = *params; return FCCF_OK; }
-uint64_t fccf_launch_count(const fccf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t fccf_launch_count(const fccf_ctx* ctx) {
+  if (!ctx) return 0;
+  uint64_t n = ctx->launches;
+  for (const Lane* L : ctx->lanes) n += L->launches;
+  return n;
+}
 void* fccf_stream_handle(const fccf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 }  // extern "C"
 
-static Work make_work(fccf_ctx* ctx, float leaf) {
-  Work w; w.c[0] = ctx->c[0]; w.c[1] = ctx->c[1]; w.st = ctx->d_st; w.p = ctx->p; w.leaf = leaf;
+static Work make_work(fccf_ctx* ctx, Lane* L, float leaf) {
+  Work w; w.c[0] = L->c[0]; w.c[1] = L->c[1]; w.st = L->d_st; w.p = ctx->p; w.leaf = leaf;
   return w;
 }
 
-static int check_status(fccf_ctx* ctx) {
-  int st = ctx->h_st->status;
+static int check_status(fccf_ctx* ctx, int st) {
   if (st == 0) return FCCF_OK;
   char b[256];
   snprintf(b, sizeof b, "device status 0x%x:%s%s%s%s%s", st, (st & ST_OCT_DEPTH) ? " octree deeper than the 32-bit Morton key" : "",
@@ -211,117 +252,169 @@ static int check_status(fccf_ctx* ctx) {
   return FCCF_ERR_CAPACITY;
 }
 
-// the whole registration with both raw clouds resident in d_raw[0] (TAR) / d_raw[1] (SRC)
-static int run_pipeline(fccf_ctx* ctx, int n_tar, int n_src, float leaf, float T_out[16], fccf_timing* tm, bool had_h2d) {
-  cudaStream_t s = ctx->stream;
-  Work w = make_work(ctx, leaf);
-  uint64_t l0 = ctx->launches;
-  launch_init_state(s, ctx->d_st, n_tar, n_src, &ctx->launches);
-  launch_voxelgrid(s, w, 0, 2, &ctx->launches);            // main(): FCCF.cpp:1668-1678
-  CK(cudaEventRecord(ctx->ev[2], s));
-  launch_voxelgrid(s, w, 1, 2, &ctx->launches);            // FCCF.cpp:1377-1387
-  cudaEventRecord(ctx->sev[0], s);
-  launch_planes(s, w, 2, 1, &ctx->launches);               // FCCF.cpp:1400-1401
-  cudaEventRecord(ctx->sev[1], s);
-  launch_hypotheses(s, w, ctx->h, &ctx->launches);         // FCCF.cpp:1406-1427, 1439-1462
-  cudaEventRecord(ctx->sev[2], s);
-  launch_cluster(s, w, ctx->h, &ctx->launches);            // FCCF.cpp:1464-1466
-  cudaEventRecord(ctx->sev[3], s);
-  launch_quick_verify(s, w, ctx->h, &ctx->launches);       // FCCF.cpp:1468-1494
-  cudaEventRecord(ctx->sev[4], s);
-  launch_fine_verify_fuse(s, w, ctx->h, &ctx->launches);   // FCCF.cpp:1499-1606
-  CK(cudaEventRecord(ctx->ev[3], s));
-  CK(cudaMemcpyAsync(ctx->h_st, ctx->d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(ctx->ev[4], s));
-  CK(cudaStreamSynchronize(s));
+// Enqueues one whole registration on the lane's stream (no host synchronisation): optional H2D of both
+// raw clouds, every kernel of main() + computer_transform_guess, and the read-back of the result block.
+// tar/src: host pointers (host_in) or device pointers.
+static int lane_enqueue(fccf_ctx* ctx, Lane* L, const float* src, size_t n_src, const float* tar, size_t n_tar, float leaf, bool host_in) {
+  cudaStream_t s = L->stream;
+  L->l0 = L->launches; L->had_h2d = host_in;
+  CK(cudaEventRecord(L->ev[0], s));
+  if (host_in) {
+    if (n_tar) CK(cudaMemcpyAsync(L->d_raw[0], tar, n_tar * 12, cudaMemcpyHostToDevice, s));
+    if (n_src) CK(cudaMemcpyAsync(L->d_raw[1], src, n_src * 12, cudaMemcpyHostToDevice, s));
+    L->last_h2d = (n_tar + n_src) * 12;
+    L->c[0].raw = L->d_raw[0]; L->c[1].raw = L->d_raw[1];
+  } else { L->c[0].raw = tar; L->c[1].raw = src; L->last_h2d = 0; }
+  CK(cudaEventRecord(L->ev[1], s));
+  Work w = make_work(ctx, L, leaf);
+  launch_init_state(s, L->d_st, (int)n_tar, (int)n_src, &L->launches);
+  launch_voxelgrid(s, w, 0, 2, &L->launches);            // main(): FCCF.cpp:1668-1678
+  CK(cudaEventRecord(L->ev[2], s));
+  launch_voxelgrid(s, w, 1, 2, &L->launches);            // FCCF.cpp:1377-1387
+  cudaEventRecord(L->sev[0], s);
+  launch_planes(s, w, 2, 1, &L->launches);               // FCCF.cpp:1400-1401
+  cudaEventRecord(L->sev[1], s);
+  launch_hypotheses(s, w, L->h, &L->launches);           // FCCF.cpp:1406-1427, 1439-1462
+  cudaEventRecord(L->sev[2], s);
+  launch_cluster(s, w, L->h, &L->launches);              // FCCF.cpp:1464-1466
+  cudaEventRecord(L->sev[3], s);
+  launch_quick_verify(s, w, L->h, &L->launches);         // FCCF.cpp:1468-1494
+  cudaEventRecord(L->sev[4], s);
+  launch_fine_verify_fuse(s, w, L->h, &L->launches);     // FCCF.cpp:1499-1606
+  CK(cudaEventRecord(L->ev[3], s));
+  CK(cudaMemcpyAsync(L->h_st, L->d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(L->ev[4], s));
+  L->busy = true;
+  return FCCF_OK;
+}
+
+// Waits for the lane's registration, returns the matrix and (optionally) its device timings.
+static int lane_finish(fccf_ctx* ctx, Lane* L, float T_out[16], fccf_timing* tm) {
+  CK(cudaStreamSynchronize(L->stream));
   CK(cudaGetLastError());
-  ctx->have_run = true; ctx->leaf = leaf;
-  for (int i = 0; i < 16; i++) T_out[i] = ctx->h_st->T_final[i];
+  L->busy = false;
+  L->c[0].raw = L->d_raw[0]; L->c[1].raw = L->d_raw[1];
+  for (int i = 0; i < 16; i++) T_out[i] = L->h_st->T_final[i];
   if (tm) {
     memset(tm, 0, sizeof *tm);
-    if (had_h2d) cudaEventElapsedTime(&tm->h2d_ms, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&tm->downsample_ms, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&tm->pipeline_ms, ctx->ev[2], ctx->ev[3]);
-    cudaEventElapsedTime(&tm->d2h_ms, ctx->ev[3], ctx->ev[4]);
-    cudaEventElapsedTime(&tm->total_ms, ctx->ev[0], ctx->ev[4]);
-    tm->n_launches = (int)(ctx->launches - l0);
-    tm->h2d_bytes = had_h2d ? (unsigned long long)ctx->last_h2d : 0ull;
+    if (L->had_h2d) cudaEventElapsedTime(&tm->h2d_ms, L->ev[0], L->ev[1]);
+    cudaEventElapsedTime(&tm->downsample_ms, L->ev[1], L->ev[2]);
+    cudaEventElapsedTime(&tm->pipeline_ms, L->ev[2], L->ev[3]);
+    cudaEventElapsedTime(&tm->d2h_ms, L->ev[3], L->ev[4]);
+    cudaEventElapsedTime(&tm->total_ms, L->ev[0], L->ev[4]);
+    tm->n_launches = (int)(L->launches - L->l0);
+    tm->h2d_bytes = (unsigned long long)L->last_h2d;
     tm->d2h_bytes = sizeof(PipeState);
     tm->stage_ms[0] = tm->downsample_ms;
-    cudaEventElapsedTime(&tm->stage_ms[1], ctx->ev[2], ctx->sev[0]);
-    for (int k = 0; k < 4; k++) cudaEventElapsedTime(&tm->stage_ms[2 + k], ctx->sev[k], ctx->sev[k + 1]);
-    cudaEventElapsedTime(&tm->stage_ms[6], ctx->sev[4], ctx->ev[3]);
+    cudaEventElapsedTime(&tm->stage_ms[1], L->ev[2], L->sev[0]);
+    for (int k = 0; k < 4; k++) cudaEventElapsedTime(&tm->stage_ms[2 + k], L->sev[k], L->sev[k + 1]);
+    cudaEventElapsedTime(&tm->stage_ms[6], L->sev[4], L->ev[3]);
   }
-  return check_status(ctx);
+  return check_status(ctx, L->h_st->status);
+}
+
+static int register_one(fccf_ctx* ctx, const float* src, size_t n_src, const float* tar, size_t n_tar, float leaf, float T_out[16], fccf_timing* timing, bool host_in) {
+  if (!ctx) return FCCF_ERR_NO_DEVICE;
+  if (!T_out || (!src && n_src) || (!tar && n_tar) || !(leaf > 0.f)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  Lane* L = ctx->lanes[0];
+  int rc = ensure_capacity(ctx, L, n_tar, n_src);
+  if (rc) return rc;
+  rc = lane_enqueue(ctx, L, src, n_src, tar, n_tar, leaf, host_in);
+  if (rc) return rc;
+  rc = lane_finish(ctx, L, T_out, timing);
+  ctx->have_run = true; ctx->leaf = leaf;
+  return rc;
+}
+
+// Batch of independent pairs: up to max_lanes registrations in flight, one lane (stream + workspace)
+// each; pair b waits only for the lane it reuses.  timing: device times summed over the pairs, and
+// total_ms = host wall clock of the whole batch.
+static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, const size_t* n_src, const float* const* tar, const size_t* n_tar,
+                         float leaf, float* T_out, fccf_timing* timing, bool host_in) {
+  if (!ctx) return FCCF_ERR_NO_DEVICE;
+  if (n_pairs < 0 || (n_pairs && (!src || !tar || !n_src || !n_tar || !T_out)) || !(leaf > 0.f)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  fccf_timing acc; memset(&acc, 0, sizeof acc);
+  if (n_pairs == 0) { if (timing) *timing = acc; return FCCF_OK; }
+  int nl = std::min(ctx->max_lanes, n_pairs);
+  size_t nmax = 0;
+  for (int b = 0; b < n_pairs; b++) { if ((!src[b] && n_src[b]) || (!tar[b] && n_tar[b])) { ctx->err = "bad argument"; return FCCF_ERR_ARG; } nmax = std::max(nmax, std::max(n_src[b], n_tar[b])); }
+  while ((int)ctx->lanes.size() < nl) { Lane* L = nullptr; int rc = lane_create(ctx, &L); if (rc) return rc; ctx->lanes.push_back(L); }
+  for (int l = 0; l < nl; l++) { int rc = ensure_capacity(ctx, ctx->lanes[l], nmax, nmax); if (rc) return rc; }
+  // device time of the whole batch: an event on lane 0 before the first enqueue, and one on lane 0
+  // after it has waited for the last registration of every lane
+  Lane* Z = ctx->lanes[0];
+  auto t0 = std::chrono::steady_clock::now();
+  CK(cudaEventRecord(Z->sev[6], Z->stream));
+  int worst = FCCF_OK;
+  float enq_ms = 0.f;
+  auto collect = [&](Lane* L) -> int {
+    fccf_timing t;
+    int rc = lane_finish(ctx, L, T_out + 16 * (size_t)L->pair, &t);
+    acc.h2d_ms += t.h2d_ms; acc.downsample_ms += t.downsample_ms; acc.pipeline_ms += t.pipeline_ms; acc.d2h_ms += t.d2h_ms; acc.n_launches += t.n_launches;
+    acc.h2d_bytes += t.h2d_bytes; acc.d2h_bytes += t.d2h_bytes; for (int k = 0; k < 8; k++) acc.stage_ms[k] += t.stage_ms[k];
+    return rc;
+  };
+  for (int b = 0; b < n_pairs; b++) {
+    Lane* L = ctx->lanes[b % nl];
+    if (L->busy) { int rc = collect(L); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc; if (rc) worst = rc; }
+    L->pair = b;
+    auto te0 = std::chrono::steady_clock::now();
+    int rc = lane_enqueue(ctx, L, src[b], n_src[b], tar[b], n_tar[b], leaf, host_in);
+    enq_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - te0).count();
+    if (rc) return rc;
+  }
+  if (getenv("FCCF_DEBUG_TIMING")) fprintf(stderr, "[fccf] batch of %d: host enqueue %.3f ms total (%.3f ms/pair)\n", n_pairs, enq_ms, enq_ms / n_pairs);
+  for (int l = 1; l < nl; l++) if (ctx->lanes[l]->busy) CK(cudaStreamWaitEvent(Z->stream, ctx->lanes[l]->ev[4], 0));
+  CK(cudaEventRecord(Z->sev[7], Z->stream));
+  for (int l = 0; l < nl; l++) if (ctx->lanes[l]->busy) { int rc = collect(ctx->lanes[l]); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc; if (rc) worst = rc; }
+  CK(cudaEventSynchronize(Z->sev[7]));
+  cudaEventElapsedTime(&acc.total_ms, Z->sev[6], Z->sev[7]);
+  acc.stage_ms[7] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (timing) *timing = acc;
+  ctx->have_run = true; ctx->leaf = leaf;    // blobs: the last pair that ran on lane 0
+  return worst;
 }
 
 extern "C" {
 
 int fccf_register(fccf_ctx* ctx, const float* src_xyz, size_t n_src, const float* tar_xyz, size_t n_tar, float leaf, float T_out[16], fccf_timing* timing) {
-  if (!ctx) return FCCF_ERR_NO_DEVICE;
-  if (!T_out || (!src_xyz && n_src) || (!tar_xyz && n_tar) || !(leaf > 0.f)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
-  CK(cudaSetDevice(ctx->device));
-  int rc = ensure_capacity(ctx, n_tar, n_src);
-  if (rc) return rc;
-  cudaStream_t s = ctx->stream;
-  CK(cudaEventRecord(ctx->ev[0], s));
-  if (n_tar) CK(cudaMemcpyAsync(ctx->d_raw[0], tar_xyz, n_tar * 12, cudaMemcpyHostToDevice, s));
-  if (n_src) CK(cudaMemcpyAsync(ctx->d_raw[1], src_xyz, n_src * 12, cudaMemcpyHostToDevice, s));
-  CK(cudaEventRecord(ctx->ev[1], s));
-  ctx->last_h2d = (n_tar + n_src) * 12;
-  return run_pipeline(ctx, (int)n_tar, (int)n_src, leaf, T_out, timing, true);
+  return register_one(ctx, src_xyz, n_src, tar_xyz, n_tar, leaf, T_out, timing, true);
 }
 
 int fccf_register_device(fccf_ctx* ctx, const float* d_src_xyz, size_t n_src, const float* d_tar_xyz, size_t n_tar, float leaf, float T_out[16], fccf_timing* timing) {
-  if (!ctx) return FCCF_ERR_NO_DEVICE;
-  if (!T_out || !(leaf > 0.f)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
-  CK(cudaSetDevice(ctx->device));
-  int rc = ensure_capacity(ctx, n_tar, n_src);
-  if (rc) return rc;
-  cudaStream_t s = ctx->stream;
-  ctx->c[0].raw = d_tar_xyz; ctx->c[1].raw = d_src_xyz;
-  CK(cudaEventRecord(ctx->ev[0], s));
-  CK(cudaEventRecord(ctx->ev[1], s));
-  rc = run_pipeline(ctx, (int)n_tar, (int)n_src, leaf, T_out, timing, false);
-  ctx->c[0].raw = ctx->d_raw[0]; ctx->c[1].raw = ctx->d_raw[1];
-  return rc;
+  return register_one(ctx, d_src_xyz, n_src, d_tar_xyz, n_tar, leaf, T_out, timing, false);
 }
 
 int fccf_register_batch(fccf_ctx* ctx, int n_pairs, const float* const* src_xyz, const size_t* n_src, const float* const* tar_xyz, const size_t* n_tar,
                         float leaf, float* T_out, fccf_timing* timing) {
-  if (!ctx) return FCCF_ERR_NO_DEVICE;
-  fccf_timing acc; memset(&acc, 0, sizeof acc);
-  int worst = FCCF_OK;
-  for (int b = 0; b < n_pairs; b++) {
-    fccf_timing t;
-    int rc = fccf_register(ctx, src_xyz[b], n_src[b], tar_xyz[b], n_tar[b], leaf, T_out + 16 * (size_t)b, &t);
-    if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc;
-    if (rc) worst = rc;
-    acc.h2d_ms += t.h2d_ms; acc.downsample_ms += t.downsample_ms; acc.pipeline_ms += t.pipeline_ms; acc.d2h_ms += t.d2h_ms; acc.total_ms += t.total_ms; acc.n_launches += t.n_launches;
-    acc.h2d_bytes += t.h2d_bytes; acc.d2h_bytes += t.d2h_bytes; for (int k = 0; k < 8; k++) acc.stage_ms[k] += t.stage_ms[k];
-  }
-  if (timing) *timing = acc;
-  return worst;
+  return register_many(ctx, n_pairs, src_xyz, n_src, tar_xyz, n_tar, leaf, T_out, timing, true);
+}
+
+int fccf_register_batch_device(fccf_ctx* ctx, int n_pairs, const float* const* d_src_xyz, const size_t* n_src, const float* const* d_tar_xyz, const size_t* n_tar,
+                               float leaf, float* T_out, fccf_timing* timing) {
+  return register_many(ctx, n_pairs, d_src_xyz, n_src, d_tar_xyz, n_tar, leaf, T_out, timing, false);
 }
 
 int fccf_voxelgrid(fccf_ctx* ctx, const float* xyz, size_t n, float leaf, float* out_xyz, int64_t* out_cell, int32_t* out_cnt, size_t* n_out) {
   if (!ctx) return FCCF_ERR_NO_DEVICE;
   if (!n_out || (!xyz && n) || !(leaf > 0.f)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
-  int rc = ensure_capacity(ctx, n, 0);
+  int rc = ensure_capacity(ctx, ctx->lanes[0], n, 0);
   if (rc) return rc;
   cudaStream_t s = ctx->stream;
-  if (n) CK(cudaMemcpyAsync(ctx->d_raw[0], xyz, n * 12, cudaMemcpyHostToDevice, s));
-  Work w = make_work(ctx, leaf);
-  launch_init_state(s, ctx->d_st, (int)n, 0, &ctx->launches);
+  if (n) CK(cudaMemcpyAsync(ctx->L0().d_raw[0], xyz, n * 12, cudaMemcpyHostToDevice, s));
+  Work w = make_work(ctx, ctx->lanes[0], leaf);
+  launch_init_state(s, ctx->L0().d_st, (int)n, 0, &ctx->launches);
   launch_voxelgrid(s, w, 0, 1, &ctx->launches);
-  CK(cudaMemcpyAsync(ctx->h_st, ctx->d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->L0().h_st, ctx->L0().d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  size_t m = (size_t)ctx->h_st->vg[0][0].n_out;
+  size_t m = (size_t)ctx->L0().h_st->vg[0][0].n_out;
   *n_out = m;
-  if (m && out_xyz) CK(cudaMemcpy(out_xyz, ctx->c[0].vg_xyz[0], m * 12, cudaMemcpyDeviceToHost));
-  if (m && out_cell) CK(cudaMemcpy(out_cell, ctx->c[0].vg_cell[0], m * 8, cudaMemcpyDeviceToHost));
-  if (m && out_cnt) CK(cudaMemcpy(out_cnt, ctx->c[0].vg_cnt[0], m * 4, cudaMemcpyDeviceToHost));
+  if (m && out_xyz) CK(cudaMemcpy(out_xyz, ctx->L0().c[0].vg_xyz[0], m * 12, cudaMemcpyDeviceToHost));
+  if (m && out_cell) CK(cudaMemcpy(out_cell, ctx->L0().c[0].vg_cell[0], m * 8, cudaMemcpyDeviceToHost));
+  if (m && out_cnt) CK(cudaMemcpy(out_cnt, ctx->L0().c[0].vg_cnt[0], m * 4, cudaMemcpyDeviceToHost));
   CK(cudaGetLastError());
   ctx->have_run = false;
   return FCCF_OK;
@@ -331,21 +424,21 @@ int fccf_extract_planes(fccf_ctx* ctx, const float* xyz, size_t n, int32_t* n_fa
   if (!ctx) return FCCF_ERR_NO_DEVICE;
   if (!xyz && n) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
-  int rc = ensure_capacity(ctx, n, 0);
+  int rc = ensure_capacity(ctx, ctx->lanes[0], n, 0);
   if (rc) return rc;
   cudaStream_t s = ctx->stream;
-  Work w = make_work(ctx, 1.0f);
-  launch_init_state(s, ctx->d_st, 0, 0, &ctx->launches);
-  if (n) CK(cudaMemcpyAsync(ctx->c[0].vg_xyz[1], xyz, n * 12, cudaMemcpyHostToDevice, s));
+  Work w = make_work(ctx, ctx->lanes[0], 1.0f);
+  launch_init_state(s, ctx->L0().d_st, 0, 0, &ctx->launches);
+  if (n) CK(cudaMemcpyAsync(ctx->L0().c[0].vg_xyz[1], xyz, n * 12, cudaMemcpyHostToDevice, s));
   int nn = (int)n;
-  CK(cudaMemcpyAsync(&ctx->d_st->vg[1][0].n_out, &nn, 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(&ctx->L0().d_st->vg[1][0].n_out, &nn, 4, cudaMemcpyHostToDevice, s));
   launch_planes(s, w, 1, 1, &ctx->launches);
-  CK(cudaMemcpyAsync(ctx->h_st, ctx->d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(ctx->L0().h_st, ctx->L0().d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
-  if (n_faces) *n_faces = ctx->h_st->ft[0].F;
+  if (n_faces) *n_faces = ctx->L0().h_st->ft[0].F;
   ctx->have_run = true;
-  return check_status(ctx);
+  return check_status(ctx, ctx->L0().h_st->status);
 }
 
 static int score_prepare(fccf_ctx* ctx, const float* T, size_t n_hyp, const float* s1, size_t n1, const float* s2, size_t n2) {
@@ -363,26 +456,27 @@ static int score_prepare(fccf_ctx* ctx, const float* T, size_t n_hyp, const floa
   size_t oldT = ctx->sc_capT;
   if ((rc = grow(ctx->d_sc_T, ctx->sc_capT, 16 * n_hyp + 16))) return rc;
   if (ctx->sc_capT != oldT || !ctx->d_sc_scores) { if (ctx->d_sc_scores) CK(cudaFree(ctx->d_sc_scores)); CK(cudaMalloc(&ctx->d_sc_scores, ctx->sc_capT / 16 * 4 + 64)); }
-  int cap_hash = 1024; while ((size_t)cap_hash < 2 * n1) cap_hash <<= 1;
-  if (cap_hash > ctx->sc_cap_hash) {
+  if ((int)std::max<size_t>(n1, 1024) > ctx->sc_cap_hash) {     // sc_cap_hash: capacity in static points of the stand-alone table
     if (ctx->sc_arena.base) CK(cudaFree(ctx->sc_arena.base));
     ctx->sc_arena = Arena();
-    int rows = (int)std::min<size_t>(148, std::max<size_t>(1, ((size_t)1 << 29) / ((size_t)cap_hash * 4)));
-    size_t bytes = (size_t)cap_hash * 12 + (size_t)cap_hash * 4 * rows + 4096;
+    int capn = (int)std::max<size_t>(n1, 1024);
+    int rows = (int)std::min<size_t>(148 * 4, std::max<size_t>(4, ((size_t)1 << 30) / ((size_t)capn * 4)));
+    rows &= ~3;
+    size_t bytes = score_ws_layout(nullptr, nullptr, capn, rows);
     CK(cudaMalloc(&ctx->sc_arena.base, bytes));
-    ctx->sc_ws.keys = ctx->sc_arena.take<u64>(cap_hash); ctx->sc_ws.s_cnt = ctx->sc_arena.take<int>(cap_hash); ctx->sc_ws.t_cnt = ctx->sc_arena.take<int>((size_t)cap_hash * rows);
-    ctx->sc_ws.cap_hash = cap_hash; ctx->sc_ws.t_rows = rows; ctx->sc_cap_hash = cap_hash;
+    score_ws_layout(&ctx->sc_ws, ctx->sc_arena.base, capn, rows);
+    ctx->sc_cap_hash = capn;
   }
   if (!ctx->d_sc_ss) { CK(cudaMalloc(&ctx->d_sc_ss, sizeof(ScoreState))); CK(cudaMalloc(&ctx->d_sc_n, 64)); }
-  ctx->sc_ws.ss = ctx->d_sc_ss; ctx->sc_ws.status = &ctx->d_st->status;
+  ctx->sc_ws.ss = ctx->d_sc_ss; ctx->sc_ws.status = &ctx->L0().d_st->status;
   int nn[2] = {(int)n1, (int)n2};
-  CK(cudaMemsetAsync(&ctx->d_st->status, 0, 4, s));
+  CK(cudaMemsetAsync(&ctx->L0().d_st->status, 0, 4, s));
   CK(cudaMemcpyAsync(ctx->d_sc_n, nn, 8, cudaMemcpyHostToDevice, s));
   if (n1) CK(cudaMemcpyAsync(ctx->d_sc_s1, s1, n1 * 12, cudaMemcpyHostToDevice, s));
   if (n2) CK(cudaMemcpyAsync(ctx->d_sc_s2, s2, n2 * 12, cudaMemcpyHostToDevice, s));
   if (n_hyp) CK(cudaMemcpyAsync(ctx->d_sc_T, T, n_hyp * 64, cudaMemcpyHostToDevice, s));
-  launch_score_build(s, ctx->p, ctx->d_sc_s1, ctx->d_sc_n, ctx->d_sc_n + 1, (int)std::max<size_t>(n1, 1), ctx->sc_ws, &ctx->launches);
-  ctx->sc_n2 = n2;
+  launch_score_build(s, ctx->p, ctx->d_sc_s1, ctx->d_sc_n, ctx->d_sc_n + 1, ctx->sc_ws, &ctx->launches);
+  ctx->sc_n2 = n2; ctx->sc_nhyp = n_hyp;
   return FCCF_OK;
 }
 
@@ -395,11 +489,11 @@ int fccf_score_hypotheses(fccf_ctx* ctx, const float* T, size_t n_hyp, const flo
   launch_score_list(ctx->stream, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, &ctx->launches);
   if (n_hyp) CK(cudaMemcpyAsync(scores, ctx->d_sc_scores, n_hyp * 4, cudaMemcpyDeviceToHost, ctx->stream));
   int st = 0;
-  CK(cudaMemcpyAsync(&st, &ctx->d_st->status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&st, &ctx->L0().d_st->status, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
-  ctx->h_st->status = st;
-  return check_status(ctx);
+  ctx->L0().h_st->status = st;
+  return check_status(ctx, ctx->L0().h_st->status);
 }
 
 int fccf_score_hypotheses_bench(fccf_ctx* ctx, const float* T, size_t n_hyp, const float* s1_xyz, size_t n1, const float* s2_xyz, size_t n2, int repeat,
@@ -412,13 +506,28 @@ int fccf_score_hypotheses_bench(fccf_ctx* ctx, const float* T, size_t n_hyp, con
   cudaStream_t s = ctx->stream;
   for (int w = 0; w < 3; w++) launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, &ctx->launches);
   CK(cudaStreamSynchronize(s));
-  CK(cudaEventRecord(ctx->ev[0], s));
+  CK(cudaEventRecord(ctx->L0().ev[0], s));
   for (int r = 0; r < repeat; r++) launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, &ctx->launches);
-  CK(cudaEventRecord(ctx->ev[1], s));
+  CK(cudaEventRecord(ctx->L0().ev[1], s));
   CK(cudaStreamSynchronize(s));
-  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->L0().ev[0], ctx->L0().ev[1]);
   if (kernel_ms) *kernel_ms = ms / repeat;
   if (scores && n_hyp) CK(cudaMemcpy(scores, ctx->d_sc_scores, n_hyp * 4, cudaMemcpyDeviceToHost));
+  CK(cudaGetLastError());
+  return FCCF_OK;
+}
+
+int fccf_score_best(fccf_ctx* ctx, size_t index_base, int64_t* packed_host, int64_t* packed_device) {
+  if (!ctx) return FCCF_ERR_NO_DEVICE;
+  if (!ctx->d_sc_scores || (!packed_host && !packed_device)) { ctx->err = "bad argument / no previous fccf_score_hypotheses call"; return FCCF_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->d_sc_best) CK(cudaMalloc(&ctx->d_sc_best, 8));
+  launch_score_best(ctx->stream, ctx->d_sc_scores, (int)ctx->sc_nhyp, (long long)index_base, ctx->d_sc_best, &ctx->launches);
+  if (packed_device) CK(cudaMemcpyAsync(packed_device, ctx->d_sc_best, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  long long h = 0;
+  if (packed_host) CK(cudaMemcpyAsync(&h, ctx->d_sc_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (packed_host) *packed_host = (int64_t)h;
   CK(cudaGetLastError());
   return FCCF_OK;
 }
@@ -480,7 +589,7 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   std::string name(name_c);
-  const PipeState& st = *ctx->h_st;
+  const PipeState& st = *ctx->L0().h_st;
   std::vector<char> out; int dt = FCCF_F32;
   auto fetch = [&](const void* dptr, size_t nbytes) -> std::vector<char> {
     std::vector<char> v(nbytes);
@@ -493,95 +602,95 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
   int ci = (last == '1') ? 0 : ((last == '2') ? 1 : -1);       // cloud tag
   int ti = (last >= '0' && last <= '2') ? last - '0' : -1;      // type tag
   bool ok = true;
-  if ((stem == "vg1_xyz" || stem == "vg2_xyz") && ci >= 0) { int sgi = stem[2] - '1'; out = fetch(ctx->c[ci].vg_xyz[sgi], (size_t)st.vg[sgi][ci].n_out * 12); dt = FCCF_F32; }
-  else if ((stem == "vg1_cell" || stem == "vg2_cell") && ci >= 0) { int sgi = stem[2] - '1'; out = fetch(ctx->c[ci].vg_cell[sgi], (size_t)st.vg[sgi][ci].n_out * 8); dt = FCCF_I64; }
-  else if ((stem == "vg1_cnt" || stem == "vg2_cnt") && ci >= 0) { int sgi = stem[2] - '1'; out = fetch(ctx->c[ci].vg_cnt[sgi], (size_t)st.vg[sgi][ci].n_out * 4); dt = FCCF_I32; }
+  if ((stem == "vg1_xyz" || stem == "vg2_xyz") && ci >= 0) { int sgi = stem[2] - '1'; out = fetch(ctx->L0().c[ci].vg_xyz[sgi], (size_t)st.vg[sgi][ci].n_out * 12); dt = FCCF_F32; }
+  else if ((stem == "vg1_cell" || stem == "vg2_cell") && ci >= 0) { int sgi = stem[2] - '1'; out = fetch(ctx->L0().c[ci].vg_cell[sgi], (size_t)st.vg[sgi][ci].n_out * 8); dt = FCCF_I64; }
+  else if ((stem == "vg1_cnt" || stem == "vg2_cnt") && ci >= 0) { int sgi = stem[2] - '1'; out = fetch(ctx->L0().c[ci].vg_cnt[sgi], (size_t)st.vg[sgi][ci].n_out * 4); dt = FCCF_I32; }
   else if (stem == "cloud_centroid" && ci >= 0) put(st.oct[ci].cc, 12, FCCF_F32);
   else if (stem == "oct_min" && ci >= 0) put(st.oct[ci].mn, 24, FCCF_F64);
   else if (stem == "oct_depth" && ci >= 0) put(&st.oct[ci].depth, 4, FCCF_I32);
   else if ((stem == "vox_key" || stem == "vox_cnt" || stem == "vox_flag" || stem == "vox_plane") && ci >= 0) {
     int V = st.oct[ci].V;
-    std::vector<char> rec = fetch(ctx->c[ci].vox_rec, (size_t)V * 48);
+    std::vector<char> rec = fetch(ctx->L0().c[ci].vox_rec, (size_t)V * 48);
     const float* r = (const float*)rec.data();
     if (stem == "vox_key") { std::vector<int> k(3 * (size_t)V); for (int v = 0; v < V; v++) for (int a = 0; a < 3; a++) memcpy(&k[3 * v + a], &r[12 * v + 9 + a], 4); put(k.data(), k.size() * 4, FCCF_I32); }
     else if (stem == "vox_cnt") { std::vector<int> k(V); for (int v = 0; v < V; v++) k[v] = (int)r[12 * v + 7]; put(k.data(), k.size() * 4, FCCF_I32); }
     else if (stem == "vox_flag") { std::vector<int> k(V); for (int v = 0; v < V; v++) k[v] = (int)r[12 * v + 8]; put(k.data(), k.size() * 4, FCCF_I32); }
     else { std::vector<float> k(8 * (size_t)V); for (int v = 0; v < V; v++) { for (int a = 0; a < 7; a++) k[8 * v + a] = r[12 * v + a]; k[8 * v + 7] = r[12 * v + 8] > 0 ? r[12 * v + 7] : 0.f; } put(k.data(), k.size() * 4, FCCF_F32); }
   }
-  else if (stem == "vox_pidx" && ci >= 0) { out = fetch(ctx->c[ci].idxA, (size_t)st.oct[ci].n * 4); dt = FCCF_I32; }
-  else if (stem == "sub" && ci >= 0) { out = fetch(ctx->c[ci].sub, (size_t)st.oct[ci].S * 12); dt = FCCF_F32; }
+  else if (stem == "vox_pidx" && ci >= 0) { out = fetch(ctx->L0().c[ci].idxA, (size_t)st.oct[ci].n * 4); dt = FCCF_I32; }
+  else if (stem == "sub" && ci >= 0) { out = fetch(ctx->L0().c[ci].sub, (size_t)st.oct[ci].S * 12); dt = FCCF_F32; }
   else if (stem == "pvox" && ci >= 0) {
-    int Vp = st.oct[ci].Vp; std::vector<char> raw = fetch(ctx->c[ci].pvox, (size_t)Vp * 32); const float* r = (const float*)raw.data();
+    int Vp = st.oct[ci].Vp; std::vector<char> raw = fetch(ctx->L0().c[ci].pvox, (size_t)Vp * 32); const float* r = (const float*)raw.data();
     std::vector<float> k(7 * (size_t)Vp); for (int v = 0; v < Vp; v++) for (int a = 0; a < 7; a++) k[7 * v + a] = r[8 * v + a];
     put(k.data(), k.size() * 4, FCCF_F32);
   }
-  else if (stem == "grow_label" && ci >= 0) { out = fetch(ctx->c[ci].grow_label, (size_t)st.oct[ci].Vp * 4); dt = FCCF_I32; }
-  else if (stem == "merge_label" && ci >= 0) { out = fetch(ctx->c[ci].merge_label, (size_t)st.oct[ci].Vp * 4); dt = FCCF_I32; }
+  else if (stem == "grow_label" && ci >= 0) { out = fetch(ctx->L0().c[ci].grow_label, (size_t)st.oct[ci].Vp * 4); dt = FCCF_I32; }
+  else if (stem == "merge_label" && ci >= 0) { out = fetch(ctx->L0().c[ci].merge_label, (size_t)st.oct[ci].Vp * 4); dt = FCCF_I32; }
   else if (stem == "n_stage1_faces" && ci >= 0) put(&st.oct[ci].F1, 4, FCCF_I32);
   else if (stem == "face_plane" && ci >= 0) { std::vector<float> k; for (int f = 0; f < st.ft[ci].F; f++) for (int a = 0; a < 7; a++) k.push_back(st.ft[ci].plane[f][a]); put(k.data(), k.size() * 4, FCCF_F32); }
   else if (stem == "face_nvox" && ci >= 0) { std::vector<int> k; for (int f = 0; f < st.ft[ci].F; f++) k.push_back((int)st.ft[ci].plane[f][7]); put(k.data(), k.size() * 4, FCCF_I32); }
   else if (stem == "face_id" && ci >= 0) put(st.ft[ci].id, (size_t)st.ft[ci].F * 4, FCCF_I32);
   else if (stem == "face_theta" && ci >= 0) put(st.ft[ci].theta, (size_t)st.ft[ci].F * 8, FCCF_F64);
-  else if (stem == "face_off" && ci >= 0) { out = fetch(ctx->c[ci].face_off, (size_t)(st.ft[ci].F + 1) * 4); dt = FCCF_I32; }
+  else if (stem == "face_off" && ci >= 0) { out = fetch(ctx->L0().c[ci].face_off, (size_t)(st.ft[ci].F + 1) * 4); dt = FCCF_I32; }
   else if (stem == "face_vox" && ci >= 0) {
-    std::vector<char> off = fetch(ctx->c[ci].face_off, (size_t)(st.ft[ci].F + 1) * 4);
+    std::vector<char> off = fetch(ctx->L0().c[ci].face_off, (size_t)(st.ft[ci].F + 1) * 4);
     int tot = ((const int*)off.data())[st.ft[ci].F];
-    out = fetch(ctx->c[ci].face_vox, (size_t)tot * 4); dt = FCCF_I32;
+    out = fetch(ctx->L0().c[ci].face_vox, (size_t)tot * 4); dt = FCCF_I32;
   }
   else if (stem == "base" && ci >= 0) { std::vector<int> k; const BaseTable& b = st.base[ci]; for (int i = 0; i < b.B; i++) { k.push_back(b.i[i]); k.push_back(b.j[i]); k.push_back(b.type[i]); } put(k.data(), k.size() * 4, FCCF_I32); }
   else if (stem == "base_angle" && ci >= 0) put(st.base[ci].angle, (size_t)st.base[ci].B * 4, FCCF_F32);
   else if (name == "matches") {
     int NM = st.n_match, B2 = st.base[1].B;
-    std::vector<char> raw = fetch(ctx->h.match_cnt, (size_t)NM * 4); const int* mc = (const int*)raw.data();
+    std::vector<char> raw = fetch(ctx->L0().h.match_cnt, (size_t)NM * 4); const int* mc = (const int*)raw.data();
     std::vector<int> k; for (int i = 0; i < NM; i++) if (mc[i] > 0) { k.push_back(i / B2); k.push_back(i % B2); k.push_back(mc[i]); }
     put(k.data(), k.size() * 4, FCCF_I32);
   }
   else if (name == "n_hyp") put(st.n_hyp, 12, FCCF_I32);
   else if (name == "n_centres") put(st.n_centre, 12, FCCF_I32);
   else if (name == "cluster_num") put(st.cluster_num, 12, FCCF_I32);
-  else if (stem == "hyp" && ti >= 0) { out = fetch(ctx->h.hyp_T + (size_t)st.hyp_off[ti] * 12, (size_t)st.n_hyp[ti] * 48); dt = FCCF_F32; }
+  else if (stem == "hyp" && ti >= 0) { out = fetch(ctx->L0().h.hyp_T + (size_t)st.hyp_off[ti] * 12, (size_t)st.n_hyp[ti] * 48); dt = FCCF_F32; }
   else if (stem == "hyp_qt" && ti >= 0) {
-    int n = st.n_hyp[ti]; std::vector<char> raw = fetch(ctx->h.hyp_qt + (size_t)st.hyp_off[ti] * 8, (size_t)n * 32); const float* r = (const float*)raw.data();
+    int n = st.n_hyp[ti]; std::vector<char> raw = fetch(ctx->L0().h.hyp_qt + (size_t)st.hyp_off[ti] * 8, (size_t)n * 32); const float* r = (const float*)raw.data();
     std::vector<float> k(7 * (size_t)n); for (int i = 0; i < n; i++) for (int a = 0; a < 7; a++) k[7 * i + a] = r[8 * i + a];
     put(k.data(), k.size() * 4, FCCF_F32);
   }
   else if ((stem == "cluster_seed_sorted" || stem == "cluster_size_sorted") && ti >= 0) {
     int K = st.n_seeds[ti]; size_t base = (size_t)st.hyp_off[ti];
-    std::vector<char> pk = fetch(ctx->h.c_key + base, (size_t)K * 4), pp = fetch(ctx->h.c_perm + base, (size_t)K * 4), ps = fetch(ctx->h.c_seeds + base, (size_t)K * 4);
+    std::vector<char> pk = fetch(ctx->L0().h.c_key + base, (size_t)K * 4), pp = fetch(ctx->L0().h.c_perm + base, (size_t)K * 4), ps = fetch(ctx->L0().h.c_seeds + base, (size_t)K * 4);
     if (stem == "cluster_size_sorted") { out = pk; }
     else { std::vector<int> k(K); for (int i = 0; i < K; i++) k[i] = ((const int*)ps.data())[((const int*)pp.data())[i]]; put(k.data(), k.size() * 4, FCCF_I32); }
     dt = FCCF_I32;
   }
   else if (stem == "centre" && ti >= 0) {
-    int n = st.n_centre[ti]; std::vector<char> raw = fetch(ctx->h.centre + (size_t)ti * FCCF_MAXCENTRE * 8, (size_t)n * 32); const float* r = (const float*)raw.data();
+    int n = st.n_centre[ti]; std::vector<char> raw = fetch(ctx->L0().h.centre + (size_t)ti * FCCF_MAXCENTRE * 8, (size_t)n * 32); const float* r = (const float*)raw.data();
     std::vector<float> k(7 * (size_t)n); for (int i = 0; i < n; i++) for (int a = 0; a < 7; a++) k[7 * i + a] = r[8 * i + a];
     put(k.data(), k.size() * 4, FCCF_F32);
   }
-  else if (stem == "qv_score" && ti >= 0) { out = fetch(ctx->h.qv_score + (size_t)ti * FCCF_MAXCENTRE, (size_t)st.n_centre[ti] * 4); dt = FCCF_F32; }
-  else if (stem == "qv_T" && ti >= 0) { out = fetch(ctx->h.qv_T + (size_t)ti * FCCF_MAXCENTRE * 16, (size_t)st.n_centre[ti] * 64); dt = FCCF_F32; }
-  else if (stem == "qv_iters" && ti >= 0) { out = fetch(ctx->h.qv_iters + (size_t)ti * FCCF_MAXCENTRE, (size_t)st.n_centre[ti] * 4); dt = FCCF_I32; }
+  else if (stem == "qv_score" && ti >= 0) { out = fetch(ctx->L0().h.qv_score + (size_t)ti * FCCF_MAXCENTRE, (size_t)st.n_centre[ti] * 4); dt = FCCF_F32; }
+  else if (stem == "qv_T" && ti >= 0) { out = fetch(ctx->L0().h.qv_T + (size_t)ti * FCCF_MAXCENTRE * 16, (size_t)st.n_centre[ti] * 64); dt = FCCF_F32; }
+  else if (stem == "qv_iters" && ti >= 0) { out = fetch(ctx->L0().h.qv_iters + (size_t)ti * FCCF_MAXCENTRE, (size_t)st.n_centre[ti] * 4); dt = FCCF_I32; }
   else if ((stem == "qv_pairs" || stem == "qv_pair_off") && ti >= 0) {
     int n = st.n_centre[ti];
-    std::vector<char> np = fetch(ctx->h.qv_npair + (size_t)ti * FCCF_MAXCENTRE, (size_t)n * 4), pr = fetch(ctx->h.qv_pairs + (size_t)ti * FCCF_MAXCENTRE * 32, (size_t)n * 128);
+    std::vector<char> np = fetch(ctx->L0().h.qv_npair + (size_t)ti * FCCF_MAXCENTRE, (size_t)n * 4), pr = fetch(ctx->L0().h.qv_pairs + (size_t)ti * FCCF_MAXCENTRE * 32, (size_t)n * 128);
     std::vector<int> pairs, off;
     for (int i = 0; i < n; i++) { off.push_back((int)pairs.size() / 2); int c = ((const int*)np.data())[i]; for (int k = 0; k < 2 * c; k++) pairs.push_back(((const int*)pr.data())[32 * i + k]); }
     off.push_back((int)pairs.size() / 2);
     if (stem == "qv_pairs") put(pairs.data(), pairs.size() * 4, FCCF_I32); else put(off.data(), off.size() * 4, FCCF_I32);
   }
-  else if (stem == "top_T" && ti >= 0) { out = fetch(ctx->h.top_T + (size_t)ti * FCCF_TOPK * 16, (size_t)st.n_top[ti] * 64); dt = FCCF_F32; }
-  else if (stem == "top_s1" && ti >= 0) { out = fetch(ctx->h.top_s1 + (size_t)ti * FCCF_TOPK, (size_t)st.n_top[ti] * 4); dt = FCCF_F32; }
-  else if (stem == "top_s2" && ti >= 0) { out = fetch(ctx->h.top_s2 + (size_t)ti * FCCF_TOPK, (size_t)st.n_top[ti] * 4); dt = FCCF_F32; }
-  else if (stem == "top_centre" && ti >= 0) { out = fetch(ctx->h.top_centre + (size_t)ti * FCCF_TOPK, (size_t)st.n_top[ti] * 4); dt = FCCF_I32; }
+  else if (stem == "top_T" && ti >= 0) { out = fetch(ctx->L0().h.top_T + (size_t)ti * FCCF_TOPK * 16, (size_t)st.n_top[ti] * 64); dt = FCCF_F32; }
+  else if (stem == "top_s1" && ti >= 0) { out = fetch(ctx->L0().h.top_s1 + (size_t)ti * FCCF_TOPK, (size_t)st.n_top[ti] * 4); dt = FCCF_F32; }
+  else if (stem == "top_s2" && ti >= 0) { out = fetch(ctx->L0().h.top_s2 + (size_t)ti * FCCF_TOPK, (size_t)st.n_top[ti] * 4); dt = FCCF_F32; }
+  else if (stem == "top_centre" && ti >= 0) { out = fetch(ctx->L0().h.top_centre + (size_t)ti * FCCF_TOPK, (size_t)st.n_top[ti] * 4); dt = FCCF_I32; }
   else if ((stem == "fv_counts" || stem == "fv_off") && ti >= 0) {
     // per-voxel (s,t) of every fine-verified hypothesis of this type, rows sorted lexicographically
-    ScoreWS ws; ws.keys = ctx->h.fv_keys; ws.s_cnt = ctx->h.fv_s; ws.t_cnt = ctx->h.fv_t; ws.cap_hash = ctx->h.cap_hash; ws.t_rows = 3 * FCCF_TOPK; ws.ss = &ctx->d_st->fv; ws.status = &ctx->d_st->status;
-    int cap_rows = std::max(st.fv.cap_eff, 1);
+    ScoreWS ws = ctx->L0().h.fv; ws.ss = &ctx->L0().d_st->fv; ws.status = &ctx->L0().d_st->status;
+    int cap_rows = std::max(st.fv.n_occ, 1);
     int* d_rows = nullptr; int* d_n = nullptr;
     CK(cudaMalloc(&d_rows, (size_t)cap_rows * 20)); CK(cudaMalloc(&d_n, 4));
     std::vector<int> all, off;
     for (int k = 0; k < st.n_top[ti]; k++) {
       CK(cudaMemsetAsync(d_n, 0, 4, ctx->stream));
-      launch_score_dump(ctx->stream, ctx->p, ctx->h.top_T + ((size_t)ti * FCCF_TOPK + k) * 16, ctx->c[1].sub, ws, d_rows, cap_rows, d_n, &ctx->launches);
+      launch_score_dump(ctx->stream, ctx->p, ctx->L0().h.top_T + ((size_t)ti * FCCF_TOPK + k) * 16, ctx->L0().c[1].sub, ws, d_rows, cap_rows, d_n, &ctx->launches);
       int n = 0; CK(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
       n = std::min(n, cap_rows);
       std::vector<int> rows(5 * (size_t)n); if (n) CK(cudaMemcpy(rows.data(), d_rows, (size_t)n * 20, cudaMemcpyDeviceToHost));

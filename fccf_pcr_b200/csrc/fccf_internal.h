@@ -54,9 +54,13 @@ struct BaseTable {
   int i[FCCF_MAXBASE], j[FCCF_MAXBASE], type[FCCF_MAXBASE];
   float angle[FCCF_MAXBASE];
 };
-struct ScoreState {          // fine-verify lattice + hash set-up (device)
+struct ScoreState {          // fine-verify lattice + static voxel table set-up (device)
   double mn[3];              // lattice origin: voxel faces lie at mn + k*res (mn = first static point - res)
-  int n1, n2, cap_eff, used;
+  int lmin[3], lmax[3];      // bounding box of the static cloud in lattice cells
+  int dims[3];
+  float lo_f[3], hi_f[3];    // a float q lies inside the box iff lo_f <= q < hi_f
+  int n1, n2, n_occ, cap_eff, nbits, n_keys, mode, pad;
+  int tickets[4];
 };
 struct PipeState {
   VGState vg[2][2];          // [stage: 0 main(), 1 computer_transform_guess][cloud: 0 = "1" (TAR file), 1 = "2" (SRC file)]
@@ -125,6 +129,18 @@ void launch_voxelgrid(cudaStream_t s, const Work& w, int stage, int ncloud, uint
 // face_extrate for both clouds (input: vg_xyz[1] with st->vg[1][c].n_out points)
 void launch_planes(cudaStream_t s, const Work& w, int ncloud, int src_stage, uint64_t* launches);
 
+struct ScoreWS {
+  int cap_points, cap_hash, t_rows;
+  u64 *keyA, *keyB; u32 *idxA, *idxB; u32 *hist, *segblk; int* seg_start;   // voxel-key sort of the static cloud
+  u32* vkey; int* s_cnt;     // per occupied static voxel (ascending compact key): key, static point count
+  u32 *hkey, *hid;           // open-addressing hash: compact key -> voxel id
+  unsigned short* dense;     // dense cell -> voxel id table (bounding boxes of <= 32768 cells)
+  int* t_cnt;                // t_rows x cap_points moving-point counters (when the table exceeds shared memory)
+  ScoreState* ss; int* status;
+};
+// carves a ScoreWS out of `base` (nullptr: only computes the size); returns the bytes needed
+size_t score_ws_layout(ScoreWS* ws, char* base, int cap_points, int t_rows);
+
 // hypotheses / clustering / verification workspace
 struct HypWS {
   int cap_hyp;
@@ -146,9 +162,7 @@ struct HypWS {
   int* rank_perm;            // 3 x FCCF_MAXCENTRE
   float* top_T;              // 3 x FCCF_TOPK x 16
   float* top_s1; float* top_s2; int* top_centre;
-  // fine verify
-  u64* fv_keys; int* fv_s; int* fv_t;   // hash: cap_hash slots; fv_t: [3*FCCF_TOPK][cap_hash] (used when the table exceeds shared memory)
-  int cap_hash;
+  ScoreWS fv;                // fine verify: static voxel table of cloud 1's leftover points
 };
 void launch_hypotheses(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
 void launch_cluster(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
@@ -158,15 +172,12 @@ void launch_fine_verify_fuse(cudaStream_t s, const Work& w, const HypWS& h, uint
 // stand-alone stage entry points (C-ABI helpers)
 void launch_quick_verify_list(cudaStream_t s, const fccf_params& p, float* d_T16, int n, const float* d_planes1, int f1,
                               const float* d_planes2, int f2, float* d_score, int* d_npair, int* d_pairs, int* d_iters, uint64_t* launches);
-struct ScoreWS {
-  u64* keys; int* s_cnt; int* t_cnt;   // t_cnt: n_rows x cap_hash global counters (fallback when the table exceeds shared memory)
-  int cap_hash; int t_rows;
-  ScoreState* ss; int* status;
-};
 // lattice + static hash of the static leftover cloud (n1/n2 are device-side counts)
-void launch_score_build(cudaStream_t s, const fccf_params& p, const float* d_s1, const int* d_n1, const int* d_n2, int cap_points, const ScoreWS& ws, uint64_t* launches);
+void launch_score_build(cudaStream_t s, const fccf_params& p, const float* d_s1, const int* d_n1, const int* d_n2, const ScoreWS& ws, uint64_t* launches);
 // scores n_hyp hypotheses (row-major 4x4 each) -> d_scores
 void launch_score_list(cudaStream_t s, const fccf_params& p, const float* d_T16, int n_hyp, const float* d_s2, const ScoreWS& ws, float* d_scores, uint64_t* launches);
+// packed (score, index) maximum of a device score list -> *d_out (8 bytes)
+void launch_score_best(cudaStream_t s, const float* d_scores, int n, long long index_base, long long* d_out, uint64_t* launches);
 // per-voxel (s,t) rows of one hypothesis: rows of 5 ints, *d_nrows rows
 void launch_score_dump(cudaStream_t s, const fccf_params& p, const float* d_T16, const float* d_s2, const ScoreWS& ws, int* d_rows, int cap_rows, int* d_nrows, uint64_t* launches);
 

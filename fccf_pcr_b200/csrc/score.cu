@@ -1,36 +1,32 @@
-// score.cu — fine_verify (FCCF.cpp:785-839) as "hypothesis scoring", per-type best + gate
-// (FCCF.cpp:1546-1605) and fuse_answer (1291-1368).
+// score.cu — fine_verify (FCCF.cpp:785-839) as "hypothesis scoring", the block-reduced argmax over a
+// score list, per-type best + gate (FCCF.cpp:1546-1605) and fuse_answer (1291-1368).
 //
 // The reference rebuilds a pcl octree (0.5 m) over static + transformed moving leftover points for
 // every hypothesis and counts both kinds per voxel.  The voxel lattice is anchored on the first
-// static point (pcl's first insert), so it does not depend on the hypothesis: a static
-// open-addressing hash of the occupied static voxels (64-bit packed lattice coordinates, linear
-// probing) is built once; scoring a hypothesis is then, per moving point, a float32 3x4 transform
-// (pcl::transformPointCloud's SSE order), a float64 lattice key, one probe and one counter
-// increment.  One CTA scores one hypothesis at a time with its counters in shared memory (global
-// fallback for very large tables); the per-voxel integer counts (s,t) are exactly the reference's.
+// static point (pcl's first insert), so it does not depend on the hypothesis.  Here, once per pair:
+//   score_bbox    lattice coordinates l = floor((double(p) - mn) / res) of the static points, their
+//                 bounding box, and from it a compact 32-bit voxel key ((cx*dy + cy)*dz + cz) plus
+//                 exact float bounds of the box (a float q is inside iff lo_f <= q < hi_f)
+//   sort+segments (sort.cu) occupied static voxels in ascending key order: voxel id, static count
+//   score_insert  open-addressing hash  compact key -> voxel id  (linear probing, load <= 0.5)
+// and per hypothesis (score_kernel): per moving point a float32 3x4 transform in pcl's SSE order, six
+// float compares against the box, a float64 lattice key, one probe and one counter increment; then
+// sum over the occupied voxels in id order of (s+t)*min/max.  A CTA scores SC_NH hypotheses per
+// sweep over the moving cloud with the hash and the counters in shared memory (global-memory
+// fallback for tables that do not fit).  Voxel ids are the sort order, so per-voxel integer counts
+// (s,t) are exactly the reference's and the float32 score does not depend on the hash layout.
 #include "fccf_dev.cuh"
 #include "fccf_internal.h"
 
 namespace fccf {
 
-#define SC_EMPTY 0xffffffffffffffffull
-#define SC_OFF (1 << 20)
-#define SC_THREADS 512
-#define SC_SMEM_SLOTS 32768      // 128 KB of u32 counters
-
-__device__ __forceinline__ u64 sc_hash(u64 k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33; return k; }
-__device__ __forceinline__ bool sc_key(const ScoreState* ss, double inv_res_is_div, float x, float y, float z, u64& key) {
-  // lattice coordinate = floor((double(p) - mn) / res); pcl: key = (unsigned)((p - min)/res) on a box whose
-  // min is mn shifted by whole voxels
-  long long lx = (long long)floor(((double)x - ss->mn[0]) / inv_res_is_div);
-  long long ly = (long long)floor(((double)y - ss->mn[1]) / inv_res_is_div);
-  long long lz = (long long)floor(((double)z - ss->mn[2]) / inv_res_is_div);
-  lx += SC_OFF; ly += SC_OFF; lz += SC_OFF;
-  if ((unsigned long long)lx >= (1ull << 21) || (unsigned long long)ly >= (1ull << 21) || (unsigned long long)lz >= (1ull << 21)) return false;
-  key = ((u64)lx << 42) | ((u64)ly << 21) | (u64)lz;
-  return true;
-}
+#define SC_EMPTY32 0xffffffffu
+#define SC_LIM (1 << 20)         // |lattice coordinate| bound of the static cloud
+#define SC_THREADS 1024
+#define SC_NH 4                  // global-table kernel: hypotheses per sweep over the moving cloud
+#define SC_WARPS 32              // shared-memory kernel: one hypothesis per warp
+#define SC_DYN_BYTES 204800      // dynamic shared memory of the shared-memory kernel (200 KB)
+#define SC_DENSE_CELLS 32768     // bounding boxes up to this many cells use a dense cell -> voxel id table
 
 struct ScArgs {
   ScoreWS ws;
@@ -42,13 +38,17 @@ struct ScArgs {
   float res;
 };
 
+__device__ __forceinline__ unsigned sc_hash32(u32 k) { return k * 0x9E3779B1u; }
+
+// lattice origin: first insert into an empty pcl octree: box = p0 +- res/2, padded to depth 1
 __global__ void score_setup_kernel(const __grid_constant__ ScArgs A) {
   ScoreState* ss = A.ws.ss;
+  if (threadIdx.x != 0) return;
   int n1 = *A.n1p, n2 = *A.n2p;
-  ss->n1 = n1; ss->n2 = n2; ss->used = 0;
+  if (n1 > A.ws.cap_points) { n1 = 0; atomicOr(A.ws.status, ST_HASH_FULL); }
+  ss->n1 = n1; ss->n2 = n2; ss->n_occ = 0; ss->n_keys = n1; ss->nbits = 1; ss->cap_eff = 64; ss->mode = 2;
   double res = (double)A.res;
   if (n1 > 0) {
-    // first insert into an empty pcl octree: box = p0 +- res/2, then padded to depth 1 (getKeyBitSize)
     const float minValue = 1.1920928955078125e-07f;
     for (int a = 0; a < 3; a++) {
       double mn = (double)A.s1[a] - res / 2, mx = (double)A.s1[a] + res / 2;
@@ -58,113 +58,371 @@ __global__ void score_setup_kernel(const __grid_constant__ ScArgs A) {
       ss->mn[a] = mn;
     }
   } else { ss->mn[0] = ss->mn[1] = ss->mn[2] = 0.0; }
-  int want = 64;
-  while (want < 2 * n1 && want < A.ws.cap_hash) want <<= 1;
-  if (want > A.ws.cap_hash) want = A.ws.cap_hash;
-  ss->cap_eff = want;
+  for (int a = 0; a < 3; a++) { ss->lmin[a] = 0x7fffffff; ss->lmax[a] = (int)0x80000000; ss->dims[a] = 1; ss->lo_f[a] = 0.f; ss->hi_f[a] = 0.f; }
+  for (int a = 0; a < 4; a++) ss->tickets[a] = 0;
 }
-__global__ void __launch_bounds__(256) score_clear_kernel(const __grid_constant__ ScArgs A) {
-  const int cap = A.ws.ss->cap_eff;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) { A.ws.keys[i] = SC_EMPTY; A.ws.s_cnt[i] = 0; }
+
+__device__ __forceinline__ bool sc_lattice(const ScoreState* ss, double res, float x, float y, float z, int l[3]) {
+  double v[3] = {floor(((double)x - ss->mn[0]) / res), floor(((double)y - ss->mn[1]) / res), floor(((double)z - ss->mn[2]) / res)};
+  bool ok = true;
+#pragma unroll
+  for (int a = 0; a < 3; a++) { ok = ok && (v[a] > -(double)SC_LIM) && (v[a] < (double)SC_LIM); l[a] = ok ? (int)v[a] : 0; }
+  return ok;
+}
+
+// bounding box of the static lattice coordinates; the last block derives the compact key layout
+__global__ void __launch_bounds__(256) score_bbox_kernel(const __grid_constant__ ScArgs A) {
+  ScoreState* ss = A.ws.ss;
+  const int n1 = ss->n1;
+  const double res = (double)A.res;
+  int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+  bool bad = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += gridDim.x * blockDim.x) {
+    int l[3];
+    if (!sc_lattice(ss, res, A.s1[3 * i], A.s1[3 * i + 1], A.s1[3 * i + 2], l)) { bad = true; continue; }
+#pragma unroll
+    for (int a = 0; a < 3; a++) { mn[a] = min(mn[a], l[a]); mx[a] = max(mx[a], l[a]); }
+  }
+  for (int o = 16; o; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o)); mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o)); }
+  }
+  if ((threadIdx.x & 31) == 0 && mn[0] != 0x7fffffff) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { atomicMin(&ss->lmin[a], mn[a]); atomicMax(&ss->lmax[a], mx[a]); }
+  }
+  if (bad) atomicOr(A.ws.status, ST_HASH_FULL);
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ss->tickets[0], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  ss->tickets[0] = 0;
+  if (n1 <= 0) { ss->n_keys = 0; return; }
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; a++) { lo[a] = atomicAdd(&ss->lmin[a], 0); hi[a] = atomicAdd(&ss->lmax[a], 0); }
+  if (lo[0] == 0x7fffffff || (atomicAdd(A.ws.status, 0) & ST_HASH_FULL)) { ss->n_keys = 0; ss->n1 = 0; return; }   // static cloud outside the supported lattice range
+  unsigned long long tot = 1;
+  for (int a = 0; a < 3; a++) { ss->dims[a] = hi[a] - lo[a] + 1; tot *= (unsigned long long)ss->dims[a]; }
+  if (tot >= 0xffffffffull) { atomicOr(A.ws.status, ST_HASH_FULL); ss->n_keys = 0; ss->n1 = 0; return; }
+  int nbits = 64 - __clzll(tot);
+  ss->nbits = nbits < 1 ? 1 : nbits;
+  // a float q lies in lattice cells [lo, hi] iff  Lo <= double(q) < Hi  with  Lo = mn + lo*res,
+  // Hi = mn + (hi+1)*res (both exact: res is a small binary fraction in practice; otherwise the
+  // per-point key below still decides) iff  lo_f <= q < hi_f  with both rounded UP to float
+  for (int a = 0; a < 3; a++) {
+    double Lo = ss->mn[a] + (double)lo[a] * res, Hi = ss->mn[a] + (double)(hi[a] + 1) * res;
+    ss->lo_f[a] = __double2float_ru(Lo);
+    ss->hi_f[a] = __double2float_ru(Hi);
+  }
+}
+
+__device__ __forceinline__ u32 sc_compact(const ScoreState* ss, const int l[3]) {
+  return (u32)(((l[0] - ss->lmin[0]) * ss->dims[1] + (l[1] - ss->lmin[1])) * ss->dims[2] + (l[2] - ss->lmin[2]));
+}
+
+__global__ void __launch_bounds__(256) score_keys_kernel(const __grid_constant__ ScArgs A) {
+  const ScoreState* ss = A.ws.ss;
+  const int n = ss->n_keys;
+  const double res = (double)A.res;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int l[3];
+    sc_lattice(ss, res, A.s1[3 * i], A.s1[3 * i + 1], A.s1[3 * i + 2], l);
+    A.ws.keyA[i] = (u64)sc_compact(ss, l);
+  }
+}
+
+// Table plan from the number of occupied voxels (device-side, every thread computes the same):
+//   cap   hash slots (power of two >= 2 * n_occ)
+//   mode  0: dense cell -> id table + per-warp 16-bit counters in shared memory
+//         1: hash + per-warp 16-bit counters in shared memory
+//         2: hash and 32-bit counters in global memory (score_kernel)
+struct ScPlan { int cap, mode, row_words, nocc_pad, tab_bytes; unsigned cells; };
+__device__ __forceinline__ ScPlan sc_plan(const ScoreState* ss, int cap_hash) {
+  ScPlan P;
+  const int nocc = ss->n_occ;
+  int cap = 64;
+  while (cap < 2 * nocc && cap < cap_hash) cap <<= 1;
+  P.cap = cap;
+  P.cells = (unsigned)ss->dims[0] * (unsigned)ss->dims[1] * (unsigned)ss->dims[2];
+  P.nocc_pad = (nocc + 63) & ~63;
+  P.row_words = P.nocc_pad / 2;
+  size_t fixed = (size_t)4 * P.nocc_pad + (size_t)SC_WARPS * 4 * P.row_words;
+  bool small = nocc < 65535 && ss->n2 < 65536;      // 16-bit ids and counters
+  P.mode = 2; P.tab_bytes = 0;
+  if (small && P.cells <= SC_DENSE_CELLS && fixed + ((2 * (size_t)P.cells + 15) & ~(size_t)15) <= SC_DYN_BYTES) { P.mode = 0; P.tab_bytes = (int)((2 * P.cells + 15) & ~15u); }
+  else if (small && fixed + (size_t)6 * cap <= SC_DYN_BYTES) { P.mode = 1; P.tab_bytes = 6 * cap; }
+  return P;
+}
+
+// per occupied voxel (ascending key): key and static count; clears the hash and the dense table
+__global__ void __launch_bounds__(256) score_table_kernel(const __grid_constant__ ScArgs A) {
+  ScoreState* ss = A.ws.ss;
+  const int nocc = ss->n_occ;
+  const ScPlan P = sc_plan(ss, A.ws.cap_hash);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ss->cap_eff = P.cap; ss->mode = P.mode; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.cap; i += gridDim.x * blockDim.x) A.ws.hkey[i] = SC_EMPTY32;
+  if (P.mode == 0) for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (P.cells + 1) / 2; i += gridDim.x * blockDim.x) ((u32*)A.ws.dense)[i] = 0xffffffffu;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nocc; v += gridDim.x * blockDim.x) {
+    int b = A.ws.seg_start[v], e = A.ws.seg_start[v + 1];
+    A.ws.vkey[v] = (u32)A.ws.keyA[b];
+    A.ws.s_cnt[v] = e - b;
+  }
 }
 __global__ void __launch_bounds__(256) score_insert_kernel(const __grid_constant__ ScArgs A) {
   const ScoreState* ss = A.ws.ss;
-  const int n1 = ss->n1, cap = ss->cap_eff;
+  const int nocc = ss->n_occ, cap = ss->cap_eff, mode = ss->mode;
   const unsigned mask = (unsigned)cap - 1u;
-  const double res = (double)A.res;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += gridDim.x * blockDim.x) {
-    u64 key;
-    if (!sc_key(ss, res, A.s1[3 * i], A.s1[3 * i + 1], A.s1[3 * i + 2], key)) { atomicOr(A.ws.status, ST_HASH_FULL); continue; }
-    unsigned h = (unsigned)sc_hash(key) & mask;
+  int shift = 32 - (31 - __clz(cap));
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nocc; v += gridDim.x * blockDim.x) {
+    u32 key = A.ws.vkey[v];
+    if (mode == 0) A.ws.dense[key] = (unsigned short)v;       // compact key == cell index
+    unsigned h = (sc_hash32(key) >> shift) & mask;
     for (int probe = 0; probe < cap; probe++) {
-      u64 prev = atomicCAS((unsigned long long*)&A.ws.keys[h], SC_EMPTY, key);
-      if (prev == SC_EMPTY || prev == key) { atomicAdd(&A.ws.s_cnt[h], 1); break; }
+      u32 prev = atomicCAS(&A.ws.hkey[h], SC_EMPTY32, key);
+      if (prev == SC_EMPTY32) { A.ws.hid[h] = (u32)v; break; }
       h = (h + 1) & mask;
-      if (probe == cap - 1) atomicOr(A.ws.status, ST_HASH_FULL);
     }
   }
 }
 
-// scores one hypothesis with the whole CTA; cnt: cap counters (shared or global)
-__device__ float score_one(const ScArgs& A, const float* T16, int* cnt, float* s_red) {
-  const ScoreState* ss = A.ws.ss;
-  const int cap = ss->cap_eff, n2 = ss->n2, n1 = ss->n1;
-  const unsigned mask = (unsigned)cap - 1u;
+// ---- scoring ---------------------------------------------------------------------------------
+// voxel id of the transformed point, or -1
+template <bool POW2>
+__device__ __forceinline__ int sc_lookup(const float* __restrict__ T, float px, float py, float pz, const float* lo_f, const float* hi_f, const double* mnd,
+                                         double res_or_inv, const int* lmin, int dx, int dy, int dz, const u32* __restrict__ hkey, const u32* __restrict__ hid,
+                                         unsigned mask, int shift) {
+  // pcl::transformPointCloud (SSE order): x*c0 + (y*c1 + (z*c2 + c3))
+  float qx = px * T[0] + (py * T[1] + (pz * T[2] + T[3]));
+  float qy = px * T[4] + (py * T[5] + (pz * T[6] + T[7]));
+  float qz = px * T[8] + (py * T[9] + (pz * T[10] + T[11]));
+  if (!(qx >= lo_f[0] && qx < hi_f[0] && qy >= lo_f[1] && qy < hi_f[1] && qz >= lo_f[2] && qz < hi_f[2])) return -1;
+  double vx, vy, vz;
+  if (POW2) { vx = ((double)qx - mnd[0]) * res_or_inv; vy = ((double)qy - mnd[1]) * res_or_inv; vz = ((double)qz - mnd[2]) * res_or_inv; }   // exact: 1/res is a power of two
+  else { vx = ((double)qx - mnd[0]) / res_or_inv; vy = ((double)qy - mnd[1]) / res_or_inv; vz = ((double)qz - mnd[2]) / res_or_inv; }
+  // floor of a small non-huge double: round-down add of 1.5 * 2^52 leaves the integer in the low word
+  int lx = __double2loint(__dadd_rd(vx, 6755399441055744.0)), ly = __double2loint(__dadd_rd(vy, 6755399441055744.0)), lz = __double2loint(__dadd_rd(vz, 6755399441055744.0));
+  u32 cx = (u32)(lx - lmin[0]), cy = (u32)(ly - lmin[1]), cz = (u32)(lz - lmin[2]);
+  if (!(cx < (u32)dx && cy < (u32)dy && cz < (u32)dz)) return -1;      // belt and braces for inexact box bounds
+  u32 key = (cx * (u32)dy + cy) * (u32)dz + cz;
+  unsigned h = (sc_hash32(key) >> shift) & mask;
+  while (true) {
+    u32 k = hkey[h];
+    if (k == key) return (int)hid[h];
+    if (k == SC_EMPTY32) return -1;
+    h = (h + 1) & mask;
+  }
+}
+
+// deterministic block sum (fixed tree): valid in thread 0
+__device__ __forceinline__ float sc_block_sum(float part, float* s_red) {
   const int t = threadIdx.x;
-  const double res = (double)A.res;
-  float T[12];
-#pragma unroll
-  for (int i = 0; i < 12; i++) T[i] = T16[i];
-  for (int h = t; h < cap; h += SC_THREADS) cnt[h] = 0;
-  __syncthreads();
-  const u64* __restrict__ keys = A.ws.keys;
-  for (int i = t; i < n2; i += SC_THREADS) {
-    f3 q = tf_se3(T, mk3(A.s2[3 * i], A.s2[3 * i + 1], A.s2[3 * i + 2]));
-    u64 key;
-    if (!sc_key(ss, res, q.x, q.y, q.z, key)) continue;
-    unsigned h = (unsigned)sc_hash(key) & mask;
-    while (true) {
-      u64 k = __ldg(&keys[h]);
-      if (k == key) { atomicAdd(&cnt[h], 1); break; }
-      if (k == SC_EMPTY) break;
-      h = (h + 1) & mask;
-    }
-  }
-  __syncthreads();
-  float part = 0.f;
-  for (int h = t; h < cap; h += SC_THREADS) {
-    int tt = cnt[h];
-    if (tt > 0) {
-      float fs = (float)A.ws.s_cnt[h], ft = (float)tt;
-      float mn = fs < ft ? fs : ft, mx = fs > ft ? fs : ft;
-      part = part + (fs + ft) * (mn / mx);
-    }
-  }
   for (int o = 16; o; o >>= 1) part = part + __shfl_xor_sync(0xffffffffu, part, o);
   if ((t & 31) == 0) s_red[t >> 5] = part;
   __syncthreads();
   float tot = 0.f;
-  if (t < 32) {
-    float v = (t < SC_THREADS / 32) ? s_red[t] : 0.f;
-    for (int o = 16; o; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
-    tot = v;
-  }
+  if (t == 0) { for (int w = 0; w < SC_THREADS / 32; w++) tot = tot + s_red[w]; }
   __syncthreads();
-  return tot / (float)(n1 + n2);   // valid on warp 0
+  return tot;
 }
 
-extern __shared__ int sc_dyn[];
-template <bool SMEM>
-__global__ void __launch_bounds__(SC_THREADS) score_kernel(const __grid_constant__ ScArgs A) {
-  __shared__ float s_red[SC_THREADS / 32];
-  const int cap = A.ws.ss->cap_eff;
-  const bool use_smem = SMEM && cap <= SC_SMEM_SLOTS;
-  if (!use_smem && (int)blockIdx.x >= A.ws.t_rows) return;
-  int* cnt = use_smem ? sc_dyn : (A.ws.t_cnt + (size_t)blockIdx.x * A.ws.cap_hash);
-  const int stride = use_smem ? gridDim.x : min((int)gridDim.x, A.ws.t_rows);
-  for (int h = blockIdx.x; h < A.n_hyp; h += stride) {
-    if (A.n_top) { int ty = h / FCCF_TOPK, k = h - ty * FCCF_TOPK; if (k >= A.n_top[ty]) continue; }
-    float sc = score_one(A, A.T + (size_t)h * 16, cnt, s_red);
-    if (threadIdx.x == 0) A.scores[h] = sc;
-  }
-}
+extern __shared__ __align__(16) unsigned char sc_dyn[];
 
-__global__ void __launch_bounds__(SC_THREADS) score_dump_kernel(const __grid_constant__ ScArgs A) {
-  __shared__ float s_red[SC_THREADS / 32];
+// ---- shared-memory kernel (plan modes 0 and 1): one hypothesis per warp ----------------------------
+// Each CTA keeps the static voxel table (dense cell -> id, or hash) and the static counts in shared
+// memory; each of its 32 warps scores one hypothesis at a time with the 3x4 transform in registers and
+// a private row of 16-bit counters (two per 32-bit word, shared-memory atomics), sweeping the moving
+// cloud 32 points at a time.  No block-wide synchronisation after the table load.
+template <bool POW2>
+__global__ void __launch_bounds__(SC_THREADS, 1) score_warp_kernel(const __grid_constant__ ScArgs A) {
   const ScoreState* ss = A.ws.ss;
-  int* cnt = A.ws.t_cnt;
-  score_one(A, A.T, cnt, s_red);
+  const int mode = ss->mode;
+  if (mode == 2) return;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int nocc = ss->n_occ, n1 = ss->n1, n2 = ss->n2;
+  const ScPlan P = sc_plan(ss, A.ws.cap_hash);
+  unsigned short* tab16 = (unsigned short*)sc_dyn;                       // mode 0: cells x u16
+  u32* hkey = (u32*)sc_dyn; unsigned short* hid16 = (unsigned short*)(hkey + P.cap);   // mode 1
+  int* s_cnt = (int*)(sc_dyn + P.tab_bytes);
+  u32* row = (u32*)(s_cnt + P.nocc_pad) + (size_t)warp * P.row_words;
+  if (mode == 0) { for (unsigned i = t; i < (P.cells + 1) / 2; i += SC_THREADS) ((u32*)tab16)[i] = ((const u32*)A.ws.dense)[i]; }
+  else { for (int i = t; i < P.cap; i += SC_THREADS) { hkey[i] = A.ws.hkey[i]; hid16[i] = (unsigned short)A.ws.hid[i]; } }
+  for (int i = t; i < P.nocc_pad; i += SC_THREADS) s_cnt[i] = i < nocc ? A.ws.s_cnt[i] : 0;
   __syncthreads();
-  const int cap = ss->cap_eff;
-  for (int h = threadIdx.x; h < cap; h += SC_THREADS) {
-    int tt = cnt[h];
+  const float lo0 = ss->lo_f[0], lo1 = ss->lo_f[1], lo2 = ss->lo_f[2], hi0 = ss->hi_f[0], hi1 = ss->hi_f[1], hi2 = ss->hi_f[2];
+  const double m0 = ss->mn[0], m1 = ss->mn[1], m2 = ss->mn[2];
+  const int l0 = ss->lmin[0], l1 = ss->lmin[1], l2 = ss->lmin[2];
+  const u32 dx = (u32)ss->dims[0], dy = (u32)ss->dims[1], dz = (u32)ss->dims[2];
+  const unsigned mask = (unsigned)P.cap - 1u;
+  const int shift = 32 - (31 - __clz(P.cap));
+  const double rr = POW2 ? 1.0 / (double)A.res : (double)A.res;
+  const float* __restrict__ s2 = A.s2;
+  const float inv_tot = 0.f; (void)inv_tot;
+  for (int h = blockIdx.x * SC_WARPS + warp; h < A.n_hyp; h += gridDim.x * SC_WARPS) {
+    if (A.n_top) { int ty = h / FCCF_TOPK, kk = h - ty * FCCF_TOPK; if (kk >= A.n_top[ty]) continue; }
+    const float4* Tp = (const float4*)(A.T + (size_t)h * 16);
+    const float4 r0 = __ldg(Tp), r1 = __ldg(Tp + 1), r2 = __ldg(Tp + 2);
+    for (int i = lane; i < P.row_words; i += 32) row[i] = 0u;
+    __syncwarp();
+#pragma unroll 2
+    for (int i = lane; i < n2; i += 32) {
+      const float px = s2[3 * i], py = s2[3 * i + 1], pz = s2[3 * i + 2];
+      // pcl::transformPointCloud (SSE order): x*c0 + (y*c1 + (z*c2 + c3))
+      const float qx = px * r0.x + (py * r0.y + (pz * r0.z + r0.w));
+      const float qy = px * r1.x + (py * r1.y + (pz * r1.z + r1.w));
+      const float qz = px * r2.x + (py * r2.y + (pz * r2.z + r2.w));
+      if (qx >= lo0 && qx < hi0 && qy >= lo1 && qy < hi1 && qz >= lo2 && qz < hi2) {
+        double vx, vy, vz;
+        if (POW2) { vx = ((double)qx - m0) * rr; vy = ((double)qy - m1) * rr; vz = ((double)qz - m2) * rr; }
+        else { vx = ((double)qx - m0) / rr; vy = ((double)qy - m1) / rr; vz = ((double)qz - m2) / rr; }
+        const u32 cx = (u32)(__double2loint(__dadd_rd(vx, 6755399441055744.0)) - l0);
+        const u32 cy = (u32)(__double2loint(__dadd_rd(vy, 6755399441055744.0)) - l1);
+        const u32 cz = (u32)(__double2loint(__dadd_rd(vz, 6755399441055744.0)) - l2);
+        if (cx < dx && cy < dy && cz < dz) {
+          const u32 key = (cx * dy + cy) * dz + cz;
+          u32 id = 0xffffu;
+          if (mode == 0) id = tab16[key];
+          else {
+            unsigned hh = (sc_hash32(key) >> shift) & mask;
+            while (true) {
+              u32 k = hkey[hh];
+              if (k == key) { id = hid16[hh]; break; }
+              if (k == SC_EMPTY32) break;
+              hh = (hh + 1) & mask;
+            }
+          }
+          if (id != 0xffffu) atomicAdd(&row[id >> 1], (id & 1u) ? 0x10000u : 1u);
+        }
+      }
+    }
+    __syncwarp();
+    float part = 0.f;
+    for (int w = lane; w < P.row_words; w += 32) {
+      const u32 c2 = row[w];
+      if (c2) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int tt = (int)((c2 >> (16 * e)) & 0xffffu);
+          if (tt > 0) {
+            float fs = (float)s_cnt[2 * w + e], ft = (float)tt;
+            float mn = fs < ft ? fs : ft, mx = fs > ft ? fs : ft;
+            part = part + (fs + ft) * (mn / mx);
+          }
+        }
+      }
+    }
+    for (int o = 16; o; o >>= 1) part = part + __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) A.scores[h] = part / (float)(n1 + n2);
+    __syncwarp();
+  }
+}
+
+// ---- global-table kernel (plan mode 2) ------------------------------------------------------------
+// One CTA scores groups of SC_NH hypotheses; the hash is read from global memory (L2) and the 32-bit
+// counters live in the CTA's rows of t_cnt.
+template <bool POW2>
+__global__ void __launch_bounds__(SC_THREADS) score_kernel(const __grid_constant__ ScArgs A) {
+  const ScoreState* ss = A.ws.ss;
+  if (ss->mode != 2) return;                      // the launcher issues both kernels; one of them runs
+  const int t = threadIdx.x;
+  const int nocc = ss->n_occ, cap = ss->cap_eff, n1 = ss->n1, n2 = ss->n2;
+  __shared__ float s_T[SC_NH][12];
+  __shared__ float s_red[SC_THREADS / 32];
+  __shared__ float s_lo[3], s_hi[3];
+  __shared__ double s_mn[3];
+  __shared__ int s_lmin[3];
+  if ((int)blockIdx.x * SC_NH + SC_NH > A.ws.t_rows) return;
+  const u32* hkey = A.ws.hkey; const u32* hid = A.ws.hid; const int* s_cnt = A.ws.s_cnt;
+  int* cnt = A.ws.t_cnt + (size_t)blockIdx.x * SC_NH * A.ws.cap_points;
+  const int cstride = A.ws.cap_points;
+  if (t < 3) { s_lo[t] = ss->lo_f[t]; s_hi[t] = ss->hi_f[t]; s_mn[t] = ss->mn[t]; s_lmin[t] = ss->lmin[t]; }
+  const int dx = ss->dims[0], dy = ss->dims[1], dz = ss->dims[2];
+  const unsigned mask = (unsigned)cap - 1u;
+  const int shift = 32 - (31 - __clz(cap));
+  const double rr = POW2 ? 1.0 / (double)A.res : (double)A.res;
+  const int ngroups = (A.n_hyp + SC_NH - 1) / SC_NH;
+  const int gstride = min((int)gridDim.x, A.ws.t_rows / SC_NH);
+  const float* __restrict__ s2 = A.s2;
+  for (int g = blockIdx.x; g < ngroups; g += gstride) {
+    const int h0 = g * SC_NH;
+    unsigned actm = 0;
+#pragma unroll
+    for (int k = 0; k < SC_NH; k++) {
+      int h = h0 + k;
+      bool a = h < A.n_hyp;
+      if (a && A.n_top) { int ty = h / FCCF_TOPK, kk = h - ty * FCCF_TOPK; a = kk < A.n_top[ty]; }
+      if (a) actm |= 1u << k;
+    }
+    if (!actm) continue;
+    __syncthreads();
+    if (t < SC_NH * 12) { int k = t / 12, e = t - k * 12; s_T[k][e] = (h0 + k < A.n_hyp) ? A.T[(size_t)(h0 + k) * 16 + e] : 0.f; }
+#pragma unroll
+    for (int k = 0; k < SC_NH; k++) for (int i = t; i < nocc; i += SC_THREADS) cnt[(size_t)k * cstride + i] = 0;
+    __syncthreads();
+    for (int i = t; i < n2; i += SC_THREADS) {
+      float px = s2[3 * i], py = s2[3 * i + 1], pz = s2[3 * i + 2];
+#pragma unroll
+      for (int k = 0; k < SC_NH; k++) {
+        if (!((actm >> k) & 1u)) continue;
+        int id = sc_lookup<POW2>(s_T[k], px, py, pz, s_lo, s_hi, s_mn, rr, s_lmin, dx, dy, dz, hkey, hid, mask, shift);
+        if (id >= 0) atomicAdd(&cnt[(size_t)k * cstride + id], 1);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SC_NH; k++) {
+      if (!((actm >> k) & 1u)) continue;             // uniform across the block
+      float part = 0.f;
+      for (int v = t; v < nocc; v += SC_THREADS) {
+        int tt = cnt[(size_t)k * cstride + v];
+        if (tt > 0) {
+          float fs = (float)s_cnt[v], ft = (float)tt;
+          float mn = fs < ft ? fs : ft, mx = fs > ft ? fs : ft;
+          part = part + (fs + ft) * (mn / mx);
+        }
+      }
+      float tot = sc_block_sum(part, s_red);
+      if (t == 0) A.scores[h0 + k] = tot / (float)(n1 + n2);
+    }
+  }
+}
+
+// per-voxel rows (Lx, Ly, Lz, s, t) of ONE hypothesis, L relative to the voxel of the first static point
+template <bool POW2>
+__global__ void __launch_bounds__(SC_THREADS) score_dump_kernel(const __grid_constant__ ScArgs A) {
+  const ScoreState* ss = A.ws.ss;
+  const int t = threadIdx.x;
+  const int nocc = ss->n_occ, cap = ss->cap_eff, n2 = ss->n2;
+  int* cnt = A.ws.t_cnt;
+  __shared__ float s_T[12];
+  __shared__ float s_lo[3], s_hi[3];
+  __shared__ double s_mn[3];
+  __shared__ int s_lmin[3];
+  if (t < 12) s_T[t] = A.T[t];
+  if (t < 3) { s_lo[t] = ss->lo_f[t]; s_hi[t] = ss->hi_f[t]; s_mn[t] = ss->mn[t]; s_lmin[t] = ss->lmin[t]; }
+  for (int i = t; i < nocc; i += SC_THREADS) cnt[i] = 0;
+  __syncthreads();
+  const int dx = ss->dims[0], dy = ss->dims[1], dz = ss->dims[2];
+  const unsigned mask = (unsigned)cap - 1u;
+  const int shift = 32 - (31 - __clz(cap));
+  const double rr = POW2 ? 1.0 / (double)A.res : (double)A.res;
+  for (int i = t; i < n2; i += SC_THREADS) {
+    int id = sc_lookup<POW2>(s_T, A.s2[3 * i], A.s2[3 * i + 1], A.s2[3 * i + 2], s_lo, s_hi, s_mn, rr, s_lmin, dx, dy, dz, A.ws.hkey, A.ws.hid, mask, shift);
+    if (id >= 0) atomicAdd(&cnt[id], 1);
+  }
+  __syncthreads();
+  for (int v = t; v < nocc; v += SC_THREADS) {
+    int tt = cnt[v];
     if (tt > 0) {
       int r = atomicAdd(A.nrows, 1);
       if (r < A.cap_rows) {
-        u64 k = A.ws.keys[h];
-        // rows are relative to the voxel of the first static point (lattice coordinate 1)
-        A.rows[5 * r] = (int)((k >> 42) & 0x1fffff) - SC_OFF - 1; A.rows[5 * r + 1] = (int)((k >> 21) & 0x1fffff) - SC_OFF - 1; A.rows[5 * r + 2] = (int)(k & 0x1fffff) - SC_OFF - 1;
-        A.rows[5 * r + 3] = A.ws.s_cnt[h]; A.rows[5 * r + 4] = tt;
+        u32 k = A.ws.vkey[v];
+        int cz = (int)(k % (u32)dz); k /= (u32)dz; int cy = (int)(k % (u32)dy); int cx = (int)(k / (u32)dy);
+        // lattice coordinate of the first static point is 1 on every axis
+        A.rows[5 * r] = cx + ss->lmin[0] - 1; A.rows[5 * r + 1] = cy + ss->lmin[1] - 1; A.rows[5 * r + 2] = cz + ss->lmin[2] - 1;
+        A.rows[5 * r + 3] = A.ws.s_cnt[v]; A.rows[5 * r + 4] = tt;
       }
     }
   }
@@ -174,37 +432,121 @@ static void fill_common(ScArgs& A, const fccf_params& p, const ScoreWS& ws) {
   A.ws = ws; A.res = p.fine_verify_voxel_size; A.s1 = nullptr; A.n1p = nullptr; A.n2p = nullptr; A.s2 = nullptr; A.T = nullptr; A.n_hyp = 0; A.n_top = nullptr;
   A.scores = nullptr; A.rows = nullptr; A.cap_rows = 0; A.nrows = nullptr;
 }
+static bool is_pow2_res(float res) { int e; float m = frexpf(res, &e); return m == 0.5f && res > 0.f; }
 
-void launch_score_build(cudaStream_t s, const fccf_params& p, const float* d_s1, const int* d_n1, const int* d_n2, int cap_points, const ScoreWS& ws, uint64_t* launches) {
-  ScArgs A; fill_common(A, p, ws);
-  A.s1 = d_s1; A.n1p = d_n1; A.n2p = d_n2;
-  score_setup_kernel<<<1, 1, 0, s>>>(A);
-  int nb = (ws.cap_hash + 255) / 256; if (nb > 1184) nb = 1184;
-  score_clear_kernel<<<nb, 256, 0, s>>>(A);
-  int nbi = (cap_points + 255) / 256; if (nbi > 1184) nbi = 1184; if (nbi < 1) nbi = 1;
-  score_insert_kernel<<<nbi, 256, 0, s>>>(A);
-  if (launches) *launches += 3;
+size_t score_ws_layout(ScoreWS* ws, char* base, int cap_points, int t_rows) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> char* { char* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; };
+  size_t c = (size_t)(cap_points < 1024 ? 1024 : cap_points), nb = c / RS_TILE + 2;
+  int cap_hash = 1024; while ((size_t)cap_hash < 2 * c) cap_hash <<= 1;
+  ScoreWS w;
+  w.cap_points = (int)c; w.cap_hash = cap_hash; w.t_rows = t_rows;
+  w.keyA = (u64*)take(8 * c); w.keyB = (u64*)take(8 * c); w.idxA = (u32*)take(4 * c); w.idxB = (u32*)take(4 * c);
+  w.hist = (u32*)take(nb * 1024); w.segblk = (u32*)take(nb * 4); w.seg_start = (int*)take(4 * (c + 1));
+  w.vkey = (u32*)take(4 * c); w.s_cnt = (int*)take(4 * c);
+  w.hkey = (u32*)take(4 * (size_t)cap_hash); w.hid = (u32*)take(4 * (size_t)cap_hash);
+  w.dense = (unsigned short*)take(2 * (size_t)SC_DENSE_CELLS + 64);
+  w.t_cnt = (int*)take(4 * c * (size_t)t_rows);
+  w.ss = nullptr; w.status = nullptr;
+  if (ws) *ws = w;
+  return off + 256;
 }
 
-static void score_launch(cudaStream_t s, ScArgs& A, int nblocks) {
+void launch_score_build(cudaStream_t s, const fccf_params& p, const float* d_s1, const int* d_n1, const int* d_n2, const ScoreWS& ws, uint64_t* launches) {
+  ScArgs A; fill_common(A, p, ws);
+  A.s1 = d_s1; A.n1p = d_n1; A.n2p = d_n2;
+  int cap = ws.cap_points;
+  int nb = (cap + 255) / 256; if (nb > 1184) nb = 1184; if (nb < 1) nb = 1;
+  score_setup_kernel<<<1, 32, 0, s>>>(A);
+  score_bbox_kernel<<<nb, 256, 0, s>>>(A);
+  score_keys_kernel<<<nb, 256, 0, s>>>(A);
+  if (launches) *launches += 3;
+  SortJobs ab, ba;
+  SortJob j; j.kin = ws.keyA; j.kout = ws.keyB; j.vin = ws.idxA; j.vout = ws.idxB; j.n = &ws.ss->n_keys; j.nbits = &ws.ss->nbits; j.hist = ws.hist; j.ticket = &ws.ss->tickets[1];
+  ab.j[0] = j; ab.j[1] = j; ab.j[2] = j;
+  SortJob k = j; k.kin = ws.keyB; k.kout = ws.keyA; k.vin = ws.idxB; k.vout = ws.idxA;
+  ba.j[0] = k; ba.j[1] = k; ba.j[2] = k;
+  launch_sort(s, ab, ba, 1, cap, 4, launches);
+  SegJobs sj; SegJob g; g.keys = ws.keyA; g.n = &ws.ss->n_keys; g.seg_start = ws.seg_start; g.nseg = &ws.ss->n_occ; g.blk = ws.segblk; g.ticket = &ws.ss->tickets[2];
+  sj.j[0] = g; sj.j[1] = g; sj.j[2] = g;
+  launch_segments(s, sj, 1, cap, launches);
+  int nbh = (ws.cap_hash + 255) / 256; if (nbh > 1184) nbh = 1184;
+  score_table_kernel<<<nbh, 256, 0, s>>>(A);
+  score_insert_kernel<<<nb, 256, 0, s>>>(A);
+  if (launches) *launches += 2;
+}
+
+static void score_launch(cudaStream_t s, ScArgs& A, int n_hyp, uint64_t* launches) {
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM_SLOTS * 4); attr = true; }
-  score_kernel<true><<<nblocks, SC_THREADS, SC_SMEM_SLOTS * 4, s>>>(A);
+  if (!attr) {
+    cudaFuncSetAttribute(score_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_DYN_BYTES);
+    cudaFuncSetAttribute(score_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_DYN_BYTES);
+    attr = true;
+  }
+  if (n_hyp < 1) return;
+  int nbw = (n_hyp + SC_WARPS - 1) / SC_WARPS; if (nbw > 148) nbw = 148;
+  int ngroups = (n_hyp + SC_NH - 1) / SC_NH;
+  int nbg = A.ws.t_rows / SC_NH; if (nbg > ngroups) nbg = ngroups; if (nbg > 148) nbg = 148; if (nbg < 1) nbg = 1;
+  // which kernel does the work is a device-side fact (table plan); the other one exits at once
+  if (is_pow2_res(A.res)) {
+    score_warp_kernel<true><<<nbw, SC_THREADS, SC_DYN_BYTES, s>>>(A);
+    score_kernel<true><<<nbg, SC_THREADS, 0, s>>>(A);
+  } else {
+    score_warp_kernel<false><<<nbw, SC_THREADS, SC_DYN_BYTES, s>>>(A);
+    score_kernel<false><<<nbg, SC_THREADS, 0, s>>>(A);
+  }
+  if (launches) *launches += 2;
 }
 
 void launch_score_list(cudaStream_t s, const fccf_params& p, const float* d_T16, int n_hyp, const float* d_s2, const ScoreWS& ws, float* d_scores, uint64_t* launches) {
   if (n_hyp <= 0) return;
   ScArgs A; fill_common(A, p, ws);
   A.T = d_T16; A.n_hyp = n_hyp; A.s2 = d_s2; A.scores = d_scores;
-  int nb = n_hyp < 148 ? n_hyp : 148;
-  score_launch(s, A, nb);
-  if (launches) *launches += 1;
+  score_launch(s, A, n_hyp, launches);
 }
 
 void launch_score_dump(cudaStream_t s, const fccf_params& p, const float* d_T16, const float* d_s2, const ScoreWS& ws, int* d_rows, int cap_rows, int* d_nrows, uint64_t* launches) {
   ScArgs A; fill_common(A, p, ws);
   A.T = d_T16; A.n_hyp = 1; A.s2 = d_s2; A.rows = d_rows; A.cap_rows = cap_rows; A.nrows = d_nrows;
-  score_dump_kernel<<<1, SC_THREADS, 0, s>>>(A);
+  if (is_pow2_res(A.res)) score_dump_kernel<true><<<1, SC_THREADS, 0, s>>>(A);
+  else score_dump_kernel<false><<<1, SC_THREADS, 0, s>>>(A);
+  if (launches) *launches += 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-reduced argmax over a score list: packed = (order-preserving int of the score) << 32 |
+// (0xFFFFFFFF - global index); the signed 64-bit maximum is the highest score, smallest index among
+// ties (the reference's strict `>` first-maximum scans, FCCF.cpp:1559).  NaN ranks below everything.
+// One atomicMax per block; across GPUs the same word goes through one 8-byte all-reduce (max).
+__device__ __forceinline__ long long pack_score(float sc, long long gidx) {
+  int key;
+  if (sc != sc) key = (int)0x80000000;
+  else { sc = sc + 0.0f; int b = __float_as_int(sc); key = b >= 0 ? b : (b ^ 0x7fffffff); }
+  return ((long long)key << 32) | (long long)(0xffffffffll - gidx);
+}
+__global__ void __launch_bounds__(256) score_best_kernel(const float* __restrict__ scores, int n, long long index_base, long long* out) {
+  long long best = (long long)0x8000000000000000ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    long long p = pack_score(scores[i], index_base + i);
+    best = p > best ? p : best;
+  }
+  for (int o = 16; o; o >>= 1) { long long q = __shfl_xor_sync(0xffffffffu, best, o); best = q > best ? q : best; }
+  __shared__ long long s_b[8];
+  if ((threadIdx.x & 31) == 0) s_b[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) best = s_b[w] > best ? s_b[w] : best;
+    atomicMax(out, best);
+  }
+}
+void launch_score_best(cudaStream_t s, const float* d_scores, int n, long long index_base, long long* d_out, uint64_t* launches) {
+  cudaMemsetAsync(d_out, 0, 8, s);
+  // LLONG_MIN = 0x8000...: set the top byte
+  static const unsigned char top = 0x80;
+  cudaMemsetAsync((char*)d_out + 7, top, 1, s);
+  if (n <= 0) return;
+  int nb = (n + 255) / 256; if (nb > 592) nb = 592;
+  score_best_kernel<<<nb, 256, 0, s>>>(d_scores, n, index_base, d_out);
   if (launches) *launches += 1;
 }
 
@@ -255,15 +597,14 @@ __global__ void fuse_kernel(const __grid_constant__ FuseArgs A) {
 
 void launch_fine_verify_fuse(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
   PipeState* st = w.st;
-  ScoreWS ws; ws.keys = h.fv_keys; ws.s_cnt = h.fv_s; ws.t_cnt = h.fv_t; ws.cap_hash = h.cap_hash; ws.t_rows = 3 * FCCF_TOPK; ws.ss = &st->fv; ws.status = &st->status;
-  int cap_pts = w.c[0].cap;
-  launch_score_build(s, w.p, w.c[0].sub, &st->oct[0].S, &st->oct[1].S, cap_pts, ws, launches);
+  ScoreWS ws = h.fv; ws.ss = &st->fv; ws.status = &st->status;
+  launch_score_build(s, w.p, w.c[0].sub, &st->oct[0].S, &st->oct[1].S, ws, launches);
   ScArgs A; fill_common(A, w.p, ws);
   A.T = h.top_T; A.n_hyp = 3 * FCCF_TOPK; A.n_top = st->n_top; A.s2 = w.c[1].sub; A.scores = h.top_s2;
-  score_launch(s, A, 3 * FCCF_TOPK);
+  score_launch(s, A, 3 * FCCF_TOPK, launches);
   FuseArgs F; F.st = st; F.top_T = h.top_T; F.top_s1 = h.top_s1; F.top_s2 = h.top_s2; F.fine_number = w.p.fine_verify_number;
   fuse_kernel<<<1, 1, 0, s>>>(F);
-  if (launches) *launches += 2;
+  if (launches) *launches += 1;
 }
 
 }  // namespace fccf

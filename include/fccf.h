@@ -44,7 +44,8 @@ typedef struct fccf_params {
   float seclct_cluster_number;                                        /* :171 */
   float rough_threshold_gl;                                           /* :175 */
   int emulate_pcl_overflow; /* 1: reproduce pcl::VoxelGrid's int32 bail-out (output = input) */
-  int reserved[3];
+  int batch_lanes;          /* registrations kept in flight by fccf_register_batch* (0: default 8) */
+  int reserved[2];
 } fccf_params;
 
 typedef struct fccf_timing {
@@ -55,7 +56,8 @@ typedef struct fccf_timing {
   float total_ms;     /* end to end, host pointers in -> matrix out */
   int n_launches;     /* kernels launched for this registration */
   unsigned long long h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host */
-  float stage_ms[8];  /* voxelgrid(main), voxelgrid(pipeline), planes, hypotheses, cluster, quick_verify, fine_verify+fuse, - */
+  float stage_ms[8];  /* voxelgrid(main), voxelgrid(pipeline), planes, hypotheses, cluster, quick_verify, fine_verify+fuse;
+                         [7]: batch entry points only, host wall clock of the whole batch in ms */
 } fccf_timing;
 
 enum { FCCF_OK = 0, FCCF_ERR_CUDA = 1, FCCF_ERR_ARG = 2, FCCF_ERR_CAPACITY = 3, FCCF_ERR_NO_DEVICE = 4 };
@@ -81,9 +83,15 @@ int fccf_register(fccf_ctx* ctx, const float* src_xyz, size_t n_src, const float
 int fccf_register_device(fccf_ctx* ctx, const float* d_src_xyz, size_t n_src, const float* d_tar_xyz, size_t n_tar,
                          float leaf, float T_out[16], fccf_timing* timing);
 
-/* Batch of independent pairs (BASELINE config 4): pair b uses src[b]/tar[b]; T_out is B x 16. */
+/* Batch of independent pairs (BASELINE config 4): pair b uses src[b]/tar[b]; T_out is B x 16.  Up to
+ * params.batch_lanes registrations are in flight at once (one stream + workspace each); results are
+ * bit-identical to fccf_register on each pair.  timing: per-stage device times summed over the pairs,
+ * total_ms = device time of the whole batch (CUDA events spanning every lane), stage_ms[7] = host wall clock. */
 int fccf_register_batch(fccf_ctx* ctx, int n_pairs, const float* const* src_xyz, const size_t* n_src,
                         const float* const* tar_xyz, const size_t* n_tar, float leaf, float* T_out, fccf_timing* timing);
+/* Same with every cloud already resident in device memory (arrays of device pointers, held on the host). */
+int fccf_register_batch_device(fccf_ctx* ctx, int n_pairs, const float* const* d_src_xyz, const size_t* n_src,
+                               const float* const* d_tar_xyz, const size_t* n_tar, float leaf, float* T_out, fccf_timing* timing);
 
 /* replaces: pcl::VoxelGrid<PointXYZ>::filter as called at FCCF.cpp:1668-1678 / 1377-1387.
  * out_xyz: capacity n points; out_cell (int64 linear cell index) / out_cnt may be NULL. */
@@ -104,6 +112,13 @@ int fccf_score_hypotheses(fccf_ctx* ctx, const float* T, size_t n_hyp, const flo
  * times; returns the average kernel milliseconds per launch in *kernel_ms. */
 int fccf_score_hypotheses_bench(fccf_ctx* ctx, const float* T, size_t n_hyp, const float* s1_xyz, size_t n1,
                                 const float* s2_xyz, size_t n2, int repeat, float* scores, float* kernel_ms);
+/* replaces: the best-hypothesis scan (strict `>` first maximum, FCCF.cpp:1559) over the scores of the
+ * last fccf_score_hypotheses[_bench] call, as a block-reduced argmax on the device.  The result is one
+ * packed int64: (order-preserving int32 of the float score) << 32 | (0xFFFFFFFF - (index_base + i));
+ * its signed maximum over several GPUs (one 8-byte all-reduce) is the global best, smallest index
+ * among ties.  packed_host and/or packed_device (a device pointer, e.g. an NCCL buffer) receive it. */
+int fccf_score_best(fccf_ctx* ctx, size_t index_base, int64_t* packed_host, int64_t* packed_device);
+
 /* Per-voxel overlap counts of hypothesis `hyp` of the last fccf_score_hypotheses call: rows of
  * (Lx, Ly, Lz, s, t) for voxels holding both static and moving points; returns rows in *n_rows. */
 int fccf_score_counts(fccf_ctx* ctx, size_t hyp, int32_t* rows, size_t cap_rows, size_t* n_rows);

@@ -232,6 +232,23 @@ def test_score_hypotheses_inlier_counts_bit_exact(ctx, orc):
     assert ctx.score_hypotheses(far[None], s1, s2)[0] == 0.0
 
 
+def test_score_best_is_the_first_maximum(ctx):
+    from fccf_pcr_b200 import dist as D
+
+    rng = np.random.default_rng(33)
+    s1 = (rng.uniform(-1, 1, (2000, 3)) * [4, 3, 1]).astype(np.float32)
+    s2, _ = _moved(rng, s1, 1500, 0, 0)
+    Ts = np.stack([_moved(rng, s1, 1, rng.uniform(-6, 6), rng.uniform(-0.3, 0.3, 3))[1] for _ in range(300)])
+    Ts[17] = Ts[5]; Ts[200] = Ts[5]                      # exact ties: the smallest index must win
+    sc = ctx.score_hypotheses(Ts, s1, s2)
+    packed = ctx.score_best(1000)
+    score, idx = D.unpack_score_index(packed)
+    assert packed == D.local_best(sc, 1000)
+    assert float(score) == float(sc.max()) and int(idx) == 1000 + int(np.argmax(sc))
+    best, gi, _ = D.sharded_best_hypothesis(ctx, Ts, s1, s2)      # world size 1: no collective
+    assert gi == int(np.argmax(sc)) and best == float(sc.max())
+
+
 def test_score_hypotheses_full_size_properties(ctx):
     """BASELINE config 3 size (hundreds of thousands of leftover points): checks that do not need the oracle."""
     rng = np.random.default_rng(32)
