@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -51,6 +52,10 @@ struct Lane {
   size_t last_h2d = 0;
   uint64_t launches = 0, l0 = 0;
   bool busy = false; int pair = -1; bool had_h2d = false;
+  CallArgs* h_call = nullptr;    // pinned
+  cudaGraphExec_t gexec = nullptr;   // the whole pipeline of this lane, captured once per workspace / parameter set
+  int graph_launches = 0;        // kernel nodes in the graph
+  uint64_t params_epoch = 0;
 };
 
 struct fccf_ctx {
@@ -61,6 +66,8 @@ struct fccf_ctx {
   uint64_t launches = 0;           // kernels launched outside the lanes (stand-alone stage entry points)
   std::vector<Lane*> lanes;
   int max_lanes = 8;
+  bool use_graph = true;
+  uint64_t params_epoch = 1;
   int cap_hyp = 1 << 18;
   bool have_run = false;
   float leaf = 0.f;
@@ -102,7 +109,8 @@ static void cloud_carve(Arena& a, CloudWS& w, int cap) {
 static int lane_create(fccf_ctx* ctx, Lane** out) {
   Lane* L = new Lane();
   if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) { delete L; ctx->err = "cudaStreamCreate failed"; return FCCF_ERR_CUDA; }
-  if (cudaMalloc(&L->d_st, sizeof(PipeState)) != cudaSuccess || cudaMallocHost(&L->h_st, sizeof(PipeState)) != cudaSuccess) { delete L; ctx->err = "state allocation failed"; return FCCF_ERR_CUDA; }
+  if (cudaMalloc(&L->d_st, sizeof(PipeState)) != cudaSuccess || cudaMallocHost(&L->h_st, sizeof(PipeState)) != cudaSuccess ||
+      cudaMallocHost(&L->h_call, sizeof(CallArgs)) != cudaSuccess) { delete L; ctx->err = "state allocation failed"; return FCCF_ERR_CUDA; }
   cudaMemset(L->d_st, 0, sizeof(PipeState));
   for (int i = 0; i < 6; i++) cudaEventCreate(&L->ev[i]);
   for (int i = 0; i < 8; i++) cudaEventCreate(&L->sev[i]);
@@ -116,6 +124,8 @@ static void lane_destroy(Lane* L) {
   if (L->hyp_arena.base) cudaFree(L->hyp_arena.base);
   if (L->d_st) cudaFree(L->d_st);
   if (L->h_st) cudaFreeHost(L->h_st);
+  if (L->h_call) cudaFreeHost(L->h_call);
+  if (L->gexec) cudaGraphExecDestroy(L->gexec);
   for (int i = 0; i < 6; i++) cudaEventDestroy(L->ev[i]);
   for (int i = 0; i < 8; i++) cudaEventDestroy(L->sev[i]);
   if (L->stream) cudaStreamDestroy(L->stream);
@@ -129,6 +139,7 @@ static int ensure_capacity(fccf_ctx* ctx, Lane* L, size_t n0, size_t n1) {
   if (need > (size_t)1 << 30) { ctx->err = "cloud too large"; return FCCF_ERR_ARG; }
   int cap = (int)((need + 4095) & ~(size_t)4095);
   CK(cudaStreamSynchronize(L->stream));
+  if (L->gexec) { cudaGraphExecDestroy(L->gexec); L->gexec = nullptr; }
   for (int c = 0; c < 2; c++) {
     if (L->cloud_arena[c].base) CK(cudaFree(L->cloud_arena[c].base));
     if (L->d_raw[c]) CK(cudaFree(L->d_raw[c]));
@@ -148,7 +159,7 @@ static int ensure_capacity(fccf_ctx* ctx, Lane* L, size_t n0, size_t n1) {
   size_t ch = (size_t)ctx->cap_hyp, nbh = ch / RS_TILE + 2;
   size_t bytes = 0;
   auto add = [&](size_t x) { bytes += (x + 255) & ~(size_t)255; };
-  add(4 * FCCF_MAXMATCH); add(4 * FCCF_MAXMATCH); add(48 * ch); add(32 * ch); add(16 * ch);
+  add(4 * FCCF_MAXMATCH); add(4 * FCCF_MAXMATCH); add(48 * ch); add(32 * ch); add(16 * ch); add(8 * ch);
   add(8 * ch); add(8 * ch); add(4 * ch); add(4 * ch); add(nbh * 1024);
   for (int k = 0; k < 5; k++) add(4 * ch);
   add(8 * ch); add(8 * ch);
@@ -163,7 +174,7 @@ static int ensure_capacity(fccf_ctx* ctx, Lane* L, size_t n0, size_t n1) {
   Arena& a = L->hyp_arena;
   h.cap_hyp = ctx->cap_hyp;
   h.match_cnt = a.take<int>(FCCF_MAXMATCH); h.match_off = a.take<int>(FCCF_MAXMATCH);
-  h.hyp_T = a.take<float>(12 * ch); h.hyp_qt = a.take<float>(8 * ch); h.hyp_ax = a.take<float>(4 * ch);
+  h.hyp_T = a.take<float>(12 * ch); h.hyp_qt = a.take<float>(8 * ch); h.hyp_ax = a.take<float>(4 * ch); h.hyp_an = a.take<double>(ch);
   h.ckeyA = a.take<u64>(ch); h.ckeyB = a.take<u64>(ch); h.cidxA = a.take<u32>(ch); h.cidxB = a.take<u32>(ch); h.chist = a.take<u32>(nbh * 256);
   h.c_state = a.take<int>(ch); h.c_size = a.take<int>(ch); h.c_seeds = a.take<int>(ch); h.c_perm = a.take<int>(ch); h.c_key = a.take<int>(ch);
   h.c_members = a.take<int>(2 * ch); h.c_mdist = a.take<float>(2 * ch);
@@ -202,7 +213,9 @@ fccf_ctx* fccf_create(int device, const fccf_params* params) {
   fccf_ctx* ctx = new fccf_ctx();
   ctx->device = device;
   if (params) ctx->p = *params; else fccf_default_params(&ctx->p);
-  if (ctx->p.batch_lanes > 0) ctx->max_lanes = ctx->p.batch_lanes > 64 ? 64 : ctx->p.batch_lanes;
+  if (ctx->p.batch_lanes > 0) ctx->max_lanes = ctx->p.batch_lanes > 256 ? 256 : ctx->p.batch_lanes;
+  if (const char* e = getenv("FCCF_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
+  score_init_attributes();
   Lane* L = nullptr;
   if (lane_create(ctx, &L) != FCCF_OK) { delete ctx; return nullptr; }
   ctx->lanes.push_back(L);
@@ -226,7 +239,11 @@ void fccf_destroy(fccf_ctx* ctx) {
 }
 
 const char* fccf_last_error(const fccf_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no usable CUDA device)"; }
-int fccf_set_params(fccf_ctx* ctx, const fccf_params* params) { if (!ctx || !params) return FCCF_ERR_ARG; ctx->p = *params; return FCCF_OK; }
+int fccf_set_params(fccf_ctx* ctx, const fccf_params* params) {
+  if (!ctx || !params) return FCCF_ERR_ARG;
+  ctx->p = *params; ctx->params_epoch++;     // captured graphs hold the old values: re-capture lazily
+  return FCCF_OK;
+}
 uint64_t fccf_launch_count(const fccf_ctx* ctx) {
   if (!ctx) return 0;
   uint64_t n = ctx->launches;
@@ -237,8 +254,33 @@ void* fccf_stream_handle(const fccf_ctx* ctx) { return ctx ? (void*)ctx->stream 
 
 }  // extern "C"
 
+namespace fccf {
+// theta(c) = (float)(acos((double)c) * 180 / pi) as in compute_normal_angel (FCCF.cpp:375-376), monotone
+// non-increasing in c: bisection over the ordered float bit patterns of [-1, 1]
+float angle_cut(float thr_deg, bool strict) {
+  auto theta = [](float c) { return (float)(acos((double)c) * 180 / 3.14159265358979323846); };
+  auto pass = [&](float c) { float th = theta(c); return strict ? (th < thr_deg) : (th <= thr_deg); };
+  auto ord = [](float f) { int32_t i; memcpy(&i, &f, 4); return i >= 0 ? (int64_t)i : (int64_t)(i ^ 0x7fffffff); };
+  auto unord = [](int64_t o) { int32_t i = (int32_t)o; if (i < 0) i ^= 0x7fffffff; float f; memcpy(&f, &i, 4); return f; };
+  if (!pass(1.0f)) return 2.0f;          // nothing passes
+  int64_t lo = ord(-1.0f), hi = ord(1.0f);   // invariant: pass(unord(hi))
+  if (pass(-1.0f)) return -1.0f;
+  while (hi - lo > 1) { int64_t mid = lo + (hi - lo) / 2; if (pass(unord(mid))) hi = mid; else lo = mid; }
+  return unord(hi);
+}
+AngleCuts make_angle_cuts(const fccf_params& p) {
+  AngleCuts c;
+  c.third_lt = angle_cut(p.third_plane_normal_threshold, true);
+  c.qv_lt = angle_cut(p.quick_verify_angel_threshold, true);
+  c.cluster_lt = angle_cut(p.cluster_angel_threshold, true);
+  c.grow1_le = angle_cut(p.normal_vector_threshold1, false);
+  c.grow2_le = angle_cut(p.normal_vector_threshold2, false);
+  return c;
+}
+}  // namespace fccf
+
 static Work make_work(fccf_ctx* ctx, Lane* L, float leaf) {
-  Work w; w.c[0] = L->c[0]; w.c[1] = L->c[1]; w.st = L->d_st; w.p = ctx->p; w.leaf = leaf;
+  Work w; w.c[0] = L->c[0]; w.c[1] = L->c[1]; w.st = L->d_st; w.p = ctx->p; w.cuts = make_angle_cuts(ctx->p); w.leaf = leaf;
   return w;
 }
 
@@ -252,9 +294,37 @@ static int check_status(fccf_ctx* ctx, int st) {
   return FCCF_ERR_CAPACITY;
 }
 
-// Enqueues one whole registration on the lane's stream (no host synchronisation): optional H2D of both
-// raw clouds, every kernel of main() + computer_transform_guess, and the read-back of the result block.
-// tar/src: host pointers (host_in) or device pointers.
+// Every kernel of main() + computer_transform_guess and the read-back of the result block, in stream
+// order on the lane's stream.  All sizes are device-side and the per-call values (point counts, leaf,
+// raw-cloud pointers) are read from st->call, so the sequence is identical for every call on this lane:
+// it is captured into a CUDA graph once and replayed afterwards.
+static int lane_pipeline(fccf_ctx* ctx, Lane* L, uint64_t* launches, bool capturing) {
+  cudaStream_t s = L->stream;
+  // inside a capture a plain cudaEventRecord is only a dependency; the External flag makes a timing node
+  auto rec = [&](cudaEvent_t e) { return capturing ? cudaEventRecordWithFlags(e, s, cudaEventRecordExternal) : cudaEventRecord(e, s); };
+  Work w = make_work(ctx, L, 0.f);
+  launch_init_state(s, L->d_st, launches);
+  launch_voxelgrid(s, w, 0, 2, launches);            // main(): FCCF.cpp:1668-1678
+  CK(rec(L->ev[2]));
+  launch_voxelgrid(s, w, 1, 2, launches);            // FCCF.cpp:1377-1387
+  CK(rec(L->sev[0]));
+  launch_planes(s, w, 2, 1, launches);               // FCCF.cpp:1400-1401
+  CK(rec(L->sev[1]));
+  launch_hypotheses(s, w, L->h, launches);           // FCCF.cpp:1406-1427, 1439-1462
+  CK(rec(L->sev[2]));
+  launch_cluster(s, w, L->h, launches);              // FCCF.cpp:1464-1466
+  CK(rec(L->sev[3]));
+  launch_quick_verify(s, w, L->h, launches);         // FCCF.cpp:1468-1494
+  CK(rec(L->sev[4]));
+  launch_fine_verify_fuse(s, w, L->h, launches);     // FCCF.cpp:1499-1606
+  CK(rec(L->ev[3]));
+  CK(cudaMemcpyAsync(L->h_st, L->d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
+  return FCCF_OK;
+}
+
+// Enqueues one whole registration on the lane's stream (no host synchronisation): the per-call block,
+// optional H2D of both raw clouds, then the pipeline (graph replay).  tar/src: host pointers (host_in)
+// or device pointers.
 static int lane_enqueue(fccf_ctx* ctx, Lane* L, const float* src, size_t n_src, const float* tar, size_t n_tar, float leaf, bool host_in) {
   cudaStream_t s = L->stream;
   L->l0 = L->launches; L->had_h2d = host_in;
@@ -263,26 +333,31 @@ static int lane_enqueue(fccf_ctx* ctx, Lane* L, const float* src, size_t n_src, 
     if (n_tar) CK(cudaMemcpyAsync(L->d_raw[0], tar, n_tar * 12, cudaMemcpyHostToDevice, s));
     if (n_src) CK(cudaMemcpyAsync(L->d_raw[1], src, n_src * 12, cudaMemcpyHostToDevice, s));
     L->last_h2d = (n_tar + n_src) * 12;
-    L->c[0].raw = L->d_raw[0]; L->c[1].raw = L->d_raw[1];
-  } else { L->c[0].raw = tar; L->c[1].raw = src; L->last_h2d = 0; }
+  } else L->last_h2d = 0;
+  L->h_call->n0 = (int)n_tar; L->h_call->n1 = (int)n_src; L->h_call->leaf = leaf; L->h_call->pad = 0;
+  L->h_call->raw[0] = host_in ? L->d_raw[0] : tar; L->h_call->raw[1] = host_in ? L->d_raw[1] : src;
+  CK(cudaMemcpyAsync(&L->d_st->call, L->h_call, sizeof(CallArgs), cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(L->ev[1], s));
-  Work w = make_work(ctx, L, leaf);
-  launch_init_state(s, L->d_st, (int)n_tar, (int)n_src, &L->launches);
-  launch_voxelgrid(s, w, 0, 2, &L->launches);            // main(): FCCF.cpp:1668-1678
-  CK(cudaEventRecord(L->ev[2], s));
-  launch_voxelgrid(s, w, 1, 2, &L->launches);            // FCCF.cpp:1377-1387
-  cudaEventRecord(L->sev[0], s);
-  launch_planes(s, w, 2, 1, &L->launches);               // FCCF.cpp:1400-1401
-  cudaEventRecord(L->sev[1], s);
-  launch_hypotheses(s, w, L->h, &L->launches);           // FCCF.cpp:1406-1427, 1439-1462
-  cudaEventRecord(L->sev[2], s);
-  launch_cluster(s, w, L->h, &L->launches);              // FCCF.cpp:1464-1466
-  cudaEventRecord(L->sev[3], s);
-  launch_quick_verify(s, w, L->h, &L->launches);         // FCCF.cpp:1468-1494
-  cudaEventRecord(L->sev[4], s);
-  launch_fine_verify_fuse(s, w, L->h, &L->launches);     // FCCF.cpp:1499-1606
-  CK(cudaEventRecord(L->ev[3], s));
-  CK(cudaMemcpyAsync(L->h_st, L->d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
+  if (ctx->use_graph) {
+    if (!L->gexec || L->params_epoch != ctx->params_epoch) {
+      if (L->gexec) { cudaGraphExecDestroy(L->gexec); L->gexec = nullptr; }
+      cudaGraph_t g = nullptr;
+      uint64_t cnt = 0;
+      CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+      int rc = lane_pipeline(ctx, L, &cnt, true);
+      cudaError_t e = cudaStreamEndCapture(s, &g);
+      if (rc != FCCF_OK || e != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); ctx->err = std::string("graph capture failed: ") + cudaGetErrorString(e); cudaGetLastError(); return FCCF_ERR_CUDA; }
+      e = cudaGraphInstantiate(&L->gexec, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) { L->gexec = nullptr; ctx->err = std::string("graph instantiation failed: ") + cudaGetErrorString(e); return FCCF_ERR_CUDA; }
+      L->graph_launches = (int)cnt; L->params_epoch = ctx->params_epoch;
+    }
+    CK(cudaGraphLaunch(L->gexec, s));
+    L->launches += (uint64_t)L->graph_launches;
+  } else {
+    int rc = lane_pipeline(ctx, L, &L->launches, false);
+    if (rc) return rc;
+  }
   CK(cudaEventRecord(L->ev[4], s));
   L->busy = true;
   return FCCF_OK;
@@ -293,7 +368,6 @@ static int lane_finish(fccf_ctx* ctx, Lane* L, float T_out[16], fccf_timing* tm)
   CK(cudaStreamSynchronize(L->stream));
   CK(cudaGetLastError());
   L->busy = false;
-  L->c[0].raw = L->d_raw[0]; L->c[1].raw = L->d_raw[1];
   for (int i = 0; i < 16; i++) T_out[i] = L->h_st->T_final[i];
   if (tm) {
     memset(tm, 0, sizeof *tm);
@@ -406,7 +480,9 @@ int fccf_voxelgrid(fccf_ctx* ctx, const float* xyz, size_t n, float leaf, float*
   cudaStream_t s = ctx->stream;
   if (n) CK(cudaMemcpyAsync(ctx->L0().d_raw[0], xyz, n * 12, cudaMemcpyHostToDevice, s));
   Work w = make_work(ctx, ctx->lanes[0], leaf);
-  launch_init_state(s, ctx->L0().d_st, (int)n, 0, &ctx->launches);
+  { CallArgs* hc = ctx->L0().h_call; hc->n0 = (int)n; hc->n1 = 0; hc->leaf = leaf; hc->pad = 0; hc->raw[0] = ctx->L0().d_raw[0]; hc->raw[1] = ctx->L0().d_raw[1];
+    CK(cudaMemcpyAsync(&ctx->L0().d_st->call, hc, sizeof(CallArgs), cudaMemcpyHostToDevice, s)); }
+  launch_init_state(s, ctx->L0().d_st, &ctx->launches);
   launch_voxelgrid(s, w, 0, 1, &ctx->launches);
   CK(cudaMemcpyAsync(ctx->L0().h_st, ctx->L0().d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -428,7 +504,9 @@ int fccf_extract_planes(fccf_ctx* ctx, const float* xyz, size_t n, int32_t* n_fa
   if (rc) return rc;
   cudaStream_t s = ctx->stream;
   Work w = make_work(ctx, ctx->lanes[0], 1.0f);
-  launch_init_state(s, ctx->L0().d_st, 0, 0, &ctx->launches);
+  { CallArgs* hc = ctx->L0().h_call; hc->n0 = 0; hc->n1 = 0; hc->leaf = 1.0f; hc->pad = 0; hc->raw[0] = ctx->L0().d_raw[0]; hc->raw[1] = ctx->L0().d_raw[1];
+    CK(cudaMemcpyAsync(&ctx->L0().d_st->call, hc, sizeof(CallArgs), cudaMemcpyHostToDevice, s)); }
+  launch_init_state(s, ctx->L0().d_st, &ctx->launches);
   if (n) CK(cudaMemcpyAsync(ctx->L0().c[0].vg_xyz[1], xyz, n * 12, cudaMemcpyHostToDevice, s));
   int nn = (int)n;
   CK(cudaMemcpyAsync(&ctx->L0().d_st->vg[1][0].n_out, &nn, 4, cudaMemcpyHostToDevice, s));

@@ -21,13 +21,13 @@ namespace fccf {
 
 struct ClArgs {
   PipeState* st;
-  const float* hyp_qt; float* hyp_ax;
+  const float* hyp_qt; float* hyp_ax; double* hyp_an;
   u64* keys; const u32* order;     // order: sorted position -> global hypothesis index
   float* xs;                        // x in sorted order (global index space)
   int *state, *size, *seeds, *perm, *key, *members;
   float* mdist;
   float* centre;
-  float thr_n, ang_thr, rad, sel_num;
+  float thr_n, ang_cut, rad, sel_num;   // ang_cut: cosine cut of cluster_angel_threshold (strict <)
   int* nbits;                       // device word: key width for the sort
   int cap_hyp;
 };
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) cluster_prep_kernel(const __grid_constant
   f3 ax = quat_rotate(Q, mk3(1, 0, 0));
   float* o = A.hyp_ax + (size_t)i * 4;
   o[0] = ax.x; o[1] = ax.y; o[2] = ax.z; o[3] = 0.f;
+  A.hyp_an[i] = normal_norm(ax.x, ax.y, ax.z);
   int ty = (i >= st->hyp_off[2]) ? 2 : ((i >= st->hyp_off[1]) ? 1 : 0);
   float x = q[4];
   u32 k;
@@ -59,13 +60,12 @@ __global__ void __launch_bounds__(256) cluster_xs_kernel(const __grid_constant__
   A.xs[k] = (x != x) ? CUDART_INF_F : x;
 }
 
-__device__ __forceinline__ bool cl_neigh(const float* qi, const float* ai, const float* qj, const float* aj, float r2, float ang_thr, float* dist) {
+__device__ __forceinline__ bool cl_neigh(const float* qi, const float* ai, double ni, const float* qj, const float* aj, double nj, float r2, float ang_cut, float* dist) {
   float d0 = qi[4] - qj[4], d1 = qi[5] - qj[5], d2 = qi[6] - qj[6];
   float d = 0.f; d += d0 * d0; d += d1 * d1; d += d2 * d2;    // flann::L2_Simple
   if (!(d < r2)) return false;
-  float a = normal_angle(ai[0], ai[1], ai[2], aj[0], aj[1], aj[2]);
   if (dist) *dist = d;
-  return a < ang_thr;
+  return angle_lt(normal_cos_n(ai[0], ai[1], ai[2], ni, aj[0], aj[1], aj[2], nj), ang_cut);   // compute_normal_angel(...) < 2 degrees (FCCF.cpp:1110)
 }
 __device__ __forceinline__ void cl_window(const float* xs, int n, float x, double rr, int& lo, int& hi) {
   if (!isfinite(x)) { lo = 0; hi = 0; return; }   // a non-finite translation has no neighbour (d is NaN/inf)
@@ -115,8 +115,10 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
   const int n = st->n_hyp[ty], base = st->hyp_off[ty], tnum = st->hyp_off[3];
   const float* qt = A.hyp_qt + (size_t)base * 8;
   const float* ax = A.hyp_ax + (size_t)base * 4;
+  const double* an = A.hyp_an + base;
   float* centre = A.centre + (size_t)ty * FCCF_MAXCENTRE * 8;
   __shared__ int s_flag, s_K, s_E;
+  __shared__ unsigned long long s_sort[40];
   __shared__ int s_emit[FCCF_MAXCENTRE];
   __shared__ int s_mem[32][CL_WSCR];
   __shared__ float s_md[32][CL_WSCR];
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
         if (j >= i) continue;
         int sj = ((volatile int*)state)[j];
         if (sj == 2) continue;
-        if (cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, qt + (size_t)j * 8, ax + (size_t)j * 4, r2, A.ang_thr, nullptr)) {
+        if (cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, an[i], qt + (size_t)j * 8, ax + (size_t)j * 4, an[j], r2, A.ang_cut, nullptr)) {
           if (sj == 1) { found_seed = true; break; }
           all_dec = false;
         }
@@ -194,13 +196,13 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
     int cnt = 0;
     for (int kk = lo; kk < hi; kk++) {
       int j = (int)order[kk] - base;
-      if (cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, qt + (size_t)j * 8, ax + (size_t)j * 4, r2, A.ang_thr, nullptr)) cnt++;
+      if (cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, an[i], qt + (size_t)j * 8, ax + (size_t)j * 4, an[j], r2, A.ang_cut, nullptr)) cnt++;
     }
     size[k] = cnt; key[k] = cnt; perm[k] = k;
   }
   __syncthreads();
   // ---- range_cluster: exchange sort by size ----
-  if (t < 32) warp_exchange_sort(key, perm, K, [](int a, int b) { return a < b; });
+  block_exchange_sort(key, perm, K, s_sort);
   __syncthreads();
   // ---- adaptive cut-off walk (FCCF.cpp:1123-1229) ----
   if (t == 0) {
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
     int cntw = 0;
     for (int k0 = lo; k0 < hi; k0 += 32) {
       int kk = k0 + lane; bool ok = false; float d = 0.f; int j = -1;
-      if (kk < hi) { j = (int)order[kk] - base; ok = cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, qt + (size_t)j * 8, ax + (size_t)j * 4, r2, A.ang_thr, &d); }
+      if (kk < hi) { j = (int)order[kk] - base; ok = cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, an[i], qt + (size_t)j * 8, ax + (size_t)j * 4, an[j], r2, A.ang_cut, &d); }
       unsigned b = __ballot_sync(0xffffffffu, ok);
       if (ok) { int p = cntw + __popc(b & ((1u << lane) - 1u)); s_mem[warp][p] = j; s_md[warp][p] = d; }
       cntw += __popc(b);
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
     __syncthreads();
     for (int k0 = lo; k0 < hi; k0 += 1024) {
       int kk = k0 + t; bool ok = false; float d = 0.f; int j = -1;
-      if (kk < hi) { j = (int)order[kk] - base; ok = cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, qt + (size_t)j * 8, ax + (size_t)j * 4, r2, A.ang_thr, &d); }
+      if (kk < hi) { j = (int)order[kk] - base; ok = cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, an[i], qt + (size_t)j * 8, ax + (size_t)j * 4, an[j], r2, A.ang_cut, &d); }
       unsigned b = __ballot_sync(0xffffffffu, ok);
       if (lane == 0) s_w2[warp] = __popc(b);
       __syncthreads();
@@ -292,10 +294,10 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
 void launch_cluster(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
   ClArgs A;
   PipeState* st = w.st;
-  A.st = st; A.hyp_qt = h.hyp_qt; A.hyp_ax = h.hyp_ax; A.keys = h.ckeyA; A.order = h.cidxA; A.xs = (float*)h.c_mdist + h.cap_hyp;
+  A.st = st; A.hyp_qt = h.hyp_qt; A.hyp_ax = h.hyp_ax; A.hyp_an = h.hyp_an; A.keys = h.ckeyA; A.order = h.cidxA; A.xs = (float*)h.c_mdist + h.cap_hyp;
   A.state = h.c_state; A.size = h.c_size; A.seeds = h.c_seeds; A.perm = h.c_perm; A.key = h.c_key; A.members = h.c_members; A.mdist = h.c_mdist;
   A.centre = h.centre;
-  A.thr_n = w.p.cluster_number_threshold; A.ang_thr = w.p.cluster_angel_threshold; A.rad = w.p.cluster_distance_threshold; A.sel_num = w.p.seclct_cluster_number;
+  A.thr_n = w.p.cluster_number_threshold; A.ang_cut = w.cuts.cluster_lt; A.rad = w.p.cluster_distance_threshold; A.sel_num = w.p.seclct_cluster_number;
   A.nbits = &st->tickets[20]; A.cap_hyp = h.cap_hyp;
   int cap = h.cap_hyp;
   cluster_prep_kernel<<<(cap + 255) / 256, 256, 0, s>>>(A);

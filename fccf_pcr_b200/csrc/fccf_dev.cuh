@@ -39,6 +39,28 @@ __device__ __forceinline__ float normal_angle(float x1, float y1, float z1, floa
   float cos_theta = (float)((double)n1n3 / (na * nb));
   return (float)(acos((double)cos_theta) * 180 / 3.14159265358979323846);
 }
+// The float cosine compute_normal_angel feeds to acos, and threshold tests on it.  theta(c) =
+// (float)(acos((double)c) * 180 / pi) is monotone non-increasing in the float c, so
+//     theta <  thr   <=>   cut_lt <= c <= 1          (cut_lt = smallest float with theta(c) <  thr)
+//     theta >  thr   <=>   -1 <= c < cut_le          (cut_le = smallest float with theta(c) <= thr)
+// and theta is NaN exactly when c is NaN or outside [-1, 1] (every comparison with it is false, Q9).
+// The cuts are found once on the host by bisection over the float bit patterns with the same
+// expression (AngleCuts in fccf_internal.h), which removes the acos from every pairwise test.
+__device__ __forceinline__ float normal_cos_n(float x1, float y1, float z1, double na, float x2, float y2, float z2, double nb) {
+  double a0 = x1, a1 = y1, a2 = z1, b0 = x2, b1 = y2, b2 = z2;
+  float n1n3 = (float)sum3d(a0 * b0, a1 * b1, a2 * b2);
+  return (float)((double)n1n3 / (na * nb));
+}
+__device__ __forceinline__ double normal_norm(float x, float y, float z) { double a0 = x, a1 = y, a2 = z; return sqrt(sum3d(a0 * a0, a1 * a1, a2 * a2)); }
+__device__ __forceinline__ float normal_cos(float x1, float y1, float z1, float x2, float y2, float z2) {
+  return normal_cos_n(x1, y1, z1, normal_norm(x1, y1, z1), x2, y2, z2, normal_norm(x2, y2, z2));
+}
+__device__ __forceinline__ bool angle_lt(float c, float cut_lt) { return c >= cut_lt && c <= 1.0f; }          // compute_normal_angel(...) < thr
+__device__ __forceinline__ bool angle_not_gt(float c, float cut_le) { return !(c >= -1.0f && c < cut_le); }  // !(compute_normal_angel(...) > thr)
+// FCCF.cpp:379-389 with the threshold given as its cosine cut
+__device__ __forceinline__ bool compare_normal_cut(float x1, float y1, float z1, float x2, float y2, float z2, float cut_le) {
+  return angle_not_gt(normal_cos(x1, y1, z1, x2, y2, z2), cut_le);
+}
 // FCCF.cpp:379-389
 __device__ __forceinline__ bool compare_normal(float x1, float y1, float z1, float x2, float y2, float z2, float thr) {
   float th = normal_angle(x1, y1, z1, x2, y2, z2);
@@ -201,6 +223,74 @@ __device__ void warp_exchange_sort(K* key, int* perm, int n, Less less) {
     }
     if (moved && lane == 0) { key[i] = cur; perm[i] = curp; }
     __syncwarp();
+  }
+}
+
+// Block-cooperative form of the same exchange sort for keys with a total order (ints, non-NaN floats).
+// Pass i rotates the chain of strict left-to-right maxima of key[i..n): the maximum (first occurrence)
+// goes to position i and every other record slot receives the previous record.  With the running
+// maximum found by a block-wide prefix-max scan of (ordered key << 32 | ~position) a pass costs a few
+// barriers, and the sort stops as soon as key[i..n) is non-increasing (all later passes are no-ops) —
+// after about as many passes as there are elements above the minimum.  All threads of the block call
+// it; key/perm in shared or global memory; s_scratch: 34 u64 of shared memory.
+__device__ __forceinline__ unsigned ord_key(int v) { return (unsigned)v ^ 0x80000000u; }
+__device__ __forceinline__ unsigned ord_key(float f) { unsigned b = __float_as_uint(f + 0.0f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+template <typename K>
+__device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long* s_scratch) {
+  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, warp = t >> 5, nw = nt >> 5;
+  unsigned long long* s_w = s_scratch;                 // [32] exclusive prefix max over warps
+  unsigned long long* s_tot = s_scratch + 32;          // [1]  chunk maximum
+  unsigned long long* s_carry = s_scratch + 33;        // [1]  running maximum (packed) ...
+  K* s_ck = (K*)(s_scratch + 34);                      //      ... and the record it stands for
+  int* s_cp = (int*)(s_scratch + 35);
+  for (int i = 0; i + 1 < n; i++) {
+    // stop when key[i..n) is non-increasing: every remaining pass would be a no-op
+    int asc = 0;
+    for (int j = i + t; j + 1 < n; j += nt) asc |= (key[j] < key[j + 1]) ? 1 : 0;
+    if (!__syncthreads_or(asc)) break;
+    if (t == 0) { *s_carry = ((unsigned long long)ord_key(key[i]) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i); *s_ck = key[i]; *s_cp = perm[i]; }
+    __syncthreads();
+    for (int base = i + 1; base < n; base += nt) {
+      const int j = base + t;
+      const bool in = j < n;
+      K my_k = K(); int my_p = 0;
+      if (in) { my_k = key[j]; my_p = perm[j]; }
+      const unsigned long long mine = in ? (((unsigned long long)ord_key(my_k) << 32) | (unsigned long long)(0xffffffffu - (unsigned)j)) : 0ull;
+      unsigned long long inc = mine;                     // inclusive prefix max inside the warp
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d && y > inc) inc = y; }
+      if (lane == 31) s_w[warp] = inc;
+      __syncthreads();
+      if (warp == 0) {
+        unsigned long long w = lane < nw ? s_w[lane] : 0ull, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d && y > wi) wi = y; }
+        unsigned long long ex = __shfl_up_sync(0xffffffffu, wi, 1);
+        if (lane == 0) ex = 0ull;
+        unsigned long long tot = __shfl_sync(0xffffffffu, wi, 31);
+        s_w[lane] = ex;
+        if (lane == 0) *s_tot = tot;
+      }
+      __syncthreads();
+      const unsigned long long carry = *s_carry, tot = *s_tot;
+      unsigned long long before = __shfl_up_sync(0xffffffffu, inc, 1);
+      if (lane == 0) before = 0ull;
+      if (s_w[warp] > before) before = s_w[warp];
+      const bool from_carry = carry > before;            // the running maximum before j lies in an earlier chunk (or at i)
+      if (from_carry) before = carry;
+      const bool record = in && ((mine >> 32) > (before >> 32));   // strictly greater key
+      K src_k = K(); int src_p = 0;
+      if (record) {
+        if (from_carry) { src_k = *s_ck; src_p = *s_cp; }
+        else { const int pp = (int)(0xffffffffu - (unsigned)(before & 0xffffffffull)); src_k = key[pp]; src_p = perm[pp]; }
+      }
+      __syncthreads();                                   // all reads of this chunk are done
+      if (record) { key[j] = src_k; perm[j] = src_p; }
+      if (in && mine == tot && (tot >> 32) > (carry >> 32)) { *s_carry = mine; *s_ck = my_k; *s_cp = my_p; }   // this chunk's last record
+      __syncthreads();
+    }
+    if (t == 0) { key[i] = *s_ck; perm[i] = *s_cp; }
+    __syncthreads();
   }
 }
 

@@ -62,7 +62,13 @@ struct ScoreState {          // fine-verify lattice + static voxel table set-up 
   int n1, n2, n_occ, cap_eff, nbits, n_keys, mode, pad;
   int tickets[4];
 };
+struct CallArgs {            // per-call values, copied to the device before the (graph-replayed) pipeline runs
+  int n0, n1;                // raw point counts: cloud "1" (TAR file), cloud "2" (SRC file)
+  float leaf; int pad;
+  const float* raw[2];       // raw clouds (device)
+};
 struct PipeState {
+  CallArgs call;
   VGState vg[2][2];          // [stage: 0 main(), 1 computer_transform_guess][cloud: 0 = "1" (TAR file), 1 = "2" (SRC file)]
   OctState oct[2];
   FaceTable ft[2];
@@ -116,14 +122,22 @@ struct CloudWS {
   int* face_vox;             // member lists of the selected faces (debug)
   int* face_off;
 };
+// Cosine cuts of the angle thresholds (see fccf_dev.cuh: angle_lt / angle_not_gt): found on the host by
+// bisection over the float bit patterns with compute_normal_angel's own expression.
+struct AngleCuts { float third_lt, qv_lt, cluster_lt, grow1_le, grow2_le; };
+float angle_cut(float thr_deg, bool strict);   // smallest float c with theta(c) < thr (strict) or <= thr
+AngleCuts make_angle_cuts(const fccf_params& p);
+
 struct Work {
   CloudWS c[2];
   PipeState* st;
   fccf_params p;
+  AngleCuts cuts;
   float leaf;
 };
 
-void launch_init_state(cudaStream_t s, PipeState* st, int n0, int n1, uint64_t* launches);
+void launch_init_state(cudaStream_t s, PipeState* st, uint64_t* launches);   // reads st->call
+void score_init_attributes();   // one-time function attributes (not allowed inside a stream capture)
 // VoxelGrid stage `stage` (0: on raw clouds, 1: on the stage-0 output) for both clouds
 void launch_voxelgrid(cudaStream_t s, const Work& w, int stage, int ncloud, uint64_t* launches);
 // face_extrate for both clouds (input: vg_xyz[1] with st->vg[1][c].n_out points)
@@ -149,6 +163,7 @@ struct HypWS {
   float* hyp_T;              // cap_hyp x 12 (3x4 row-major), pools concatenated: type0, type1, type2
   float* hyp_qt;             // cap_hyp x 8: qw qx qy qz tx ty tz pad
   float* hyp_ax;             // cap_hyp x 4: rotated x axis
+  double* hyp_an;            // cap_hyp: its norm (double), for the cosine form of the 2-degree test
   u64 *ckeyA, *ckeyB; u32 *cidxA, *cidxB; u32* chist;
   int* c_state;              // per hypothesis: seed state
   int* c_size;               // per hypothesis: cluster size if seed

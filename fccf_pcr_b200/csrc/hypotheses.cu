@@ -17,7 +17,7 @@ struct HypArgs {
   int* match_cnt; int* match_off;
   float* hyp_T; float* hyp_qt;
   int cap_hyp;
-  float tmin, tmax, rough, same_thr, third_thr, third_ang;
+  float tmin, tmax, rough, same_thr, third_thr, third_cut;   // third_cut: cosine cut of third_plane_normal_threshold (strict <)
 };
 
 struct Plane { f3 c, n; float size; };
@@ -29,7 +29,7 @@ __device__ __forceinline__ Plane load_plane(const FaceTable& f, int i) {
 // FCCF.cpp:841-1018.  EMIT=false: only count the hypotheses this match pushes.
 template <bool EMIT>
 __device__ int hyp_generate(const FaceTable& f1, const FaceTable& f2, int i11, int i12, int i21, int i22,
-                            float third_thr, float third_ang, float* outT, float* outQ) {
+                            float third_thr, float third_cut, float* outT, float* outQ) {
   Plane P11 = load_plane(f1, i11), P12 = load_plane(f1, i12), P21 = load_plane(f2, i21), P22 = load_plane(f2, i22);
   f3 n1 = P11.n, m1 = P12.n, n2 = P21.n, m2 = P22.n;
   f3 r1 = cross(n2, n1); normalize(r1);
@@ -59,12 +59,14 @@ __device__ int hyp_generate(const FaceTable& f1, const FaceTable& f2, int i11, i
     if (k3 == i11 || k3 == i12) continue;
     Plane P13 = load_plane(f1, k3);
     if (!(fabsf(dot(n1cm1, P13.n)) > third_thr)) continue;
+    const double n13 = normal_norm(P13.n.x, P13.n.y, P13.n.z);
     for (int k2 = 0; k2 < F2; k2++) {
       if (k2 == i21 || k2 == i22) continue;
       Plane P2 = load_plane(f2, k2);
       f3 cn = tf_so3(T, P2.n);     // transformPointCloudWithNormals (FCCF.cpp:948), translation still 0
-      float a3 = normal_angle(P13.n.x, P13.n.y, P13.n.z, cn.x, cn.y, cn.z);
-      if (a3 < third_ang && fabsf(dot(n2cm2, cn)) > third_thr) {
+      // compute_normal_angel(k1, k2) < third_plane_normal_threshold (FCCF.cpp:949,958) through its cosine cut
+      float c3 = normal_cos_n(P13.n.x, P13.n.y, P13.n.z, n13, cn.x, cn.y, cn.z, normal_norm(cn.x, cn.y, cn.z));
+      if (angle_lt(c3, third_cut) && fabsf(dot(n2cm2, cn)) > third_thr) {
         if (EMIT) {
           f3 c23 = tf_se3(T, P2.c);
           f3 k1 = P13.n, kk2 = cn;
@@ -110,12 +112,10 @@ __device__ int hyp_generate(const FaceTable& f1, const FaceTable& f2, int i11, i
   return count;
 }
 
-__global__ void __launch_bounds__(1024) pairs_match_kernel(const __grid_constant__ HypArgs A) {
+__global__ void __launch_bounds__(256) base_pairs_kernel(const __grid_constant__ HypArgs A) {
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  __shared__ int s_w[32];
-  __shared__ u64 s_w64[32];
-  __shared__ u64 s_carry;
+  __shared__ int s_w[8];
   // ---- select_base for both clouds (FCCF.cpp:429-468) ----
   for (int c = 0; c < 2; c++) {
     const FaceTable& f = st->ft[c];
@@ -142,23 +142,37 @@ __global__ void __launch_bounds__(1024) pairs_match_kernel(const __grid_constant
       else if (ta > th1 && tb <= th1) ty = 2;
       B.type[k] = ty;
     }
-    if (t == 0) { int tot = 0; for (int w2 = 0; w2 < 32; w2++) tot += s_w[w2]; B.B = tot; }
+    if (t == 0) { int tot = 0; for (int w2 = 0; w2 < 8; w2++) tot += s_w[w2]; B.B = tot; }
     __syncthreads();
   }
-  // ---- match loop (FCCF.cpp:1415-1427): counts ----
+}
+
+// ---- match loop (FCCF.cpp:1415-1427): one thread per (pair of cloud 1, pair of cloud 2): descriptor test
+// (included angle within 5 degrees, same roughness type) and the number of hypotheses the match pushes ----
+__global__ void __launch_bounds__(128) match_count_kernel(const __grid_constant__ HypArgs A) {
+  PipeState* st = A.st;
   const int B1 = st->base[0].B, B2 = st->base[1].B;
   const int NM = B1 * B2;
-  for (int idx = t; idx < NM; idx += 1024) {
-    int i1 = idx / B2, i2 = idx - i1 * B2;
-    const BaseTable &b1 = st->base[0], &b2 = st->base[1];
-    int cnt = 0;
-    if (fabsf(b1.angle[i1] - b2.angle[i2]) < A.same_thr && b1.type[i1] == b2.type[i2] && b1.type[i1] < 3)
-      cnt = hyp_generate<false>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_ang, nullptr, nullptr);
-    A.match_cnt[idx] = cnt;
-  }
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NM) return;
+  int i1 = idx / B2, i2 = idx - i1 * B2;
+  const BaseTable &b1 = st->base[0], &b2 = st->base[1];
+  int cnt = 0;
+  if (fabsf(b1.angle[i1] - b2.angle[i2]) < A.same_thr && b1.type[i1] == b2.type[i2] && b1.type[i1] < 3)
+    cnt = hyp_generate<false>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_cut, nullptr, nullptr);
+  A.match_cnt[idx] = cnt;
+}
+
+// ---- ordered scan of the counts per type: pool offsets in the reference's push_back order ----
+__global__ void __launch_bounds__(1024) match_scan_kernel(const __grid_constant__ HypArgs A) {
+  PipeState* st = A.st;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ u64 s_w64[32];
+  __shared__ u64 s_carry;
+  const int B1 = st->base[0].B, B2 = st->base[1].B;
+  const int NM = B1 * B2;
   if (t == 0) s_carry = 0;
   __syncthreads();
-  // ---- ordered scan of the counts per type ----
   for (int i0 = 0; i0 < NM; i0 += 1024) {
     int idx = i0 + t;
     u64 x = 0;
@@ -201,17 +215,19 @@ __global__ void __launch_bounds__(128) emit_hyp_kernel(const __grid_constant__ H
   const BaseTable &b1 = st->base[0], &b2 = st->base[1];
   int ty = b1.type[i1];
   size_t off = (size_t)st->hyp_off[ty] + A.match_off[idx];
-  hyp_generate<true>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_ang, A.hyp_T + off * 12, A.hyp_qt + off * 8);
+  hyp_generate<true>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_cut, A.hyp_T + off * 12, A.hyp_qt + off * 8);
 }
 
 void launch_hypotheses(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
   HypArgs A;
   A.st = w.st; A.match_cnt = h.match_cnt; A.match_off = h.match_off; A.hyp_T = h.hyp_T; A.hyp_qt = h.hyp_qt; A.cap_hyp = h.cap_hyp;
   A.tmin = w.p.included_angle_min_threshold; A.tmax = w.p.included_angle_max_threshold; A.rough = w.p.rough_threshold_gl;
-  A.same_thr = w.p.included_angle_same_threshold; A.third_thr = w.p.third_plane_threshold; A.third_ang = w.p.third_plane_normal_threshold;
-  pairs_match_kernel<<<1, 1024, 0, s>>>(A);
+  A.same_thr = w.p.included_angle_same_threshold; A.third_thr = w.p.third_plane_threshold; A.third_cut = w.cuts.third_lt;
+  base_pairs_kernel<<<1, 256, 0, s>>>(A);
+  match_count_kernel<<<(FCCF_MAXMATCH + 127) / 128, 128, 0, s>>>(A);
+  match_scan_kernel<<<1, 1024, 0, s>>>(A);
   emit_hyp_kernel<<<(FCCF_MAXMATCH + 127) / 128, 128, 0, s>>>(A);
-  if (launches) *launches += 2;
+  if (launches) *launches += 4;
 }
 
 }  // namespace fccf

@@ -476,13 +476,11 @@ void launch_score_build(cudaStream_t s, const fccf_params& p, const float* d_s1,
   if (launches) *launches += 2;
 }
 
+void score_init_attributes() {
+  cudaFuncSetAttribute(score_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_DYN_BYTES);
+  cudaFuncSetAttribute(score_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_DYN_BYTES);
+}
 static void score_launch(cudaStream_t s, ScArgs& A, int n_hyp, uint64_t* launches) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(score_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_DYN_BYTES);
-    cudaFuncSetAttribute(score_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_DYN_BYTES);
-    attr = true;
-  }
   if (n_hyp < 1) return;
   int nbw = (n_hyp + SC_WARPS - 1) / SC_WARPS; if (nbw > 148) nbw = 148;
   int ngroups = (n_hyp + SC_NH - 1) / SC_NH;

@@ -215,7 +215,7 @@ __device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
 }
 
 // quick_verify for one hypothesis by one warp.  planes: stride 8 floats (c, n, size, -).
-__device__ float quick_verify_warp(float T[16], const float* pl1, int F1, const float* pl2, int F2, float ang_thr, float dist_thr,
+__device__ float quick_verify_warp(float T[16], const float* pl1, int F1, const float* pl2, int F2, float ang_cut, float dist_thr,
                                    float required, int lane, int* npair_out, int* pairs_out, int* iters_out) {
   // integer-truncating size sums (FCCF.cpp:693,707)
   int fs1 = 0, fs2 = 0;
@@ -228,13 +228,15 @@ __device__ float quick_verify_warp(float T[16], const float* pl1, int F1, const 
     float size1 = pl1[lane * 8 + 6];
     double d1d = sum3d((double)n1.x * (double)p1.x, (double)n1.y * (double)p1.y, (double)n1.z * (double)p1.z);
     float d1 = (float)d1d;
+    const double nn1 = normal_norm(n1.x, n1.y, n1.z);
     for (int b = 0; b < F2; b++) {
       f3 p2 = tf_se3(T, mk3(pl2[b * 8], pl2[b * 8 + 1], pl2[b * 8 + 2]));
       f3 n2 = tf_so3(T, mk3(pl2[b * 8 + 3], pl2[b * 8 + 4], pl2[b * 8 + 5]));
-      float angel = normal_angle(n1.x, n1.y, n1.z, n2.x, n2.y, n2.z);
+      // compute_normal_angel(...) < quick_verify_angel_threshold (FCCF.cpp:722-730) through its cosine cut
+      bool ang_ok = angle_lt(normal_cos_n(n1.x, n1.y, n1.z, nn1, n2.x, n2.y, n2.z, normal_norm(n2.x, n2.y, n2.z)), ang_cut);
       float d2 = (float)sum3d((double)n2.x * (double)p2.x, (double)n2.y * (double)p2.y, (double)n2.z * (double)p2.z);
       float dist = (float)fabs((double)(d1 - d2));
-      if (angel < ang_thr && dist < dist_thr) {
+      if (ang_ok && dist < dist_thr) {
         find = true;
         float size2 = pl2[b * 8 + 6];
         float mn = size1 < size2 ? size1 : size2, mx = size1 > size2 ? size1 : size2;
@@ -292,7 +294,7 @@ struct QvArgs {
   PipeState* st;
   const float* centre; float* qv_T; float* qv_score; int* qv_npair; int* qv_pairs; int* qv_iters;
   int* rank_perm; float* top_T; float* top_s1; int* top_centre;
-  float ang_thr, dist_thr, required, fine_number;
+  float ang_cut, dist_thr, required, fine_number;   // ang_cut: cosine cut of quick_verify_angel_threshold (strict <)
 };
 
 __global__ void __launch_bounds__(128) quick_verify_kernel(const __grid_constant__ QvArgs A) {
@@ -305,54 +307,59 @@ __global__ void __launch_bounds__(128) quick_verify_kernel(const __grid_constant
   q4 q; q.w = c[0]; q.x = c[1]; q.y = c[2]; q.z = c[3];
   m3 Rm = quat_to_matrix(q);   // FCCF.cpp:1470-1489
   float T[16] = {Rm.m[0][0], Rm.m[0][1], Rm.m[0][2], c[4], Rm.m[1][0], Rm.m[1][1], Rm.m[1][2], c[5], Rm.m[2][0], Rm.m[2][1], Rm.m[2][2], c[6], 0.f, 0.f, 0.f, 1.f};
-  float s = quick_verify_warp(T, &st->ft[0].plane[0][0], st->ft[0].F, &st->ft[1].plane[0][0], st->ft[1].F, A.ang_thr, A.dist_thr, A.required, lane,
+  float s = quick_verify_warp(T, &st->ft[0].plane[0][0], st->ft[0].F, &st->ft[1].plane[0][0], st->ft[1].F, A.ang_cut, A.dist_thr, A.required, lane,
                               A.qv_npair + wid, A.qv_pairs + (size_t)wid * 32, A.qv_iters + wid);
   if (lane < 16) A.qv_T[(size_t)wid * 16 + lane] = T[lane];
   if (lane == 0) A.qv_score[wid] = s;
 }
 
-// score_range + top-k (FCCF.cpp:1494-1544): one warp per type
-__global__ void __launch_bounds__(96) rank_top_kernel(const __grid_constant__ QvArgs A) {
+// score_range + top-k (FCCF.cpp:1494-1544): one CTA per type
+__global__ void __launch_bounds__(256) rank_top_kernel(const __grid_constant__ QvArgs A) {
   PipeState* st = A.st;
-  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  __shared__ float s_key[3][FCCF_MAXCENTRE];
-  __shared__ int s_perm[3][FCCF_MAXCENTRE];
+  const int t = threadIdx.x, lane = t & 31, ty = blockIdx.x;
+  __shared__ float s_key[FCCF_MAXCENTRE];
+  __shared__ int s_perm[FCCF_MAXCENTRE];
+  __shared__ unsigned long long s_sort[40];
   const int C = st->n_centre[ty];
-  for (int k = lane; k < C; k += 32) { s_key[ty][k] = A.qv_score[ty * FCCF_MAXCENTRE + k]; s_perm[ty][k] = k; }
-  __syncwarp();
-  warp_exchange_sort(s_key[ty], s_perm[ty], C, [](float a, float b) { return a < b; });
-  __syncwarp();
+  int has_nan = 0;
+  for (int k = t; k < C; k += 256) { float v = A.qv_score[ty * FCCF_MAXCENTRE + k]; s_key[k] = v; s_perm[k] = k; has_nan |= (v != v); }
+  has_nan = __syncthreads_or(has_nan);
+  if (!has_nan) block_exchange_sort(s_key, s_perm, C, s_sort);
+  else if (t < 32) warp_exchange_sort(s_key, s_perm, C, [](float a, float b) { return a < b; });   // NaN keys have no total order: literal emulation
+  __syncthreads();
   int amax = (int)A.fine_number;
   if (amax > FCCF_TOPK) amax = FCCF_TOPK;
   int nt = C < amax ? C : amax;
-  for (int k = lane; k < C; k += 32) A.rank_perm[ty * FCCF_MAXCENTRE + k] = s_perm[ty][k];
-  for (int k = 0; k < nt; k++) {
-    int ci = s_perm[ty][k];
-    if (lane < 16) A.top_T[((size_t)ty * FCCF_TOPK + k) * 16 + lane] = A.qv_T[((size_t)ty * FCCF_MAXCENTRE + ci) * 16 + lane];
-    if (lane == 0) { A.top_s1[ty * FCCF_TOPK + k] = s_key[ty][k]; A.top_centre[ty * FCCF_TOPK + k] = ci; }
+  for (int k = t; k < C; k += 256) A.rank_perm[ty * FCCF_MAXCENTRE + k] = s_perm[k];
+  if (t < 32) {
+    for (int k = 0; k < nt; k++) {
+      int ci = s_perm[k];
+      if (lane < 16) A.top_T[((size_t)ty * FCCF_TOPK + k) * 16 + lane] = A.qv_T[((size_t)ty * FCCF_MAXCENTRE + ci) * 16 + lane];
+      if (lane == 0) { A.top_s1[ty * FCCF_TOPK + k] = s_key[k]; A.top_centre[ty * FCCF_TOPK + k] = ci; }
+    }
+    if (lane == 0) st->n_top[ty] = nt;
   }
-  if (lane == 0) st->n_top[ty] = nt;
 }
 
 void launch_quick_verify(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
   QvArgs A;
   A.st = w.st; A.centre = h.centre; A.qv_T = h.qv_T; A.qv_score = h.qv_score; A.qv_npair = h.qv_npair; A.qv_pairs = h.qv_pairs; A.qv_iters = h.qv_iters;
   A.rank_perm = h.rank_perm; A.top_T = h.top_T; A.top_s1 = h.top_s1; A.top_centre = h.top_centre;
-  A.ang_thr = w.p.quick_verify_angel_threshold; A.dist_thr = w.p.quick_verify_distance_threshold; A.required = w.p.required_optimize_plane; A.fine_number = w.p.fine_verify_number;
+  A.ang_cut = w.cuts.qv_lt; A.dist_thr = w.p.quick_verify_distance_threshold; A.required = w.p.required_optimize_plane; A.fine_number = w.p.fine_verify_number;
   quick_verify_kernel<<<(3 * FCCF_MAXCENTRE + 3) / 4, 128, 0, s>>>(A);
-  rank_top_kernel<<<1, 96, 0, s>>>(A);
+  rank_top_kernel<<<3, 256, 0, s>>>(A);
   if (launches) *launches += 2;
 }
 
 // stand-alone: n hypotheses (row-major 4x4, updated in place) against two plane tables (F x 8)
-struct QvListArgs { float* T; int n; const float* pl1; int f1; const float* pl2; int f2; float* score; int* npair; int* pairs; int* iters; float ang_thr, dist_thr, required; };
+struct QvListArgs { float* T; int n; const float* pl1; int f1; const float* pl2; int f2; float* score; int* npair; int* pairs; int* iters; float ang_cut, dist_thr, required; };
 __global__ void __launch_bounds__(128) quick_verify_list_kernel(const __grid_constant__ QvListArgs A) {
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (wid >= A.n) return;
   float T[16];
   for (int i = 0; i < 16; i++) T[i] = A.T[(size_t)wid * 16 + i];
-  float s = quick_verify_warp(T, A.pl1, A.f1, A.pl2, A.f2, A.ang_thr, A.dist_thr, A.required, lane, A.npair ? A.npair + wid : nullptr,
+  float s = quick_verify_warp(T, A.pl1, A.f1, A.pl2, A.f2, A.ang_cut, A.dist_thr, A.required, lane, A.npair ? A.npair + wid : nullptr,
                               A.pairs ? A.pairs + (size_t)wid * 32 : nullptr, A.iters ? A.iters + wid : nullptr);
   if (lane < 16) A.T[(size_t)wid * 16 + lane] = T[lane];
   if (lane == 0) A.score[wid] = s;
@@ -361,7 +368,7 @@ void launch_quick_verify_list(cudaStream_t s, const fccf_params& p, float* d_T16
                               const float* d_planes2, int f2, float* d_score, int* d_npair, int* d_pairs, int* d_iters, uint64_t* launches) {
   QvListArgs A;
   A.T = d_T16; A.n = n; A.pl1 = d_planes1; A.f1 = f1; A.pl2 = d_planes2; A.f2 = f2; A.score = d_score; A.npair = d_npair; A.pairs = d_pairs; A.iters = d_iters;
-  A.ang_thr = p.quick_verify_angel_threshold; A.dist_thr = p.quick_verify_distance_threshold; A.required = p.required_optimize_plane;
+  A.ang_cut = angle_cut(p.quick_verify_angel_threshold, true); A.dist_thr = p.quick_verify_distance_threshold; A.required = p.required_optimize_plane;
   if (n <= 0) return;
   quick_verify_list_kernel<<<(n + 3) / 4, 128, 0, s>>>(A);
   if (launches) *launches += 1;

@@ -14,19 +14,19 @@
 namespace fccf {
 
 struct VGArgs {
-  const float* in[2];        // packed xyz
+  const CallArgs* call;      // leaf; raw clouds when in[c] == nullptr (stage 0)
+  const float* in[2];        // packed xyz (nullptr: call->raw[c])
   const int* n_in[2];        // device-side input count
   VGState* st[2];
   u64* keys[2];
   int* ticket[2];
-  float leaf;
   int emulate;
 };
 
 __global__ void __launch_bounds__(256) vg_minmax_kernel(const __grid_constant__ VGArgs A) {
   const int c = blockIdx.y;
   const int n = *A.n_in[c];
-  const float* p = A.in[c];
+  const float* p = A.in[c] ? A.in[c] : A.call->raw[c];
   int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
   int nf = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) vg_minmax_kernel(const __grid_constant__ 
   *A.ticket[c] = 0;
   st->n_in = n;
   int nfin = atomicAdd(&st->n_finite, 0);
-  float inv = 1.0f / A.leaf;
+  float inv = 1.0f / A.call->leaf;
   st->inv = inv;
   if (nfin == 0) { st->bail = 0; st->total = 0; st->nbits = 1; st->n_finite = 0; return; }
   float fmn[3], fmx[3];
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) vg_keys_kernel(const __grid_constant__ VG
   const int n = st->n_in;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float* p = A.in[c];
+  const float* p = A.in[c] ? A.in[c] : A.call->raw[c];
   float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
   u64 key;
   if (!(isfinite(x) && isfinite(y) && isfinite(z))) key = (u64)st->total;
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) vg_keys_kernel(const __grid_constant__ VG
 }
 
 struct VGOut {
+  const CallArgs* call;
   const float* in[2];
   const u64* keys[2];
   const u32* idx[2];
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(128) vg_centroid_kernel(const __grid_constant_
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
   const int b = A.seg_start[c][s], e = A.seg_start[c][s + 1];
-  const float* p = A.in[c];
+  const float* p = A.in[c] ? A.in[c] : A.call->raw[c];
   const u32* idx = A.idx[c];
   float sx = 0.f, sy = 0.f, sz = 0.f;
   for (int k = b; k < e; k++) {
@@ -141,9 +142,10 @@ __global__ void __launch_bounds__(128) vg_centroid_kernel(const __grid_constant_
   A.cnt[c][s] = e - b;
 }
 
-__global__ void init_state_kernel(PipeState* st, int n0, int n1) {
+__global__ void init_state_kernel(PipeState* st) {
   int t = threadIdx.x;
   if (t == 0) {
+    const int n0 = st->call.n0, n1 = st->call.n1;
     for (int s = 0; s < 2; s++) for (int c = 0; c < 2; c++) {
       VGState& v = st->vg[s][c];
       v.n_in = 0; v.n_finite = 0; v.n_out = 0; v.bail = 0; v.total = 0; v.nbits = 1;
@@ -157,8 +159,8 @@ __global__ void init_state_kernel(PipeState* st, int n0, int n1) {
   if (t < 64) st->tickets[t] = 0;
 }
 
-void launch_init_state(cudaStream_t s, PipeState* st, int n0, int n1, uint64_t* launches) {
-  init_state_kernel<<<1, 64, 0, s>>>(st, n0, n1);
+void launch_init_state(cudaStream_t s, PipeState* st, uint64_t* launches) {
+  init_state_kernel<<<1, 64, 0, s>>>(st);
   if (launches) *launches += 1;
 }
 
@@ -169,7 +171,7 @@ void launch_voxelgrid(cudaStream_t s, const Work& w, int stage, int ncloud, uint
   for (int c = 0; c < ncloud; c++) {
     const CloudWS& cw = w.c[c];
     PipeState* st = w.st;
-    A.in[c] = (stage == 0) ? cw.raw : cw.vg_xyz[0];
+    A.in[c] = (stage == 0) ? nullptr : cw.vg_xyz[0];
     A.n_in[c] = (stage == 0) ? &st->vg[0][c].n_in : &st->vg[0][c].n_out;
     A.st[c] = &st->vg[stage][c];
     A.keys[c] = cw.keyA;
@@ -186,7 +188,7 @@ void launch_voxelgrid(cudaStream_t s, const Work& w, int stage, int ncloud, uint
     if (cw.cap > cap) cap = cw.cap;
   }
   for (int c = ncloud; c < 2; c++) { A.in[c] = A.in[0]; A.n_in[c] = A.n_in[0]; A.st[c] = A.st[0]; A.keys[c] = A.keys[0]; A.ticket[c] = A.ticket[0]; }
-  A.leaf = w.leaf; A.emulate = w.p.emulate_pcl_overflow;
+  A.call = &w.st->call; O.call = &w.st->call; A.emulate = w.p.emulate_pcl_overflow;
   int nb_mm = (cap + 256 * 8 - 1) / (256 * 8);
   if (nb_mm > 592) nb_mm = 592;
   if (nb_mm < 1) nb_mm = 1;
