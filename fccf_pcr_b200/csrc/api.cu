@@ -782,6 +782,7 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
     if (stem == "fv_counts") put(all.data(), all.size() * 4, FCCF_I32); else put(off.data(), off.size() * 4, FCCF_I32);
   }
   else if (name == "type_best") put(st.type_best, sizeof st.type_best, FCCF_F32);
+  else if (name == "prof") put(st.prof, sizeof st.prof, FCCF_I64);
   else if (name == "final_T") put(st.T_final, 64, FCCF_F32);
   else ok = false;
   if (!ok) { ctx->err = "unknown blob: " + name; return FCCF_ERR_ARG; }

@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
   const double rr = rad * 1.0001 + 1e-6;
   for (int i = t; i < n; i += 1024) state[i] = (i == n - 1) ? 2 : 0;
   __syncthreads();
+#define CL_MARK(k) if (ty == 0 && t == 0) st->prof[k] = clock64();
+  CL_MARK(0)
+  int rounds = 0;
   // ---- greedy seeding as parallel rounds ----
   while (true) {
     if (t == 0) s_flag = 0;
@@ -166,9 +169,12 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
       else s_flag = 1;
     }
     __syncthreads();
+    rounds++;
     if (!s_flag) break;
     __syncthreads();
   }
+  CL_MARK(1)
+  if (ty == 0 && t == 0) st->prof[8] = rounds;
   // ---- seeds in index order + cluster sizes ----
   if (t == 0) s_K = 0;
   __syncthreads();
@@ -201,9 +207,11 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
     size[k] = cnt; key[k] = cnt; perm[k] = k;
   }
   __syncthreads();
+  CL_MARK(2)
   // ---- range_cluster: exchange sort by size ----
   block_exchange_sort(key, perm, K, s_sort);
   __syncthreads();
+  CL_MARK(3)
   // ---- adaptive cut-off walk (FCCF.cpp:1123-1229) ----
   if (t == 0) {
     int clusternum = key[0];
@@ -223,6 +231,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
   }
   __syncthreads();
   const int E = s_E;
+  CL_MARK(4)
   // ---- centres: small clusters by one warp each ----
   for (int e = warp; e < E; e += 32) {
     int k = s_emit[e]; int i = seeds[k]; int m = size[k];
@@ -256,6 +265,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
     __syncwarp();
   }
   __syncthreads();
+  CL_MARK(5)
   // ---- big clusters: whole block gathers into global scratch, rank sort, warp 0 averages ----
   int* gmem = A.members + base; float* gmd = A.mdist + base;
   int* gsorted = A.members + A.cap_hyp + base;   // second half of the member scratch
@@ -289,6 +299,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
     if (warp == 0) cl_emit_centre(qt, gsorted, m, centre + (size_t)e * 8, lane);
     __syncthreads();
   }
+  CL_MARK(6)
 }
 
 void launch_cluster(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {

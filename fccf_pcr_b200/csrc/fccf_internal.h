@@ -84,6 +84,7 @@ struct PipeState {
   ScoreState fv;
   float type_best[3][13];    // per type: best score + 3x4
   float T_final[16];
+  long long prof[32];        // clock64() marks of the single-CTA kernels (debug blob "prof")
 };
 
 struct SortJob {

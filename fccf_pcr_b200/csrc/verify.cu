@@ -25,25 +25,29 @@ __device__ __forceinline__ void crossd(const double a[3], const double b[3], dou
 __device__ __forceinline__ double dot3d(const double a[3], const double b[3]) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
 
 // f(q,a) = a + w*uv + u x uv, uv = 2 (u x a); Jacobian wrt (x,y,z,w)
-__device__ void rot_with_jac(const double q[4], const double a[3], double f[3], double J[3][4], bool want) {
+__device__ __forceinline__ void rot_with_jac(const double q[4], const double a[3], double f[3], double J[3][4], bool want) {
   const double* u = q; double w = q[3];
   double uv[3]; crossd(u, a, uv); uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
   double c2[3]; crossd(u, uv, c2);
+  #pragma unroll
   for (int i = 0; i < 3; i++) f[i] = (a[i] + w * uv[i]) + c2[i];
   if (!want) return;
+  #pragma unroll
   for (int k = 0; k < 3; k++) {
     double e[3] = {0, 0, 0}; e[k] = 1.0;
     double Av[3]; crossd(e, a, Av); Av[0] *= 2; Av[1] *= 2; Av[2] *= 2;
     double t1[3], t2[3]; crossd(e, uv, t1); crossd(u, Av, t2);
+    #pragma unroll
     for (int i = 0; i < 3; i++) J[i][k] = w * Av[i] + t1[i] + t2[i];
   }
+  #pragma unroll
   for (int i = 0; i < 3; i++) J[i][3] = uv[i];
 }
 
 struct LmRow { double n1[3], p1[3], n2[3], p2[3], w; bool active; int odd; };
 
 // residual of this lane's row and (optionally) its 6 local Jacobian entries; warp-uniform return
-__device__ bool lm_eval(const LmRow& R, const double x[7], double& r, double J[6], bool want) {
+__device__ __forceinline__ bool lm_eval(const LmRow& R, const double x[7], double& r, double J[6], bool want) {
   bool fin = true;
   r = 0.0;
   if (want) for (int c = 0; c < 6; c++) J[c] = 0.0;
@@ -52,6 +56,7 @@ __device__ bool lm_eval(const LmRow& R, const double x[7], double& r, double J[6
     double n2r[3], p2r[3], Jn[3][4], Jp[3][4];
     rot_with_jac(q, R.n2, n2r, Jn, want);
     rot_with_jac(q, R.p2, p2r, Jp, want);
+    #pragma unroll
     for (int i = 0; i < 3; i++) p2r[i] += t[i];
     double cv[3]; crossd(R.n1, n2r, cv);
     double nc = sqrt(dot3d(cv, cv));
@@ -61,22 +66,27 @@ __device__ bool lm_eval(const LmRow& R, const double x[7], double& r, double J[6
     fin = isfinite(r);
     if (want) {
       double Ja[7];
+      #pragma unroll
       for (int col = 0; col < 4; col++) {
         double dn[3] = {Jn[0][col], Jn[1][col], Jn[2][col]}, dp[3] = {Jp[0][col], Jp[1][col], Jp[2][col]};
         if (!R.odd) { double dc[3]; crossd(R.n1, dn, dc); Ja[col] = R.w * (dot3d(cv, dc) / nc); }
         else { double dd = -(dot3d(dn, p2r) + dot3d(n2r, dp)); Ja[col] = R.w * (d * dd / sd); }
       }
+      #pragma unroll
       for (int col = 0; col < 3; col++) Ja[4 + col] = R.odd ? R.w * (d * (-n2r[col]) / sd) : 0.0;
       // EigenQuaternionParameterization::ComputeJacobian (4x3)
       double Pm[4][3] = {{q[3], q[2], -q[1]}, {-q[2], q[3], q[0]}, {q[1], -q[0], q[3]}, {-q[0], -q[1], -q[2]}};
+      #pragma unroll
       for (int lc = 0; lc < 3; lc++) { double s = 0; for (int a = 0; a < 4; a++) s += Ja[a] * Pm[a][lc]; J[lc] = s; }
+      #pragma unroll
       for (int lc = 0; lc < 3; lc++) J[3 + lc] = Ja[4 + lc];
+      #pragma unroll
       for (int lc = 0; lc < 6; lc++) fin = fin && isfinite(J[lc]);
     }
   }
   return __all_sync(0xffffffffu, fin);
 }
-__device__ void lm_plus(const double x[7], const double delta[6], double out[7]) {
+__device__ __forceinline__ void lm_plus(const double x[7], const double delta[6], double out[7]) {
   double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
   if (nd > 0.0) {
     double s = sin(nd) / nd;
@@ -87,13 +97,15 @@ __device__ void lm_plus(const double x[7], const double delta[6], double out[7])
     out[1] = dq[3] * b[1] + dq[1] * b[3] + dq[2] * b[0] - dq[0] * b[2];
     out[2] = dq[3] * b[2] + dq[2] * b[3] + dq[0] * b[1] - dq[1] * b[0];
   } else { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3]; }
+  #pragma unroll
   for (int i = 0; i < 3; i++) out[4 + i] = x[4 + i] + delta[3 + i];
 }
 // min || [A; B] y - [b; 0] || by Householder QR.  Lane l holds main row l (A, b) and, for l < 6,
 // augmented row l (B = diag(lmd)).  Returns false on a zero column / non-finite solution.
-__device__ bool lm_qr_solve(double A[6], double b, double B[6], int lane, double y[6]) {
+__device__ __forceinline__ bool lm_qr_solve(double A[6], double b, double B[6], int lane, double y[6]) {
   double bb = 0.0;   // rhs of the augmented row
   const bool aug = lane < 6;
+  #pragma unroll
   for (int k = 0; k < 6; k++) {
     double mk = (lane >= k) ? A[k] : 0.0;
     double ak = aug ? B[k] : 0.0;
@@ -107,6 +119,7 @@ __device__ bool lm_qr_solve(double A[6], double b, double B[6], int lane, double
     double vtv = bfly(vm * vm + va * va);
     if (vtv == 0.0) return false;
     double beta = 2.0 / vtv;
+    #pragma unroll
     for (int j = k + 1; j < 6; j++) {
       double s = bfly(vm * A[j] + va * (aug ? B[j] : 0.0));
       s *= beta;
@@ -122,8 +135,10 @@ __device__ bool lm_qr_solve(double A[6], double b, double B[6], int lane, double
     if (lane == k) A[k] = alpha;
   }
   bool ok = true;
+  #pragma unroll
   for (int k = 5; k >= 0; k--) {
     double s = b;
+    #pragma unroll
     for (int j = k + 1; j < 6; j++) s -= A[j] * y[j];
     s = s / A[k];
     y[k] = __shfl_sync(0xffffffffu, s, k);
@@ -144,8 +159,11 @@ __device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
   int iter = 0;
   if (!lm_eval(R, x, r, J, true)) return 0;
   double cost = 0.5 * bfly(r * r);
+  #pragma unroll
   for (int c = 0; c < 6; c++) g[c] = bfly(J[c] * r);
+  #pragma unroll
   for (int c = 0; c < 6; c++) scale[c] = 1.0 / (1.0 + sqrt(bfly(J[c] * J[c])));
+  #pragma unroll
   for (int c = 0; c < 6; c++) J[c] *= scale[c];
   double gmax;
   {
@@ -163,11 +181,13 @@ __device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
     step_successful = false;
     if (!reuse_diag) for (int c = 0; c < 6; c++) diag[c] = fmin(fmax(bfly(J[c] * J[c]), min_diag), max_diag);
     double Aq[6], Bq[6], step[6];
+    #pragma unroll
     for (int c = 0; c < 6; c++) { Aq[c] = J[c]; Bq[c] = (lane == c) ? sqrt(diag[c] / radius) : 0.0; }
     bool solved = lm_qr_solve(Aq, r, Bq, lane, step);
     reuse_diag = true;
     bool valid = false; double model_change = 0;
     if (solved) {
+      #pragma unroll
       for (int c = 0; c < 6; c++) step[c] = -step[c];
       double mr = 0; for (int c = 0; c < 6; c++) mr += J[c] * step[c];
       model_change = -bfly(mr * (r + mr / 2.0));
@@ -192,11 +212,14 @@ __device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
     if (fabs(cost_change) <= function_tolerance * cost) break;
     double rel = cost_change / model_change;
     if (rel > min_relative_decrease) {
+      #pragma unroll
       for (int i = 0; i < 7; i++) x[i] = xc[i];
       x_norm = 0; for (int i = 0; i < 7; i++) x_norm += x[i] * x[i]; x_norm = sqrt(x_norm);
       cost = cand_cost;
       if (!lm_eval(R, x, r, J, true)) break;
+      #pragma unroll
       for (int c = 0; c < 6; c++) g[c] = bfly(J[c] * r);
+      #pragma unroll
       for (int c = 0; c < 6; c++) J[c] *= scale[c];
       {
         double ng[6], xp[7]; for (int c = 0; c < 6; c++) ng[c] = -g[c];
