@@ -364,7 +364,7 @@ def run_reference(args):
            "cpu_baseline": {"value": round(ms, 4), "unit": "ms/registration", "cores": procs, "kind": "port",
                             "sample": "%d steps x %d registrations (one single-threaded oracle process per host core); mean single registration %.2f ms" % (K, procs, 1e3 * float(np.mean(per)))},
            "e2e": {"value": round(ms, 4), "unit": "ms/registration", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def emit(obj):
