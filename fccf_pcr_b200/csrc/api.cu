@@ -33,52 +33,65 @@ struct Arena {
   }
 };
 
-// One registration in flight: its own stream, workspaces and result block.  A context owns lane 0
-// (the single-pair entry points and the stage entry points) and creates further lanes on demand for
-// fccf_register_batch*, which keeps several independent pairs in flight at once: most kernels of one
-// registration are single-CTA (order-dependent greedy stages), so concurrent lanes fill the other SMs.
+// One registration in flight: its workspaces and its slot in the group's state arrays.
 struct Lane {
-  cudaStream_t stream = nullptr;
   int cap_pts = 0;
   Arena cloud_arena[2];
   float* d_raw[2] = {nullptr, nullptr};
   CloudWS c[2];
-  PipeState* d_st = nullptr;
-  PipeState* h_st = nullptr;     // pinned
+  PipeState* d_st = nullptr;     // slot of Group::d_st_all
+  PipeState* h_st = nullptr;     // slot of Group::h_st_all (pinned)
   Arena hyp_arena;
   HypWS h;
+  int pair = -1;
+};
+
+struct GraphRec { int G = 0; cudaGraphExec_t exec = nullptr; int launches = 0; };
+
+// A group = the lanes that run as ONE batched launch sequence on one stream: every kernel of the
+// pipeline is launched once with grid.z = G and serves G independent registrations (most stages of one
+// registration are single-CTA, order-dependent greedy loops, so G of them fill the other SMs), and the
+// whole sequence is one CUDA graph per G.  A context owns group 0 (single-pair and stage entry points
+// use its lane 0) and a second group for fccf_register_batch*, which double-buffers: while one group
+// computes, the other receives its clouds.
+struct Group {
+  cudaStream_t stream = nullptr;
+  std::vector<Lane> lanes;
+  PipeState* d_st_all = nullptr; PipeState* h_st_all = nullptr;
+  CallArgs* d_calls = nullptr; CallArgs* h_calls = nullptr;
+  ArgTable tab;
+  std::vector<GraphRec> graphs;
+  uint64_t params_epoch = 0;
   cudaEvent_t ev[6];
   cudaEvent_t sev[8];
+  bool busy = false, had_h2d = false;
+  int G = 0;                     // lanes of the sequence in flight
   size_t last_h2d = 0;
   uint64_t launches = 0, l0 = 0;
-  bool busy = false; int pair = -1; bool had_h2d = false;
-  CallArgs* h_call = nullptr;    // pinned
-  cudaGraphExec_t gexec = nullptr;   // the whole pipeline of this lane, captured once per workspace / parameter set
-  int graph_launches = 0;        // kernel nodes in the graph
-  uint64_t params_epoch = 0;
 };
 
 struct fccf_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;   // = lanes[0]->stream
+  cudaStream_t stream = nullptr;   // = groups[0]->stream
   fccf_params p;
   std::string err;
-  uint64_t launches = 0;           // kernels launched outside the lanes (stand-alone stage entry points)
-  std::vector<Lane*> lanes;
-  int max_lanes = 8;
+  uint64_t launches = 0;           // kernels launched outside the groups (stand-alone stage entry points)
+  std::vector<Group*> groups;
+  int max_lanes = 64;
   bool use_graph = true;
   uint64_t params_epoch = 1;
   int cap_hyp = 1 << 18;
   bool have_run = false;
   float leaf = 0.f;
+  ArgTable itab;                   // immediate-mode argument table of the stand-alone stage entry points
   // stand-alone scoring
   float *d_sc_s1 = nullptr, *d_sc_s2 = nullptr, *d_sc_T = nullptr, *d_sc_scores = nullptr;
   size_t sc_cap1 = 0, sc_cap2 = 0, sc_capT = 0;
   Arena sc_arena; ScoreWS sc_ws; int sc_cap_hash = 0; ScoreState* d_sc_ss = nullptr; int* d_sc_n = nullptr;
   size_t sc_n2 = 0, sc_nhyp = 0;
   long long* d_sc_best = nullptr;
-  // lane-0 aliases used by the stage entry points and the blob reader
-  Lane& L0() { return *lanes[0]; }
+  Group& G0() { return *groups[0]; }
+  Lane& L0() { return groups[0]->lanes[0]; }
 };
 
 static size_t cloud_bytes(int cap) {
@@ -106,40 +119,70 @@ static void cloud_carve(Arena& a, CloudWS& w, int cap) {
   w.fstat = a.take<float>(16 * c); w.face_vox = a.take<int>(c); w.face_off = a.take<int>(64);
 }
 
-static int lane_create(fccf_ctx* ctx, Lane** out) {
-  Lane* L = new Lane();
-  if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) { delete L; ctx->err = "cudaStreamCreate failed"; return FCCF_ERR_CUDA; }
-  if (cudaMalloc(&L->d_st, sizeof(PipeState)) != cudaSuccess || cudaMallocHost(&L->h_st, sizeof(PipeState)) != cudaSuccess ||
-      cudaMallocHost(&L->h_call, sizeof(CallArgs)) != cudaSuccess) { delete L; ctx->err = "state allocation failed"; return FCCF_ERR_CUDA; }
-  cudaMemset(L->d_st, 0, sizeof(PipeState));
-  for (int i = 0; i < 6; i++) cudaEventCreate(&L->ev[i]);
-  for (int i = 0; i < 8; i++) cudaEventCreate(&L->sev[i]);
-  *out = L;
+static int table_create(fccf_ctx* ctx, ArgTable& t, size_t bytes, cudaStream_t s) {
+  t.cap = bytes; t.off = 0; t.stream = s;
+  if (cudaMalloc(&t.d, bytes) != cudaSuccess || cudaMallocHost(&t.h, bytes) != cudaSuccess) { ctx->err = "argument table allocation failed"; return FCCF_ERR_CUDA; }
   return FCCF_OK;
 }
-static void lane_destroy(Lane* L) {
-  if (!L) return;
-  if (L->stream) cudaStreamSynchronize(L->stream);
-  for (int c = 0; c < 2; c++) { if (L->cloud_arena[c].base) cudaFree(L->cloud_arena[c].base); if (L->d_raw[c]) cudaFree(L->d_raw[c]); }
-  if (L->hyp_arena.base) cudaFree(L->hyp_arena.base);
-  if (L->d_st) cudaFree(L->d_st);
-  if (L->h_st) cudaFreeHost(L->h_st);
-  if (L->h_call) cudaFreeHost(L->h_call);
-  if (L->gexec) cudaGraphExecDestroy(L->gexec);
-  for (int i = 0; i < 6; i++) cudaEventDestroy(L->ev[i]);
-  for (int i = 0; i < 8; i++) cudaEventDestroy(L->sev[i]);
-  if (L->stream) cudaStreamDestroy(L->stream);
-  delete L;
+static void table_destroy(ArgTable& t) {
+  if (t.d) cudaFree(t.d);
+  if (t.h) cudaFreeHost(t.h);
+  t.d = t.h = nullptr;
 }
 
-static int ensure_capacity(fccf_ctx* ctx, Lane* L, size_t n0, size_t n1) {
+static void group_drop_graphs(Group* g) {
+  for (GraphRec& r : g->graphs) if (r.exec) cudaGraphExecDestroy(r.exec);
+  g->graphs.clear();
+  g->tab.off = 0; g->tab.overflow = false;
+}
+
+static int group_create(fccf_ctx* ctx, Group** out) {
+  Group* g = new Group();
+  const int nl = ctx->max_lanes;
+  bool ok = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc(&g->d_st_all, sizeof(PipeState) * nl) == cudaSuccess && cudaMallocHost(&g->h_st_all, sizeof(PipeState) * nl) == cudaSuccess;
+  ok = ok && cudaMalloc(&g->d_calls, sizeof(CallArgs) * nl) == cudaSuccess && cudaMallocHost(&g->h_calls, sizeof(CallArgs) * nl) == cudaSuccess;
+  if (!ok) { delete g; ctx->err = "state allocation failed"; cudaGetLastError(); return FCCF_ERR_CUDA; }
+  cudaMemset(g->d_st_all, 0, sizeof(PipeState) * nl);
+  memset(g->h_st_all, 0, sizeof(PipeState) * nl);
+  // one capture of G lanes takes about 10 KB of argument blocks per lane (+ alignment)
+  if (table_create(ctx, g->tab, (size_t)nl * 3 * 12288 + (1 << 20), g->stream) != FCCF_OK) { delete g; return FCCF_ERR_CUDA; }
+  g->lanes.resize(nl);
+  for (int l = 0; l < nl; l++) { g->lanes[l].d_st = g->d_st_all + l; g->lanes[l].h_st = g->h_st_all + l; }
+  for (int i = 0; i < 6; i++) cudaEventCreate(&g->ev[i]);
+  for (int i = 0; i < 8; i++) cudaEventCreate(&g->sev[i]);
+  *out = g;
+  return FCCF_OK;
+}
+static void group_destroy(Group* g) {
+  if (!g) return;
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  group_drop_graphs(g);
+  for (Lane& L : g->lanes) {
+    for (int c = 0; c < 2; c++) { if (L.cloud_arena[c].base) cudaFree(L.cloud_arena[c].base); if (L.d_raw[c]) cudaFree(L.d_raw[c]); }
+    if (L.hyp_arena.base) cudaFree(L.hyp_arena.base);
+  }
+  if (g->d_st_all) cudaFree(g->d_st_all);
+  if (g->h_st_all) cudaFreeHost(g->h_st_all);
+  if (g->d_calls) cudaFree(g->d_calls);
+  if (g->h_calls) cudaFreeHost(g->h_calls);
+  table_destroy(g->tab);
+  for (int i = 0; i < 6; i++) cudaEventDestroy(g->ev[i]);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(g->sev[i]);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+
+// workspaces of lane `li` of group `g` for clouds of up to max(n0, n1) points
+static int ensure_capacity(fccf_ctx* ctx, Group* g, int li, size_t n0, size_t n1) {
+  Lane* L = &g->lanes[li];
   size_t need = std::max(n0, n1);
   if (need < 1024) need = 1024;
   if ((size_t)L->cap_pts >= need) return FCCF_OK;
   if (need > (size_t)1 << 30) { ctx->err = "cloud too large"; return FCCF_ERR_ARG; }
   int cap = (int)((need + 4095) & ~(size_t)4095);
-  CK(cudaStreamSynchronize(L->stream));
-  if (L->gexec) { cudaGraphExecDestroy(L->gexec); L->gexec = nullptr; }
+  CK(cudaStreamSynchronize(g->stream));
+  group_drop_graphs(g);            // captured graphs hold the old pointers
   for (int c = 0; c < 2; c++) {
     if (L->cloud_arena[c].base) CK(cudaFree(L->cloud_arena[c].base));
     if (L->d_raw[c]) CK(cudaFree(L->d_raw[c]));
@@ -203,30 +246,28 @@ void fccf_default_params(fccf_params* p) {
 }
 
 fccf_ctx* fccf_create(int device, const fccf_params* params) {
-  // Concurrent lanes need one hardware work queue each; the driver's default is 8 per device, which
-  // serialises lanes that share a queue (measured: 16 lanes 1.40 -> 0.63 ms/registration with 32).
-  // Only effective if the CUDA context of this process has not been created yet; never overrides.
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return nullptr;
   if (cudaSetDevice(device) != cudaSuccess) return nullptr;
   fccf_ctx* ctx = new fccf_ctx();
   ctx->device = device;
   if (params) ctx->p = *params; else fccf_default_params(&ctx->p);
-  if (ctx->p.batch_lanes > 0) ctx->max_lanes = ctx->p.batch_lanes > 256 ? 256 : ctx->p.batch_lanes;
+  if (ctx->p.batch_lanes > 0) ctx->max_lanes = ctx->p.batch_lanes > 1024 ? 1024 : ctx->p.batch_lanes;
   if (const char* e = getenv("FCCF_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
   score_init_attributes();
-  Lane* L = nullptr;
-  if (lane_create(ctx, &L) != FCCF_OK) { delete ctx; return nullptr; }
-  ctx->lanes.push_back(L);
-  ctx->stream = L->stream;
+  Group* g = nullptr;
+  if (group_create(ctx, &g) != FCCF_OK) { delete ctx; return nullptr; }
+  ctx->groups.push_back(g);
+  ctx->stream = g->stream;
+  if (table_create(ctx, ctx->itab, 1 << 20, ctx->stream) != FCCF_OK) { group_destroy(g); delete ctx; return nullptr; }
   return ctx;
 }
 
 void fccf_destroy(fccf_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  for (Lane* L : ctx->lanes) lane_destroy(L);
+  for (Group* g : ctx->groups) group_destroy(g);
+  table_destroy(ctx->itab);
   if (ctx->sc_arena.base) cudaFree(ctx->sc_arena.base);
   if (ctx->d_sc_s1) cudaFree(ctx->d_sc_s1);
   if (ctx->d_sc_s2) cudaFree(ctx->d_sc_s2);
@@ -241,13 +282,15 @@ void fccf_destroy(fccf_ctx* ctx) {
 const char* fccf_last_error(const fccf_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no usable CUDA device)"; }
 int fccf_set_params(fccf_ctx* ctx, const fccf_params* params) {
   if (!ctx || !params) return FCCF_ERR_ARG;
-  ctx->p = *params; ctx->params_epoch++;     // captured graphs hold the old values: re-capture lazily
+  int lanes = ctx->p.batch_lanes;
+  ctx->p = *params; ctx->p.batch_lanes = lanes;   // the lane count is fixed at creation
+  ctx->params_epoch++;                            // captured graphs hold the old values: re-capture lazily
   return FCCF_OK;
 }
 uint64_t fccf_launch_count(const fccf_ctx* ctx) {
   if (!ctx) return 0;
   uint64_t n = ctx->launches;
-  for (const Lane* L : ctx->lanes) n += L->launches;
+  for (const Group* g : ctx->groups) n += g->launches;
   return n;
 }
 void* fccf_stream_handle(const fccf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -279,9 +322,28 @@ AngleCuts make_angle_cuts(const fccf_params& p) {
 }
 }  // namespace fccf
 
-static Work make_work(fccf_ctx* ctx, Lane* L, float leaf) {
-  Work w; w.c[0] = L->c[0]; w.c[1] = L->c[1]; w.st = L->d_st; w.p = ctx->p; w.cuts = make_angle_cuts(ctx->p); w.leaf = leaf;
+static Work lane_work(const Lane& L) {
+  Work w; w.c[0] = L.c[0]; w.c[1] = L.c[1]; w.h = L.h; w.st = L.d_st;
   return w;
+}
+// Batch over lanes [0, G) of a group; `ws` must outlive the launches issued with it.
+static Batch make_batch(fccf_ctx* ctx, Group* g, int G, std::vector<Work>& ws, ArgTable* tab) {
+  ws.resize(G);
+  for (int l = 0; l < G; l++) ws[l] = lane_work(g->lanes[l]);
+  Batch b; b.w = ws.data(); b.G = G; b.tab = tab; b.p = ctx->p; b.cuts = make_angle_cuts(ctx->p);
+  return b;
+}
+
+// lane 0 of group 0 as a batch of one, with the immediate-mode argument table (stand-alone stage entry points)
+static Batch single_batch(fccf_ctx* ctx, std::vector<Work>& ws) {
+  ctx->itab.off = 0; ctx->itab.overflow = false; ctx->itab.immediate = true; ctx->itab.stream = ctx->stream;
+  return make_batch(ctx, ctx->groups[0], 1, ws, &ctx->itab);
+}
+static int set_single_call(fccf_ctx* ctx, int n0, int n1, float leaf) {
+  Group& g = ctx->G0();
+  CallArgs* hc = g.h_calls; hc->n0 = n0; hc->n1 = n1; hc->leaf = leaf; hc->pad = 0; hc->raw[0] = ctx->L0().d_raw[0]; hc->raw[1] = ctx->L0().d_raw[1];
+  CK(cudaMemcpyAsync(g.d_calls, hc, sizeof(CallArgs), cudaMemcpyHostToDevice, ctx->stream));
+  return FCCF_OK;
 }
 
 static int check_status(fccf_ctx* ctx, int st) {
@@ -294,116 +356,156 @@ static int check_status(fccf_ctx* ctx, int st) {
   return FCCF_ERR_CAPACITY;
 }
 
-// Every kernel of main() + computer_transform_guess and the read-back of the result block, in stream
-// order on the lane's stream.  All sizes are device-side and the per-call values (point counts, leaf,
-// raw-cloud pointers) are read from st->call, so the sequence is identical for every call on this lane:
-// it is captured into a CUDA graph once and replayed afterwards.
-static int lane_pipeline(fccf_ctx* ctx, Lane* L, uint64_t* launches, bool capturing) {
-  cudaStream_t s = L->stream;
+// Every kernel of main() + computer_transform_guess for G lanes and the read-back of their result
+// blocks, in stream order on the group's stream.  All sizes are device-side and the per-call values
+// (point counts, leaf, raw-cloud pointers) are read from the group's call array, so the sequence is
+// identical for every call with the same G: it is captured into a CUDA graph once and replayed.
+static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_t* launches, bool capturing) {
+  cudaStream_t s = g->stream;
   // inside a capture a plain cudaEventRecord is only a dependency; the External flag makes a timing node
   auto rec = [&](cudaEvent_t e) { return capturing ? cudaEventRecordWithFlags(e, s, cudaEventRecordExternal) : cudaEventRecord(e, s); };
-  Work w = make_work(ctx, L, 0.f);
-  launch_init_state(s, L->d_st, launches);
-  launch_voxelgrid(s, w, 0, 2, launches);            // main(): FCCF.cpp:1668-1678
-  CK(rec(L->ev[2]));
-  launch_voxelgrid(s, w, 1, 2, launches);            // FCCF.cpp:1377-1387
-  CK(rec(L->sev[0]));
-  launch_planes(s, w, 2, 1, launches);               // FCCF.cpp:1400-1401
-  CK(rec(L->sev[1]));
-  launch_hypotheses(s, w, L->h, launches);           // FCCF.cpp:1406-1427, 1439-1462
-  CK(rec(L->sev[2]));
-  launch_cluster(s, w, L->h, launches);              // FCCF.cpp:1464-1466
-  CK(rec(L->sev[3]));
-  launch_quick_verify(s, w, L->h, launches);         // FCCF.cpp:1468-1494
-  CK(rec(L->sev[4]));
-  launch_fine_verify_fuse(s, w, L->h, launches);     // FCCF.cpp:1499-1606
-  CK(rec(L->ev[3]));
-  CK(cudaMemcpyAsync(L->h_st, L->d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
+  std::vector<Work> ws;
+  Batch b = make_batch(ctx, g, G, ws, tab);
+  launch_init_state(s, b, g->d_calls, launches);
+  launch_voxelgrid(s, b, 0, 2, launches);            // main(): FCCF.cpp:1668-1678
+  CK(rec(g->ev[2]));
+  launch_voxelgrid(s, b, 1, 2, launches);            // FCCF.cpp:1377-1387
+  CK(rec(g->sev[0]));
+  launch_planes(s, b, 2, 1, launches);               // FCCF.cpp:1400-1401
+  CK(rec(g->sev[1]));
+  launch_hypotheses(s, b, launches);                 // FCCF.cpp:1406-1427, 1439-1462
+  CK(rec(g->sev[2]));
+  launch_cluster(s, b, launches);                    // FCCF.cpp:1464-1466
+  CK(rec(g->sev[3]));
+  launch_quick_verify(s, b, launches);               // FCCF.cpp:1468-1494
+  CK(rec(g->sev[4]));
+  launch_fine_verify_fuse(s, b, launches);           // FCCF.cpp:1499-1606
+  CK(rec(g->ev[3]));
+  CK(cudaMemcpyAsync(g->h_st_all, g->d_st_all, sizeof(PipeState) * (size_t)G, cudaMemcpyDeviceToHost, s));
+  if (tab->overflow) { ctx->err = "argument table overflow"; return FCCF_ERR_CAPACITY; }
   return FCCF_OK;
 }
 
-// Enqueues one whole registration on the lane's stream (no host synchronisation): the per-call block,
-// optional H2D of both raw clouds, then the pipeline (graph replay).  tar/src: host pointers (host_in)
-// or device pointers.
-static int lane_enqueue(fccf_ctx* ctx, Lane* L, const float* src, size_t n_src, const float* tar, size_t n_tar, float leaf, bool host_in) {
-  cudaStream_t s = L->stream;
-  L->l0 = L->launches; L->had_h2d = host_in;
-  CK(cudaEventRecord(L->ev[0], s));
-  if (host_in) {
-    if (n_tar) CK(cudaMemcpyAsync(L->d_raw[0], tar, n_tar * 12, cudaMemcpyHostToDevice, s));
-    if (n_src) CK(cudaMemcpyAsync(L->d_raw[1], src, n_src * 12, cudaMemcpyHostToDevice, s));
-    L->last_h2d = (n_tar + n_src) * 12;
-  } else L->last_h2d = 0;
-  L->h_call->n0 = (int)n_tar; L->h_call->n1 = (int)n_src; L->h_call->leaf = leaf; L->h_call->pad = 0;
-  L->h_call->raw[0] = host_in ? L->d_raw[0] : tar; L->h_call->raw[1] = host_in ? L->d_raw[1] : src;
-  CK(cudaMemcpyAsync(&L->d_st->call, L->h_call, sizeof(CallArgs), cudaMemcpyHostToDevice, s));
-  CK(cudaEventRecord(L->ev[1], s));
-  if (ctx->use_graph) {
-    if (!L->gexec || L->params_epoch != ctx->params_epoch) {
-      if (L->gexec) { cudaGraphExecDestroy(L->gexec); L->gexec = nullptr; }
-      cudaGraph_t g = nullptr;
-      uint64_t cnt = 0;
-      CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-      int rc = lane_pipeline(ctx, L, &cnt, true);
-      cudaError_t e = cudaStreamEndCapture(s, &g);
-      if (rc != FCCF_OK || e != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); ctx->err = std::string("graph capture failed: ") + cudaGetErrorString(e); cudaGetLastError(); return FCCF_ERR_CUDA; }
-      e = cudaGraphInstantiate(&L->gexec, g, 0);
-      cudaGraphDestroy(g);
-      if (e != cudaSuccess) { L->gexec = nullptr; ctx->err = std::string("graph instantiation failed: ") + cudaGetErrorString(e); return FCCF_ERR_CUDA; }
-      L->graph_launches = (int)cnt; L->params_epoch = ctx->params_epoch;
+static int group_graph(fccf_ctx* ctx, Group* g, int G, GraphRec** out) {
+  if (g->params_epoch != ctx->params_epoch) { CK(cudaStreamSynchronize(g->stream)); group_drop_graphs(g); g->params_epoch = ctx->params_epoch; }
+  for (GraphRec& r : g->graphs) if (r.G == G) { *out = &r; return FCCF_OK; }
+  // room for one more capture?  (about 10 KB of argument blocks per lane)
+  if (g->graphs.size() >= 6 || g->tab.off + (size_t)G * 12288 + 65536 > g->tab.cap) { CK(cudaStreamSynchronize(g->stream)); group_drop_graphs(g); }
+  cudaStream_t s = g->stream;
+  GraphRec r; r.G = G;
+  size_t off0 = g->tab.off;
+  g->tab.immediate = false;
+  cudaGraph_t graph = nullptr;
+  uint64_t cnt = 0;
+  CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+  int rc = group_pipeline(ctx, g, G, &g->tab, &cnt, true);
+  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (rc != FCCF_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc == FCCF_OK) ctx->err = std::string("graph capture failed: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    g->tab.off = off0;
+    return rc != FCCF_OK ? rc : FCCF_ERR_CUDA;
+  }
+  e = cudaGraphInstantiate(&r.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { ctx->err = std::string("graph instantiation failed: ") + cudaGetErrorString(e); g->tab.off = off0; return FCCF_ERR_CUDA; }
+  // the argument blocks of this capture, uploaded once (stream-ordered before the first replay)
+  CK(cudaMemcpyAsync(g->tab.d + off0, g->tab.h + off0, g->tab.off - off0, cudaMemcpyHostToDevice, s));
+  r.launches = (int)cnt;
+  g->graphs.push_back(r);
+  *out = &g->graphs.back();
+  return FCCF_OK;
+}
+
+// Enqueues G whole registrations on the group's stream (no host synchronisation): optional H2D of the
+// raw clouds, the per-call blocks, then the batched pipeline (graph replay).  tar/src: host pointers
+// (host_in) or device pointers; pair index of lane l = pair0 + l.
+static int group_enqueue(fccf_ctx* ctx, Group* g, int G, int pair0, const float* const* src, const size_t* n_src, const float* const* tar, const size_t* n_tar,
+                         float leaf, bool host_in) {
+  cudaStream_t s = g->stream;
+  g->l0 = g->launches; g->had_h2d = host_in; g->G = G; g->last_h2d = 0;
+  CK(cudaEventRecord(g->ev[0], s));
+  for (int l = 0; l < G; l++) {
+    Lane& L = g->lanes[l];
+    L.pair = pair0 + l;
+    if (host_in) {
+      if (n_tar[l]) CK(cudaMemcpyAsync(L.d_raw[0], tar[l], n_tar[l] * 12, cudaMemcpyHostToDevice, s));
+      if (n_src[l]) CK(cudaMemcpyAsync(L.d_raw[1], src[l], n_src[l] * 12, cudaMemcpyHostToDevice, s));
+      g->last_h2d += (n_tar[l] + n_src[l]) * 12;
     }
-    CK(cudaGraphLaunch(L->gexec, s));
-    L->launches += (uint64_t)L->graph_launches;
+    CallArgs& c = g->h_calls[l];
+    c.n0 = (int)n_tar[l]; c.n1 = (int)n_src[l]; c.leaf = leaf; c.pad = 0;
+    c.raw[0] = host_in ? L.d_raw[0] : tar[l]; c.raw[1] = host_in ? L.d_raw[1] : src[l];
+  }
+  CK(cudaMemcpyAsync(g->d_calls, g->h_calls, sizeof(CallArgs) * (size_t)G, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(g->ev[1], s));
+  if (ctx->use_graph) {
+    GraphRec* r = nullptr;
+    int rc = group_graph(ctx, g, G, &r);
+    if (rc) return rc;
+    CK(cudaGraphLaunch(r->exec, s));
+    g->launches += (uint64_t)r->launches;
   } else {
-    int rc = lane_pipeline(ctx, L, &L->launches, false);
+    g->tab.immediate = true; g->tab.off = 0; g->tab.overflow = false;
+    int rc = group_pipeline(ctx, g, G, &g->tab, &g->launches, false);
     if (rc) return rc;
   }
-  CK(cudaEventRecord(L->ev[4], s));
-  L->busy = true;
+  CK(cudaEventRecord(g->ev[4], s));
+  g->busy = true;
   return FCCF_OK;
 }
 
-// Waits for the lane's registration, returns the matrix and (optionally) its device timings.
-static int lane_finish(fccf_ctx* ctx, Lane* L, float T_out[16], fccf_timing* tm) {
-  CK(cudaStreamSynchronize(L->stream));
+// Waits for the group's registrations, returns their matrices (T_out indexed by pair) and adds the
+// group's device timings to *tm.  Returns the worst status of its lanes.
+static int group_finish(fccf_ctx* ctx, Group* g, float* T_out, fccf_timing* tm) {
+  CK(cudaStreamSynchronize(g->stream));
   CK(cudaGetLastError());
-  L->busy = false;
-  for (int i = 0; i < 16; i++) T_out[i] = L->h_st->T_final[i];
-  if (tm) {
-    memset(tm, 0, sizeof *tm);
-    if (L->had_h2d) cudaEventElapsedTime(&tm->h2d_ms, L->ev[0], L->ev[1]);
-    cudaEventElapsedTime(&tm->downsample_ms, L->ev[1], L->ev[2]);
-    cudaEventElapsedTime(&tm->pipeline_ms, L->ev[2], L->ev[3]);
-    cudaEventElapsedTime(&tm->d2h_ms, L->ev[3], L->ev[4]);
-    cudaEventElapsedTime(&tm->total_ms, L->ev[0], L->ev[4]);
-    tm->n_launches = (int)(L->launches - L->l0);
-    tm->h2d_bytes = (unsigned long long)L->last_h2d;
-    tm->d2h_bytes = sizeof(PipeState);
-    tm->stage_ms[0] = tm->downsample_ms;
-    cudaEventElapsedTime(&tm->stage_ms[1], L->ev[2], L->sev[0]);
-    for (int k = 0; k < 4; k++) cudaEventElapsedTime(&tm->stage_ms[2 + k], L->sev[k], L->sev[k + 1]);
-    cudaEventElapsedTime(&tm->stage_ms[6], L->sev[4], L->ev[3]);
+  g->busy = false;
+  int worst = FCCF_OK;
+  for (int l = 0; l < g->G; l++) {
+    Lane& L = g->lanes[l];
+    for (int i = 0; i < 16; i++) T_out[16 * (size_t)L.pair + i] = L.h_st->T_final[i];
+    int rc = check_status(ctx, L.h_st->status);
+    if (rc) worst = rc;
   }
-  return check_status(ctx, L->h_st->status);
+  if (tm) {
+    float v = 0.f;
+    if (g->had_h2d) { cudaEventElapsedTime(&v, g->ev[0], g->ev[1]); tm->h2d_ms += v; }
+    cudaEventElapsedTime(&v, g->ev[1], g->ev[2]); tm->downsample_ms += v; tm->stage_ms[0] += v;
+    cudaEventElapsedTime(&v, g->ev[2], g->ev[3]); tm->pipeline_ms += v;
+    cudaEventElapsedTime(&v, g->ev[3], g->ev[4]); tm->d2h_ms += v;
+    cudaEventElapsedTime(&v, g->ev[0], g->ev[4]); tm->total_ms += v;
+    tm->n_launches += (int)(g->launches - g->l0);
+    tm->h2d_bytes += (unsigned long long)g->last_h2d;
+    tm->d2h_bytes += sizeof(PipeState) * (unsigned long long)g->G;
+    cudaEventElapsedTime(&v, g->ev[2], g->sev[0]); tm->stage_ms[1] += v;
+    for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&v, g->sev[k], g->sev[k + 1]); tm->stage_ms[2 + k] += v; }
+    cudaEventElapsedTime(&v, g->sev[4], g->ev[3]); tm->stage_ms[6] += v;
+  }
+  return worst;
 }
 
 static int register_one(fccf_ctx* ctx, const float* src, size_t n_src, const float* tar, size_t n_tar, float leaf, float T_out[16], fccf_timing* timing, bool host_in) {
   if (!ctx) return FCCF_ERR_NO_DEVICE;
   if (!T_out || (!src && n_src) || (!tar && n_tar) || !(leaf > 0.f)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
-  Lane* L = ctx->lanes[0];
-  int rc = ensure_capacity(ctx, L, n_tar, n_src);
+  Group* g = ctx->groups[0];
+  int rc = ensure_capacity(ctx, g, 0, n_tar, n_src);
   if (rc) return rc;
-  rc = lane_enqueue(ctx, L, src, n_src, tar, n_tar, leaf, host_in);
+  rc = group_enqueue(ctx, g, 1, 0, &src, &n_src, &tar, &n_tar, leaf, host_in);
   if (rc) return rc;
-  rc = lane_finish(ctx, L, T_out, timing);
+  fccf_timing tm; memset(&tm, 0, sizeof tm);
+  rc = group_finish(ctx, g, T_out, &tm);
+  if (timing) *timing = tm;
   ctx->have_run = true; ctx->leaf = leaf;
   return rc;
 }
 
-// Batch of independent pairs: up to max_lanes registrations in flight, one lane (stream + workspace)
-// each; pair b waits only for the lane it reuses.  timing: device times summed over the pairs, and
-// total_ms = host wall clock of the whole batch.
+// Batch of independent pairs: chunks of up to max_lanes pairs, each chunk one batched launch sequence
+// on a group; two groups alternate so that the H2D of one chunk overlaps the compute of the other.
+// timing: device times summed over the chunks (each covers its whole chunk), total_ms = device time
+// of the whole batch, stage_ms[7] = host wall clock.
 static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, const size_t* n_src, const float* const* tar, const size_t* n_tar,
                          float leaf, float* T_out, fccf_timing* timing, bool host_in) {
   if (!ctx) return FCCF_ERR_NO_DEVICE;
@@ -411,43 +513,44 @@ static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, co
   CK(cudaSetDevice(ctx->device));
   fccf_timing acc; memset(&acc, 0, sizeof acc);
   if (n_pairs == 0) { if (timing) *timing = acc; return FCCF_OK; }
-  int nl = std::min(ctx->max_lanes, n_pairs);
+  const int nl = std::min(ctx->max_lanes, n_pairs);
+  const int nchunks = (n_pairs + nl - 1) / nl;
+  const int ngroups = nchunks > 1 ? 2 : 1;
   size_t nmax = 0;
   for (int b = 0; b < n_pairs; b++) { if ((!src[b] && n_src[b]) || (!tar[b] && n_tar[b])) { ctx->err = "bad argument"; return FCCF_ERR_ARG; } nmax = std::max(nmax, std::max(n_src[b], n_tar[b])); }
-  while ((int)ctx->lanes.size() < nl) { Lane* L = nullptr; int rc = lane_create(ctx, &L); if (rc) return rc; ctx->lanes.push_back(L); }
-  for (int l = 0; l < nl; l++) { int rc = ensure_capacity(ctx, ctx->lanes[l], nmax, nmax); if (rc) return rc; }
-  // device time of the whole batch: an event on lane 0 before the first enqueue, and one on lane 0
-  // after it has waited for the last registration of every lane
-  Lane* Z = ctx->lanes[0];
+  while ((int)ctx->groups.size() < ngroups) { Group* g = nullptr; int rc = group_create(ctx, &g); if (rc) return rc; ctx->groups.push_back(g); }
+  for (int gi = 0; gi < ngroups; gi++) {
+    int used = (gi == 0) ? nl : std::min(nl, n_pairs - nl);
+    for (int l = 0; l < used; l++) { int rc = ensure_capacity(ctx, ctx->groups[gi], l, nmax, nmax); if (rc) return rc; }
+  }
+  // device time of the whole batch: an event on group 0's stream before the first enqueue, and one
+  // after it has waited for the last sequence of the other group
+  Group* Z = ctx->groups[0];
   auto t0 = std::chrono::steady_clock::now();
   CK(cudaEventRecord(Z->sev[6], Z->stream));
   int worst = FCCF_OK;
   float enq_ms = 0.f;
-  auto collect = [&](Lane* L) -> int {
-    fccf_timing t;
-    int rc = lane_finish(ctx, L, T_out + 16 * (size_t)L->pair, &t);
-    acc.h2d_ms += t.h2d_ms; acc.downsample_ms += t.downsample_ms; acc.pipeline_ms += t.pipeline_ms; acc.d2h_ms += t.d2h_ms; acc.n_launches += t.n_launches;
-    acc.h2d_bytes += t.h2d_bytes; acc.d2h_bytes += t.d2h_bytes; for (int k = 0; k < 8; k++) acc.stage_ms[k] += t.stage_ms[k];
-    return rc;
-  };
-  for (int b = 0; b < n_pairs; b++) {
-    Lane* L = ctx->lanes[b % nl];
-    if (L->busy) { int rc = collect(L); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc; if (rc) worst = rc; }
-    L->pair = b;
+  for (int k = 0; k < nchunks; k++) {
+    Group* g = ctx->groups[k % ngroups];
+    if (g->busy) { int rc = group_finish(ctx, g, T_out, &acc); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc; if (rc) worst = rc; }
+    const int p0 = k * nl, G = std::min(nl, n_pairs - p0);
     auto te0 = std::chrono::steady_clock::now();
-    int rc = lane_enqueue(ctx, L, src[b], n_src[b], tar[b], n_tar[b], leaf, host_in);
+    int rc = group_enqueue(ctx, g, G, p0, src + p0, n_src + p0, tar + p0, n_tar + p0, leaf, host_in);
     enq_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - te0).count();
     if (rc) return rc;
   }
-  if (getenv("FCCF_DEBUG_TIMING")) fprintf(stderr, "[fccf] batch of %d: host enqueue %.3f ms total (%.3f ms/pair)\n", n_pairs, enq_ms, enq_ms / n_pairs);
-  for (int l = 1; l < nl; l++) if (ctx->lanes[l]->busy) CK(cudaStreamWaitEvent(Z->stream, ctx->lanes[l]->ev[4], 0));
+  if (getenv("FCCF_DEBUG_TIMING")) fprintf(stderr, "[fccf] batch of %d in %d chunk(s): host enqueue %.3f ms total\n", n_pairs, nchunks, enq_ms);
+  for (int gi = 1; gi < ngroups; gi++) if (ctx->groups[gi]->busy) CK(cudaStreamWaitEvent(Z->stream, ctx->groups[gi]->ev[4], 0));
   CK(cudaEventRecord(Z->sev[7], Z->stream));
-  for (int l = 0; l < nl; l++) if (ctx->lanes[l]->busy) { int rc = collect(ctx->lanes[l]); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc; if (rc) worst = rc; }
+  for (int gi = 0; gi < ngroups; gi++) {
+    Group* g = ctx->groups[gi];
+    if (g->busy) { int rc = group_finish(ctx, g, T_out, &acc); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc; if (rc) worst = rc; }
+  }
   CK(cudaEventSynchronize(Z->sev[7]));
   cudaEventElapsedTime(&acc.total_ms, Z->sev[6], Z->sev[7]);
   acc.stage_ms[7] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (timing) *timing = acc;
-  ctx->have_run = true; ctx->leaf = leaf;    // blobs: the last pair that ran on lane 0
+  ctx->have_run = true; ctx->leaf = leaf;    // blobs: the last pair that ran on lane 0 of group 0
   return worst;
 }
 
@@ -475,14 +578,14 @@ int fccf_voxelgrid(fccf_ctx* ctx, const float* xyz, size_t n, float leaf, float*
   if (!ctx) return FCCF_ERR_NO_DEVICE;
   if (!n_out || (!xyz && n) || !(leaf > 0.f)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
-  int rc = ensure_capacity(ctx, ctx->lanes[0], n, 0);
+  int rc = ensure_capacity(ctx, ctx->groups[0], 0, n, 0);
   if (rc) return rc;
   cudaStream_t s = ctx->stream;
+  CK(cudaStreamSynchronize(s));
   if (n) CK(cudaMemcpyAsync(ctx->L0().d_raw[0], xyz, n * 12, cudaMemcpyHostToDevice, s));
-  Work w = make_work(ctx, ctx->lanes[0], leaf);
-  { CallArgs* hc = ctx->L0().h_call; hc->n0 = (int)n; hc->n1 = 0; hc->leaf = leaf; hc->pad = 0; hc->raw[0] = ctx->L0().d_raw[0]; hc->raw[1] = ctx->L0().d_raw[1];
-    CK(cudaMemcpyAsync(&ctx->L0().d_st->call, hc, sizeof(CallArgs), cudaMemcpyHostToDevice, s)); }
-  launch_init_state(s, ctx->L0().d_st, &ctx->launches);
+  std::vector<Work> ws; Batch w = single_batch(ctx, ws);
+  if ((rc = set_single_call(ctx, (int)n, 0, leaf))) return rc;
+  launch_init_state(s, w, ctx->G0().d_calls, &ctx->launches);
   launch_voxelgrid(s, w, 0, 1, &ctx->launches);
   CK(cudaMemcpyAsync(ctx->L0().h_st, ctx->L0().d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -500,13 +603,13 @@ int fccf_extract_planes(fccf_ctx* ctx, const float* xyz, size_t n, int32_t* n_fa
   if (!ctx) return FCCF_ERR_NO_DEVICE;
   if (!xyz && n) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
-  int rc = ensure_capacity(ctx, ctx->lanes[0], n, 0);
+  int rc = ensure_capacity(ctx, ctx->groups[0], 0, n, 0);
   if (rc) return rc;
   cudaStream_t s = ctx->stream;
-  Work w = make_work(ctx, ctx->lanes[0], 1.0f);
-  { CallArgs* hc = ctx->L0().h_call; hc->n0 = 0; hc->n1 = 0; hc->leaf = 1.0f; hc->pad = 0; hc->raw[0] = ctx->L0().d_raw[0]; hc->raw[1] = ctx->L0().d_raw[1];
-    CK(cudaMemcpyAsync(&ctx->L0().d_st->call, hc, sizeof(CallArgs), cudaMemcpyHostToDevice, s)); }
-  launch_init_state(s, ctx->L0().d_st, &ctx->launches);
+  CK(cudaStreamSynchronize(s));
+  std::vector<Work> ws; Batch w = single_batch(ctx, ws);
+  if ((rc = set_single_call(ctx, 0, 0, 1.0f))) return rc;
+  launch_init_state(s, w, ctx->G0().d_calls, &ctx->launches);
   if (n) CK(cudaMemcpyAsync(ctx->L0().c[0].vg_xyz[1], xyz, n * 12, cudaMemcpyHostToDevice, s));
   int nn = (int)n;
   CK(cudaMemcpyAsync(&ctx->L0().d_st->vg[1][0].n_out, &nn, 4, cudaMemcpyHostToDevice, s));
@@ -521,6 +624,7 @@ int fccf_extract_planes(fccf_ctx* ctx, const float* xyz, size_t n, int32_t* n_fa
 
 static int score_prepare(fccf_ctx* ctx, const float* T, size_t n_hyp, const float* s1, size_t n1, const float* s2, size_t n2) {
   cudaStream_t s = ctx->stream;
+  CK(cudaStreamSynchronize(s));
   auto grow = [&](float*& p, size_t& cap, size_t need) -> int {
     if (need <= cap && p) return FCCF_OK;
     if (p) CK(cudaFree(p));
@@ -553,7 +657,9 @@ static int score_prepare(fccf_ctx* ctx, const float* T, size_t n_hyp, const floa
   if (n1) CK(cudaMemcpyAsync(ctx->d_sc_s1, s1, n1 * 12, cudaMemcpyHostToDevice, s));
   if (n2) CK(cudaMemcpyAsync(ctx->d_sc_s2, s2, n2 * 12, cudaMemcpyHostToDevice, s));
   if (n_hyp) CK(cudaMemcpyAsync(ctx->d_sc_T, T, n_hyp * 64, cudaMemcpyHostToDevice, s));
-  launch_score_build(s, ctx->p, ctx->d_sc_s1, ctx->d_sc_n, ctx->d_sc_n + 1, ctx->sc_ws, &ctx->launches);
+  ctx->itab.off = 0; ctx->itab.overflow = false; ctx->itab.immediate = true; ctx->itab.stream = s;
+  ScoreBuildJob job; job.s1 = ctx->d_sc_s1; job.n1 = ctx->d_sc_n; job.n2 = ctx->d_sc_n + 1; job.ws = ctx->sc_ws;
+  launch_score_build(s, ctx->p, &job, 1, ctx->itab, &ctx->launches);
   ctx->sc_n2 = n2; ctx->sc_nhyp = n_hyp;
   return FCCF_OK;
 }
@@ -564,7 +670,7 @@ int fccf_score_hypotheses(fccf_ctx* ctx, const float* T, size_t n_hyp, const flo
   CK(cudaSetDevice(ctx->device));
   int rc = score_prepare(ctx, T, n_hyp, s1_xyz, n1, s2_xyz, n2);
   if (rc) return rc;
-  launch_score_list(ctx->stream, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, &ctx->launches);
+  launch_score_list(ctx->stream, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, ctx->itab, &ctx->launches);
   if (n_hyp) CK(cudaMemcpyAsync(scores, ctx->d_sc_scores, n_hyp * 4, cudaMemcpyDeviceToHost, ctx->stream));
   int st = 0;
   CK(cudaMemcpyAsync(&st, &ctx->L0().d_st->status, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -582,13 +688,13 @@ int fccf_score_hypotheses_bench(fccf_ctx* ctx, const float* T, size_t n_hyp, con
   int rc = score_prepare(ctx, T, n_hyp, s1_xyz, n1, s2_xyz, n2);
   if (rc) return rc;
   cudaStream_t s = ctx->stream;
-  for (int w = 0; w < 3; w++) launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, &ctx->launches);
+  for (int w = 0; w < 3; w++) launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, ctx->itab, &ctx->launches);
   CK(cudaStreamSynchronize(s));
-  CK(cudaEventRecord(ctx->L0().ev[0], s));
-  for (int r = 0; r < repeat; r++) launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, &ctx->launches);
-  CK(cudaEventRecord(ctx->L0().ev[1], s));
+  CK(cudaEventRecord(ctx->G0().ev[0], s));
+  for (int r = 0; r < repeat; r++) launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, ctx->itab, &ctx->launches);
+  CK(cudaEventRecord(ctx->G0().ev[1], s));
   CK(cudaStreamSynchronize(s));
-  float ms = 0; cudaEventElapsedTime(&ms, ctx->L0().ev[0], ctx->L0().ev[1]);
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->G0().ev[0], ctx->G0().ev[1]);
   if (kernel_ms) *kernel_ms = ms / repeat;
   if (scores && n_hyp) CK(cudaMemcpy(scores, ctx->d_sc_scores, n_hyp * 4, cudaMemcpyDeviceToHost));
   CK(cudaGetLastError());
@@ -618,7 +724,7 @@ int fccf_score_counts(fccf_ctx* ctx, size_t hyp, int32_t* rows, size_t cap_rows,
   CK(cudaMalloc(&d_rows, std::max<size_t>(cap_rows, 1) * 20));
   CK(cudaMalloc(&d_n, 4));
   CK(cudaMemsetAsync(d_n, 0, 4, ctx->stream));
-  launch_score_dump(ctx->stream, ctx->p, ctx->d_sc_T + 16 * hyp, ctx->d_sc_s2, ctx->sc_ws, d_rows, (int)cap_rows, d_n, &ctx->launches);
+  launch_score_dump(ctx->stream, ctx->p, ctx->d_sc_T + 16 * hyp, ctx->d_sc_s2, ctx->sc_ws, d_rows, (int)cap_rows, d_n, ctx->itab, &ctx->launches);
   int n = 0;
   CK(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -666,6 +772,7 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
   if (!name_c || !ctx->have_run) { ctx->err = "no run to inspect"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->itab.off = 0; ctx->itab.overflow = false; ctx->itab.immediate = true; ctx->itab.stream = ctx->stream;
   std::string name(name_c);
   const PipeState& st = *ctx->L0().h_st;
   std::vector<char> out; int dt = FCCF_F32;
@@ -768,7 +875,7 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
     std::vector<int> all, off;
     for (int k = 0; k < st.n_top[ti]; k++) {
       CK(cudaMemsetAsync(d_n, 0, 4, ctx->stream));
-      launch_score_dump(ctx->stream, ctx->p, ctx->L0().h.top_T + ((size_t)ti * FCCF_TOPK + k) * 16, ctx->L0().c[1].sub, ws, d_rows, cap_rows, d_n, &ctx->launches);
+      launch_score_dump(ctx->stream, ctx->p, ctx->L0().h.top_T + ((size_t)ti * FCCF_TOPK + k) * 16, ctx->L0().c[1].sub, ws, d_rows, cap_rows, d_n, ctx->itab, &ctx->launches);
       int n = 0; CK(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
       n = std::min(n, cap_rows);
       std::vector<int> rows(5 * (size_t)n); if (n) CK(cudaMemcpy(rows.data(), d_rows, (size_t)n * 20, cudaMemcpyDeviceToHost));

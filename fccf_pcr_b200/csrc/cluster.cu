@@ -16,6 +16,7 @@
 //                   ordered float32 averaging.
 #include "fccf_dev.cuh"
 #include "fccf_internal.h"
+#include <vector>
 
 namespace fccf {
 
@@ -32,7 +33,8 @@ struct ClArgs {
   int cap_hyp;
 };
 
-__global__ void __launch_bounds__(256) cluster_prep_kernel(const __grid_constant__ ClArgs A) {
+__global__ void __launch_bounds__(256) cluster_prep_kernel(const ClArgs* __restrict__ AB) {
+  const ClArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int n = st->hyp_off[3];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,7 +54,8 @@ __global__ void __launch_bounds__(256) cluster_prep_kernel(const __grid_constant
   A.keys[i] = ((u64)ty << 32) | (u64)k;
 }
 
-__global__ void __launch_bounds__(256) cluster_xs_kernel(const __grid_constant__ ClArgs A) {
+__global__ void __launch_bounds__(256) cluster_xs_kernel(const ClArgs* __restrict__ AB) {
+  const ClArgs& A = AB[blockIdx.z];
   const int n = A.st->hyp_off[3];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -108,7 +111,8 @@ __device__ void cl_emit_centre(const float* qt, const int* mem, int m, float* ou
   }
 }
 
-__global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ ClArgs A) {
+__global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict__ AB) {
+  const ClArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int ty = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -302,25 +306,33 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const __grid_constant__ C
   CL_MARK(6)
 }
 
-void launch_cluster(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
-  ClArgs A;
-  PipeState* st = w.st;
-  A.st = st; A.hyp_qt = h.hyp_qt; A.hyp_ax = h.hyp_ax; A.hyp_an = h.hyp_an; A.keys = h.ckeyA; A.order = h.cidxA; A.xs = (float*)h.c_mdist + h.cap_hyp;
-  A.state = h.c_state; A.size = h.c_size; A.seeds = h.c_seeds; A.perm = h.c_perm; A.key = h.c_key; A.members = h.c_members; A.mdist = h.c_mdist;
-  A.centre = h.centre;
-  A.thr_n = w.p.cluster_number_threshold; A.ang_cut = w.cuts.cluster_lt; A.rad = w.p.cluster_distance_threshold; A.sel_num = w.p.seclct_cluster_number;
-  A.nbits = &st->tickets[20]; A.cap_hyp = h.cap_hyp;
-  int cap = h.cap_hyp;
-  cluster_prep_kernel<<<(cap + 255) / 256, 256, 0, s>>>(A);
+void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches) {
+  const int G = b.G;
+  std::vector<ClArgs> As(G); std::vector<SortJobs> abs_(G), bas_(G);
+  int cap = 1;
+  for (int g = 0; g < G; g++) {
+    const Work& w = b.w[g]; const HypWS& h = w.h;
+    ClArgs& A = As[g]; SortJobs& ab = abs_[g]; SortJobs& ba = bas_[g];
+    memset(&A, 0, sizeof A); memset(&ab, 0, sizeof ab); memset(&ba, 0, sizeof ba);
+    PipeState* st = w.st;
+    A.st = st; A.hyp_qt = h.hyp_qt; A.hyp_ax = h.hyp_ax; A.hyp_an = h.hyp_an; A.keys = h.ckeyA; A.order = h.cidxA; A.xs = (float*)h.c_mdist + h.cap_hyp;
+    A.state = h.c_state; A.size = h.c_size; A.seeds = h.c_seeds; A.perm = h.c_perm; A.key = h.c_key; A.members = h.c_members; A.mdist = h.c_mdist;
+    A.centre = h.centre;
+    A.thr_n = b.p.cluster_number_threshold; A.ang_cut = b.cuts.cluster_lt; A.rad = b.p.cluster_distance_threshold; A.sel_num = b.p.seclct_cluster_number;
+    A.nbits = &st->tickets[20]; A.cap_hyp = h.cap_hyp;
+    if (h.cap_hyp > cap) cap = h.cap_hyp;
+    SortJob j; j.kin = h.ckeyA; j.kout = h.ckeyB; j.vin = h.cidxA; j.vout = h.cidxB; j.n = &st->hyp_off[3]; j.nbits = &st->tickets[20]; j.hist = h.chist; j.ticket = &st->tickets[21];
+    ab.j[0] = j; ab.j[1] = j; ab.j[2] = j;
+    SortJob k = j; k.kin = h.ckeyB; k.kout = h.ckeyA; k.vin = h.cidxB; k.vout = h.cidxA; ba.j[0] = k; ba.j[1] = k; ba.j[2] = k;
+  }
+  const ClArgs* dA = b.tab->put(As.data(), G);
+  const SortJobs* dab = b.tab->put(abs_.data(), G); const SortJobs* dba = b.tab->put(bas_.data(), G);
+  cluster_prep_kernel<<<dim3((cap + 255) / 256, 1, G), 256, 0, s>>>(dA);
   if (launches) *launches += 1;
-  SortJobs ab, ba;
-  SortJob j; j.kin = h.ckeyA; j.kout = h.ckeyB; j.vin = h.cidxA; j.vout = h.cidxB; j.n = &st->hyp_off[3]; j.nbits = &st->tickets[20]; j.hist = h.chist; j.ticket = &st->tickets[21];
-  ab.j[0] = j;
-  SortJob k = j; k.kin = h.ckeyB; k.kout = h.ckeyA; k.vin = h.cidxB; k.vout = h.cidxA; ba.j[0] = k;
   // 34-bit keys: 6 passes of 6 bits (even pass count: result back in ckeyA / cidxA)
-  launch_sort(s, ab, ba, 1, cap, 6, launches);
-  cluster_xs_kernel<<<(cap + 255) / 256, 256, 0, s>>>(A);
-  cluster_kernel<<<3, 1024, 0, s>>>(A);
+  launch_sort(s, dab, dba, 1, G, cap, 6, launches);
+  cluster_xs_kernel<<<dim3((cap + 255) / 256, 1, G), 256, 0, s>>>(dA);
+  cluster_kernel<<<dim3(3, 1, G), 1024, 0, s>>>(dA);
   if (launches) *launches += 2;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/fccf.h"
 
 namespace fccf {
@@ -62,7 +63,7 @@ struct ScoreState {          // fine-verify lattice + static voxel table set-up 
   int n1, n2, n_occ, cap_eff, nbits, n_keys, mode, pad;
   int tickets[4];
 };
-struct CallArgs {            // per-call values, copied to the device before the (graph-replayed) pipeline runs
+struct CallArgs {            // per-call values of one lane, copied to the device before the (graph-replayed) pipeline runs
   int n0, n1;                // raw point counts: cloud "1" (TAR file), cloud "2" (SRC file)
   float leaf; int pad;
   const float* raw[2];       // raw clouds (device)
@@ -99,12 +100,37 @@ struct SegJob {
 };
 struct SegJobs { SegJob j[3]; };
 
+// ---- batched launches -------------------------------------------------------------------------
+// A launch covers G "lanes" (independent registrations in flight): grid.z = G and every CTA reads its
+// lane's argument block from a device table, A = table[blockIdx.z].  The table is filled on the host
+// while the launch sequence is issued: in immediate mode each block is copied right before its kernel
+// (stand-alone stage entry points); while a CUDA graph is being captured nothing is copied and the
+// whole table is uploaded once after the capture (the graph only holds the table's device address).
+struct ArgTable {
+  char* h = nullptr;         // pinned host mirror
+  char* d = nullptr;
+  size_t cap = 0, off = 0;
+  cudaStream_t stream = nullptr;
+  bool immediate = true;
+  bool overflow = false;
+  template <class T> const T* put(const T* v, int G) {
+    size_t bytes = (sizeof(T) * (size_t)G + 255) & ~(size_t)255;
+    if (off + bytes > cap) { overflow = true; return (const T*)d; }
+    memcpy(h + off, v, sizeof(T) * (size_t)G);
+    if (immediate) cudaMemcpyAsync(d + off, h + off, sizeof(T) * (size_t)G, cudaMemcpyHostToDevice, stream);
+    const T* r = (const T*)(d + off);
+    off += bytes;
+    return r;
+  }
+};
+
 // Stable LSD radix sort of (key,value) pairs with a device-side element count and key width;
 // `np` passes of ceil(nbits/np) <= 8 bits.  Result ends in (kout,vout) of the last pass; the
 // launcher ping-pongs between the two buffer sets given in `a` and `b` (np even: result in a).
-void launch_sort(cudaStream_t s, SortJobs jobs_ab, SortJobs jobs_ba, int njobs, int cap, int np, uint64_t* launches);
+// jobs_ab / jobs_ba: device tables of G entries.
+void launch_sort(cudaStream_t s, const SortJobs* jobs_ab, const SortJobs* jobs_ba, int njobs, int G, int cap, int np, uint64_t* launches);
 // segment heads of a sorted key array: seg_start[0..nseg], nseg
-void launch_segments(cudaStream_t s, SegJobs jobs, int njobs, int cap, uint64_t* launches);
+void launch_segments(cudaStream_t s, const SegJobs* jobs, int njobs, int G, int cap, uint64_t* launches);
 
 // per-cloud device buffers
 struct CloudWS {
@@ -129,20 +155,6 @@ struct AngleCuts { float third_lt, qv_lt, cluster_lt, grow1_le, grow2_le; };
 float angle_cut(float thr_deg, bool strict);   // smallest float c with theta(c) < thr (strict) or <= thr
 AngleCuts make_angle_cuts(const fccf_params& p);
 
-struct Work {
-  CloudWS c[2];
-  PipeState* st;
-  fccf_params p;
-  AngleCuts cuts;
-  float leaf;
-};
-
-void launch_init_state(cudaStream_t s, PipeState* st, uint64_t* launches);   // reads st->call
-void score_init_attributes();   // one-time function attributes (not allowed inside a stream capture)
-// VoxelGrid stage `stage` (0: on raw clouds, 1: on the stage-0 output) for both clouds
-void launch_voxelgrid(cudaStream_t s, const Work& w, int stage, int ncloud, uint64_t* launches);
-// face_extrate for both clouds (input: vg_xyz[1] with st->vg[1][c].n_out points)
-void launch_planes(cudaStream_t s, const Work& w, int ncloud, int src_stage, uint64_t* launches);
 
 struct ScoreWS {
   int cap_points, cap_hash, t_rows;
@@ -180,21 +192,41 @@ struct HypWS {
   float* top_s1; float* top_s2; int* top_centre;
   ScoreWS fv;                // fine verify: static voxel table of cloud 1's leftover points
 };
-void launch_hypotheses(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
-void launch_cluster(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
-void launch_quick_verify(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
-void launch_fine_verify_fuse(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches);
+struct Work {                 // one lane: its workspaces and state block
+  CloudWS c[2];
+  HypWS h;
+  PipeState* st;
+};
+struct Batch {                // the lanes one batched launch sequence covers
+  const Work* w; int G;
+  ArgTable* tab;
+  fccf_params p;
+  AngleCuts cuts;
+};
+
+// copies calls[lane] into every lane's state block and resets the per-registration counters
+void launch_init_state(cudaStream_t s, const Batch& b, const CallArgs* d_calls, uint64_t* launches);
+void score_init_attributes();   // one-time function attributes (not allowed inside a stream capture)
+// VoxelGrid stage `stage` (0: on raw clouds, 1: on the stage-0 output) for both clouds
+void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uint64_t* launches);
+// face_extrate for both clouds (input: vg_xyz[1] with st->vg[1][c].n_out points)
+void launch_planes(cudaStream_t s, const Batch& b, int ncloud, int src_stage, uint64_t* launches);
+void launch_hypotheses(cudaStream_t s, const Batch& b, uint64_t* launches);
+void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches);
+void launch_quick_verify(cudaStream_t s, const Batch& b, uint64_t* launches);
+void launch_fine_verify_fuse(cudaStream_t s, const Batch& b, uint64_t* launches);
 
 // stand-alone stage entry points (C-ABI helpers)
 void launch_quick_verify_list(cudaStream_t s, const fccf_params& p, float* d_T16, int n, const float* d_planes1, int f1,
                               const float* d_planes2, int f2, float* d_score, int* d_npair, int* d_pairs, int* d_iters, uint64_t* launches);
-// lattice + static hash of the static leftover cloud (n1/n2 are device-side counts)
-void launch_score_build(cudaStream_t s, const fccf_params& p, const float* d_s1, const int* d_n1, const int* d_n2, const ScoreWS& ws, uint64_t* launches);
+// lattice + static hash of the static leftover cloud (n1/n2 are device-side counts), G lanes at once
+struct ScoreBuildJob { const float* s1; const int* n1; const int* n2; ScoreWS ws; };
+void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJob* jobs, int G, ArgTable& tab, uint64_t* launches);
 // scores n_hyp hypotheses (row-major 4x4 each) -> d_scores
-void launch_score_list(cudaStream_t s, const fccf_params& p, const float* d_T16, int n_hyp, const float* d_s2, const ScoreWS& ws, float* d_scores, uint64_t* launches);
+void launch_score_list(cudaStream_t s, const fccf_params& p, const float* d_T16, int n_hyp, const float* d_s2, const ScoreWS& ws, float* d_scores, ArgTable& tab, uint64_t* launches);
 // packed (score, index) maximum of a device score list -> *d_out (8 bytes)
 void launch_score_best(cudaStream_t s, const float* d_scores, int n, long long index_base, long long* d_out, uint64_t* launches);
 // per-voxel (s,t) rows of one hypothesis: rows of 5 ints, *d_nrows rows
-void launch_score_dump(cudaStream_t s, const fccf_params& p, const float* d_T16, const float* d_s2, const ScoreWS& ws, int* d_rows, int cap_rows, int* d_nrows, uint64_t* launches);
+void launch_score_dump(cudaStream_t s, const fccf_params& p, const float* d_T16, const float* d_s2, const ScoreWS& ws, int* d_rows, int cap_rows, int* d_nrows, ArgTable& tab, uint64_t* launches);
 
 }  // namespace fccf

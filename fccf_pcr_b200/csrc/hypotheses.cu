@@ -9,6 +9,7 @@
 //                 writes its hypotheses (3x4 + quaternion/translation) at their pool offsets
 #include "fccf_dev.cuh"
 #include "fccf_internal.h"
+#include <vector>
 
 namespace fccf {
 
@@ -112,7 +113,8 @@ __device__ int hyp_generate(const FaceTable& f1, const FaceTable& f2, int i11, i
   return count;
 }
 
-__global__ void __launch_bounds__(256) base_pairs_kernel(const __grid_constant__ HypArgs A) {
+__global__ void __launch_bounds__(256) base_pairs_kernel(const HypArgs* __restrict__ AB) {
+  const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   __shared__ int s_w[8];
@@ -149,7 +151,8 @@ __global__ void __launch_bounds__(256) base_pairs_kernel(const __grid_constant__
 
 // ---- match loop (FCCF.cpp:1415-1427): one thread per (pair of cloud 1, pair of cloud 2): descriptor test
 // (included angle within 5 degrees, same roughness type) and the number of hypotheses the match pushes ----
-__global__ void __launch_bounds__(128) match_count_kernel(const __grid_constant__ HypArgs A) {
+__global__ void __launch_bounds__(128) match_count_kernel(const HypArgs* __restrict__ AB) {
+  const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int B1 = st->base[0].B, B2 = st->base[1].B;
   const int NM = B1 * B2;
@@ -164,7 +167,8 @@ __global__ void __launch_bounds__(128) match_count_kernel(const __grid_constant_
 }
 
 // ---- ordered scan of the counts per type: pool offsets in the reference's push_back order ----
-__global__ void __launch_bounds__(1024) match_scan_kernel(const __grid_constant__ HypArgs A) {
+__global__ void __launch_bounds__(1024) match_scan_kernel(const HypArgs* __restrict__ AB) {
+  const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   __shared__ u64 s_w64[32];
@@ -202,7 +206,8 @@ __global__ void __launch_bounds__(1024) match_scan_kernel(const __grid_constant_
   }
 }
 
-__global__ void __launch_bounds__(128) emit_hyp_kernel(const __grid_constant__ HypArgs A) {
+__global__ void __launch_bounds__(128) emit_hyp_kernel(const HypArgs* __restrict__ AB) {
+  const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int B2 = st->base[1].B;
   const int NM = st->n_match;
@@ -218,15 +223,21 @@ __global__ void __launch_bounds__(128) emit_hyp_kernel(const __grid_constant__ H
   hyp_generate<true>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_cut, A.hyp_T + off * 12, A.hyp_qt + off * 8);
 }
 
-void launch_hypotheses(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
-  HypArgs A;
-  A.st = w.st; A.match_cnt = h.match_cnt; A.match_off = h.match_off; A.hyp_T = h.hyp_T; A.hyp_qt = h.hyp_qt; A.cap_hyp = h.cap_hyp;
-  A.tmin = w.p.included_angle_min_threshold; A.tmax = w.p.included_angle_max_threshold; A.rough = w.p.rough_threshold_gl;
-  A.same_thr = w.p.included_angle_same_threshold; A.third_thr = w.p.third_plane_threshold; A.third_cut = w.cuts.third_lt;
-  base_pairs_kernel<<<1, 256, 0, s>>>(A);
-  match_count_kernel<<<(FCCF_MAXMATCH + 127) / 128, 128, 0, s>>>(A);
-  match_scan_kernel<<<1, 1024, 0, s>>>(A);
-  emit_hyp_kernel<<<(FCCF_MAXMATCH + 127) / 128, 128, 0, s>>>(A);
+void launch_hypotheses(cudaStream_t s, const Batch& b, uint64_t* launches) {
+  const int G = b.G;
+  std::vector<HypArgs> As(G);
+  for (int g = 0; g < G; g++) {
+    const Work& w = b.w[g]; const HypWS& h = w.h;
+    HypArgs& A = As[g];
+    A.st = w.st; A.match_cnt = h.match_cnt; A.match_off = h.match_off; A.hyp_T = h.hyp_T; A.hyp_qt = h.hyp_qt; A.cap_hyp = h.cap_hyp;
+    A.tmin = b.p.included_angle_min_threshold; A.tmax = b.p.included_angle_max_threshold; A.rough = b.p.rough_threshold_gl;
+    A.same_thr = b.p.included_angle_same_threshold; A.third_thr = b.p.third_plane_threshold; A.third_cut = b.cuts.third_lt;
+  }
+  const HypArgs* dA = b.tab->put(As.data(), G);
+  base_pairs_kernel<<<dim3(1, 1, G), 256, 0, s>>>(dA);
+  match_count_kernel<<<dim3((FCCF_MAXMATCH + 127) / 128, 1, G), 128, 0, s>>>(dA);
+  match_scan_kernel<<<dim3(1, 1, G), 1024, 0, s>>>(dA);
+  emit_hyp_kernel<<<dim3((FCCF_MAXMATCH + 127) / 128, 1, G), 128, 0, s>>>(dA);
   if (launches) *launches += 4;
 }
 

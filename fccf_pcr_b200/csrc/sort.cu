@@ -10,21 +10,26 @@
 // One pass = two kernels:  rs_hist (per-tile digit histograms; the last tile to finish turns
 // them into global scatter offsets) and rs_scatter (stable ranking by warp match + per-(round,
 // warp) digit counters, then a direct scatter).  Tiles are 2048 keys; grid.y batches up to
-// three independent sort jobs (both clouds of a pair) in one launch.
+// three independent sort jobs (both clouds of a pair) and grid.z the lanes (registrations in
+// flight) in one launch.
 #include "fccf_internal.h"
 
 namespace fccf {
 
+// Passes that do work: keys of up to 16 bits (every indoor-scale voxel grid) need only the first two of
+// the launched passes — the rest exit at once, and the result is where an even pass count leaves it.
+__device__ __forceinline__ int rs_active(int nbits, int np) { return (np >= 4 && (np & 1) == 0 && nbits <= 16) ? 2 : np; }
 __device__ __forceinline__ int rs_bpp(int nbits, int np) {
-  int b = (nbits + np - 1) / np;
+  int na = rs_active(nbits, np);
+  int b = (nbits + na - 1) / na;
   return b < 1 ? 1 : (b > 8 ? 8 : b);
 }
 
-__global__ void __launch_bounds__(RS_T) rs_hist_kernel(const __grid_constant__ SortJobs J, int pass, int np) {
-  const SortJob& j = J.j[blockIdx.y];
+__global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restrict__ JB, int pass, int np) {
+  const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
-  if ((int)blockIdx.x >= nact) return;
+  if ((int)blockIdx.x >= nact || pass >= rs_active(*j.nbits, np)) return;
   const int t = threadIdx.x;
   __shared__ u32 h[256];
   __shared__ int s_last;
@@ -64,11 +69,11 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const __grid_constant__ S
   j.hist[(size_t)nact * 256 + t] = h[t];
 }
 
-__global__ void __launch_bounds__(RS_T) rs_scatter_kernel(const __grid_constant__ SortJobs J, int pass, int np, int identity) {
-  const SortJob& j = J.j[blockIdx.y];
+__global__ void __launch_bounds__(RS_T) rs_scatter_kernel(const SortJobs* __restrict__ JB, int pass, int np, int identity) {
+  const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
-  if ((int)blockIdx.x >= nact) return;
+  if ((int)blockIdx.x >= nact || pass >= rs_active(*j.nbits, np)) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   __shared__ unsigned short cnt[RS_I * 8][256];
   __shared__ u32 gbase[256];
@@ -111,12 +116,12 @@ __global__ void __launch_bounds__(RS_T) rs_scatter_kernel(const __grid_constant_
   }
 }
 
-void launch_sort(cudaStream_t s, SortJobs ab, SortJobs ba, int njobs, int cap, int np, uint64_t* launches) {
+void launch_sort(cudaStream_t s, const SortJobs* ab, const SortJobs* ba, int njobs, int G, int cap, int np, uint64_t* launches) {
   int nb = (cap + RS_TILE - 1) / RS_TILE;
   if (nb < 1) nb = 1;
-  dim3 grid(nb, njobs);
+  dim3 grid(nb, njobs, G);
   for (int p = 0; p < np; p++) {
-    const SortJobs& J = (p & 1) ? ba : ab;
+    const SortJobs* J = (p & 1) ? ba : ab;
     rs_hist_kernel<<<grid, RS_T, 0, s>>>(J, p, np);
     rs_scatter_kernel<<<grid, RS_T, 0, s>>>(J, p, np, p == 0 ? 1 : 0);
     if (launches) *launches += 2;
@@ -128,8 +133,8 @@ void launch_sort(cudaStream_t s, SortJobs ab, SortJobs ba, int njobs, int cap, i
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool seg_is_head(const u64* keys, int i) { return i == 0 || keys[i] != keys[i - 1]; }
 
-__global__ void __launch_bounds__(RS_T) seg_count_kernel(const __grid_constant__ SegJobs J) {
-  const SegJob& j = J.j[blockIdx.y];
+__global__ void __launch_bounds__(RS_T) seg_count_kernel(const SegJobs* __restrict__ JB) {
+  const SegJob& j = JB[blockIdx.z].j[blockIdx.y];
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
   const int t = threadIdx.x;
@@ -173,8 +178,8 @@ __global__ void __launch_bounds__(RS_T) seg_count_kernel(const __grid_constant__
   if (t == 0) { *j.nseg = (int)carry; j.seg_start[carry] = n; *j.ticket = 0; }
 }
 
-__global__ void __launch_bounds__(RS_T) seg_write_kernel(const __grid_constant__ SegJobs J) {
-  const SegJob& j = J.j[blockIdx.y];
+__global__ void __launch_bounds__(RS_T) seg_write_kernel(const SegJobs* __restrict__ JB) {
+  const SegJob& j = JB[blockIdx.z].j[blockIdx.y];
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
   if ((int)blockIdx.x >= nact) return;
@@ -199,10 +204,10 @@ __global__ void __launch_bounds__(RS_T) seg_write_kernel(const __grid_constant__
   }
 }
 
-void launch_segments(cudaStream_t s, SegJobs jobs, int njobs, int cap, uint64_t* launches) {
+void launch_segments(cudaStream_t s, const SegJobs* jobs, int njobs, int G, int cap, uint64_t* launches) {
   int nb = (cap + RS_TILE - 1) / RS_TILE;
   if (nb < 1) nb = 1;
-  dim3 grid(nb, njobs);
+  dim3 grid(nb, njobs, G);
   seg_count_kernel<<<grid, RS_T, 0, s>>>(jobs);
   seg_write_kernel<<<grid, RS_T, 0, s>>>(jobs);
   if (launches) *launches += 2;

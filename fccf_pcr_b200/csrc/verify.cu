@@ -11,6 +11,8 @@
 // throughout — this is the FP64-pipe stage of the path.
 #include "fccf_dev.cuh"
 #include "fccf_internal.h"
+#include <cstdlib>
+#include <vector>
 
 namespace fccf {
 
@@ -20,9 +22,11 @@ __device__ __forceinline__ double bfly(double v) {
   return v;
 }
 __device__ __forceinline__ void crossd(const double a[3], const double b[3], double o[3]) {
-  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+  // explicit FMAs (the library is built with -fmad=false for the bit-exact float32 stages; the FP64
+  // refinement is tolerance-checked and the fused forms halve its dependent instruction chains)
+  o[0] = fma(a[1], b[2], -(a[2] * b[1])); o[1] = fma(a[2], b[0], -(a[0] * b[2])); o[2] = fma(a[0], b[1], -(a[1] * b[0]));
 }
-__device__ __forceinline__ double dot3d(const double a[3], const double b[3]) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
+__device__ __forceinline__ double dot3d(const double a[3], const double b[3]) { return fma(a[0], b[0], fma(a[1], b[1], a[2] * b[2])); }
 
 // f(q,a) = a + w*uv + u x uv, uv = 2 (u x a); Jacobian wrt (x,y,z,w)
 __device__ __forceinline__ void rot_with_jac(const double q[4], const double a[3], double f[3], double J[3][4], bool want) {
@@ -30,7 +34,7 @@ __device__ __forceinline__ void rot_with_jac(const double q[4], const double a[3
   double uv[3]; crossd(u, a, uv); uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
   double c2[3]; crossd(u, uv, c2);
   #pragma unroll
-  for (int i = 0; i < 3; i++) f[i] = (a[i] + w * uv[i]) + c2[i];
+  for (int i = 0; i < 3; i++) f[i] = fma(w, uv[i], a[i]) + c2[i];
   if (!want) return;
   #pragma unroll
   for (int k = 0; k < 3; k++) {
@@ -38,7 +42,7 @@ __device__ __forceinline__ void rot_with_jac(const double q[4], const double a[3
     double Av[3]; crossd(e, a, Av); Av[0] *= 2; Av[1] *= 2; Av[2] *= 2;
     double t1[3], t2[3]; crossd(e, uv, t1); crossd(u, Av, t2);
     #pragma unroll
-    for (int i = 0; i < 3; i++) J[i][k] = w * Av[i] + t1[i] + t2[i];
+    for (int i = 0; i < 3; i++) J[i][k] = fma(w, Av[i], t1[i]) + t2[i];
   }
   #pragma unroll
   for (int i = 0; i < 3; i++) J[i][3] = uv[i];
@@ -77,7 +81,7 @@ __device__ __forceinline__ bool lm_eval(const LmRow& R, const double x[7], doubl
       // EigenQuaternionParameterization::ComputeJacobian (4x3)
       double Pm[4][3] = {{q[3], q[2], -q[1]}, {-q[2], q[3], q[0]}, {q[1], -q[0], q[3]}, {-q[0], -q[1], -q[2]}};
       #pragma unroll
-      for (int lc = 0; lc < 3; lc++) { double s = 0; for (int a = 0; a < 4; a++) s += Ja[a] * Pm[a][lc]; J[lc] = s; }
+      for (int lc = 0; lc < 3; lc++) { double s = 0; for (int a = 0; a < 4; a++) s = fma(Ja[a], Pm[a][lc], s); J[lc] = s; }
       #pragma unroll
       for (int lc = 0; lc < 3; lc++) J[3 + lc] = Ja[4 + lc];
       #pragma unroll
@@ -109,28 +113,28 @@ __device__ __forceinline__ bool lm_qr_solve(double A[6], double b, double B[6], 
   for (int k = 0; k < 6; k++) {
     double mk = (lane >= k) ? A[k] : 0.0;
     double ak = aug ? B[k] : 0.0;
-    double nrm = sqrt(bfly(mk * mk + ak * ak));
+    double nrm = sqrt(bfly(fma(mk, mk, ak * ak)));
     if (nrm == 0.0) return false;
     double akk = __shfl_sync(0xffffffffu, A[k], k);
     double alpha = (akk > 0) ? -nrm : nrm;
     double v0 = akk - alpha;
     double vm = (lane == k) ? v0 : mk;     // Householder vector entries of this lane's rows
     double va = ak;
-    double vtv = bfly(vm * vm + va * va);
+    double vtv = bfly(fma(vm, vm, va * va));
     if (vtv == 0.0) return false;
     double beta = 2.0 / vtv;
     #pragma unroll
     for (int j = k + 1; j < 6; j++) {
-      double s = bfly(vm * A[j] + va * (aug ? B[j] : 0.0));
+      double s = bfly(fma(vm, A[j], va * (aug ? B[j] : 0.0)));
       s *= beta;
-      A[j] -= s * vm;
-      if (aug) B[j] -= s * va;
+      A[j] = fma(-s, vm, A[j]);
+      if (aug) B[j] = fma(-s, va, B[j]);
     }
     {
-      double s = bfly(vm * b + va * bb);
+      double s = bfly(fma(vm, b, va * bb));
       s *= beta;
-      b -= s * vm;
-      if (aug) bb -= s * va;
+      b = fma(-s, vm, b);
+      if (aug) bb = fma(-s, va, bb);
     }
     if (lane == k) A[k] = alpha;
   }
@@ -139,7 +143,7 @@ __device__ __forceinline__ bool lm_qr_solve(double A[6], double b, double B[6], 
   for (int k = 5; k >= 0; k--) {
     double s = b;
     #pragma unroll
-    for (int j = k + 1; j < 6; j++) s -= A[j] * y[j];
+    for (int j = k + 1; j < 6; j++) s = fma(-A[j], y[j], s);
     s = s / A[k];
     y[k] = __shfl_sync(0xffffffffu, s, k);
     ok = ok && isfinite(y[k]);
@@ -320,7 +324,9 @@ struct QvArgs {
   float ang_cut, dist_thr, required, fine_number;   // ang_cut: cosine cut of quick_verify_angel_threshold (strict <)
 };
 
-__global__ void __launch_bounds__(128) quick_verify_kernel(const __grid_constant__ QvArgs A) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) quick_verify_kernel(const QvArgs* __restrict__ AB) {
+  const QvArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -337,7 +343,8 @@ __global__ void __launch_bounds__(128) quick_verify_kernel(const __grid_constant
 }
 
 // score_range + top-k (FCCF.cpp:1494-1544): one CTA per type
-__global__ void __launch_bounds__(256) rank_top_kernel(const __grid_constant__ QvArgs A) {
+__global__ void __launch_bounds__(256) rank_top_kernel(const QvArgs* __restrict__ AB) {
+  const QvArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, ty = blockIdx.x;
   __shared__ float s_key[FCCF_MAXCENTRE];
@@ -364,13 +371,24 @@ __global__ void __launch_bounds__(256) rank_top_kernel(const __grid_constant__ Q
   }
 }
 
-void launch_quick_verify(cudaStream_t s, const Work& w, const HypWS& h, uint64_t* launches) {
-  QvArgs A;
-  A.st = w.st; A.centre = h.centre; A.qv_T = h.qv_T; A.qv_score = h.qv_score; A.qv_npair = h.qv_npair; A.qv_pairs = h.qv_pairs; A.qv_iters = h.qv_iters;
-  A.rank_perm = h.rank_perm; A.top_T = h.top_T; A.top_s1 = h.top_s1; A.top_centre = h.top_centre;
-  A.ang_cut = w.cuts.qv_lt; A.dist_thr = w.p.quick_verify_distance_threshold; A.required = w.p.required_optimize_plane; A.fine_number = w.p.fine_verify_number;
-  quick_verify_kernel<<<(3 * FCCF_MAXCENTRE + 3) / 4, 128, 0, s>>>(A);
-  rank_top_kernel<<<3, 256, 0, s>>>(A);
+void launch_quick_verify(cudaStream_t s, const Batch& b, uint64_t* launches) {
+  const int G = b.G;
+  std::vector<QvArgs> As(G);
+  for (int g = 0; g < G; g++) {
+    const Work& w = b.w[g]; const HypWS& h = w.h;
+    QvArgs& A = As[g];
+    A.st = w.st; A.centre = h.centre; A.qv_T = h.qv_T; A.qv_score = h.qv_score; A.qv_npair = h.qv_npair; A.qv_pairs = h.qv_pairs; A.qv_iters = h.qv_iters;
+    A.rank_perm = h.rank_perm; A.top_T = h.top_T; A.top_s1 = h.top_s1; A.top_centre = h.top_centre;
+    A.ang_cut = b.cuts.qv_lt; A.dist_thr = b.p.quick_verify_distance_threshold; A.required = b.p.required_optimize_plane; A.fine_number = b.p.fine_verify_number;
+  }
+  const QvArgs* dA = b.tab->put(As.data(), G);
+  static int occ = -1;
+  if (occ < 0) { const char* e = getenv("FCCF_QV_OCC"); occ = e ? atoi(e) : 3; }
+  dim3 grid((3 * FCCF_MAXCENTRE + 3) / 4, 1, G);
+  if (occ <= 2) quick_verify_kernel<2><<<grid, 128, 0, s>>>(dA);
+  else if (occ == 3) quick_verify_kernel<3><<<grid, 128, 0, s>>>(dA);
+  else quick_verify_kernel<4><<<grid, 128, 0, s>>>(dA);
+  rank_top_kernel<<<dim3(3, 1, G), 256, 0, s>>>(dA);
   if (launches) *launches += 2;
 }
 

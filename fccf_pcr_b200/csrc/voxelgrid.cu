@@ -10,6 +10,7 @@
 // HBM traffic per launch is 12 B/point read (+8 B key write); everything else is key traffic.
 #include "fccf_dev.cuh"
 #include "fccf_internal.h"
+#include <vector>
 
 namespace fccf {
 
@@ -23,7 +24,8 @@ struct VGArgs {
   int emulate;
 };
 
-__global__ void __launch_bounds__(256) vg_minmax_kernel(const __grid_constant__ VGArgs A) {
+__global__ void __launch_bounds__(256) vg_minmax_kernel(const VGArgs* __restrict__ AB) {
+  const VGArgs& A = AB[blockIdx.z];
   const int c = blockIdx.y;
   const int n = *A.n_in[c];
   const float* p = A.in[c] ? A.in[c] : A.call->raw[c];
@@ -88,7 +90,8 @@ __global__ void __launch_bounds__(256) vg_minmax_kernel(const __grid_constant__ 
   st->nbits = nbits < 1 ? 1 : nbits;
 }
 
-__global__ void __launch_bounds__(256) vg_keys_kernel(const __grid_constant__ VGArgs A) {
+__global__ void __launch_bounds__(256) vg_keys_kernel(const VGArgs* __restrict__ AB) {
+  const VGArgs& A = AB[blockIdx.z];
   const int c = blockIdx.y;
   const VGState* st = A.st[c];
   const int n = st->n_in;
@@ -122,7 +125,8 @@ struct VGOut {
 };
 
 // one thread per occupied cell: in-order float32 running sum (pcl::CentroidPoint<PointXYZ>)
-__global__ void __launch_bounds__(128) vg_centroid_kernel(const __grid_constant__ VGOut A) {
+__global__ void __launch_bounds__(128) vg_centroid_kernel(const VGOut* __restrict__ AB) {
+  const VGOut& A = AB[blockIdx.z];
   const int c = blockIdx.y;
   VGState* st = A.st[c];
   const int nseg = st->n_out;
@@ -142,10 +146,14 @@ __global__ void __launch_bounds__(128) vg_centroid_kernel(const __grid_constant_
   A.cnt[c][s] = e - b;
 }
 
-__global__ void init_state_kernel(PipeState* st) {
+struct InitArgs { PipeState* st; };
+__global__ void init_state_kernel(const InitArgs* __restrict__ AB, const CallArgs* __restrict__ calls) {
+  PipeState* st = AB[blockIdx.x].st;
   int t = threadIdx.x;
   if (t == 0) {
-    const int n0 = st->call.n0, n1 = st->call.n1;
+    const CallArgs call = calls[blockIdx.x];
+    st->call = call;
+    const int n0 = call.n0, n1 = call.n1;
     for (int s = 0; s < 2; s++) for (int c = 0; c < 2; c++) {
       VGState& v = st->vg[s][c];
       v.n_in = 0; v.n_finite = 0; v.n_out = 0; v.bail = 0; v.total = 0; v.nbits = 1;
@@ -159,45 +167,55 @@ __global__ void init_state_kernel(PipeState* st) {
   if (t < 64) st->tickets[t] = 0;
 }
 
-void launch_init_state(cudaStream_t s, PipeState* st, uint64_t* launches) {
-  init_state_kernel<<<1, 64, 0, s>>>(st);
+void launch_init_state(cudaStream_t s, const Batch& b, const CallArgs* d_calls, uint64_t* launches) {
+  std::vector<InitArgs> I(b.G);
+  for (int g = 0; g < b.G; g++) I[g].st = b.w[g].st;
+  init_state_kernel<<<b.G, 64, 0, s>>>(b.tab->put(I.data(), b.G), d_calls);
   if (launches) *launches += 1;
 }
 
 // stage 0: raw -> vg_xyz[0]; stage 1: vg_xyz[0] -> vg_xyz[1]
-void launch_voxelgrid(cudaStream_t s, const Work& w, int stage, int ncloud, uint64_t* launches) {
-  VGArgs A; VGOut O; SortJobs ab, ba; SegJobs sj;
+void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uint64_t* launches) {
+  const int G = b.G;
+  std::vector<VGArgs> As(G); std::vector<VGOut> Os(G); std::vector<SortJobs> abs_(G), bas_(G); std::vector<SegJobs> sjs(G);
   int cap = 1;
-  for (int c = 0; c < ncloud; c++) {
-    const CloudWS& cw = w.c[c];
+  for (int g = 0; g < G; g++) {
+    const Work& w = b.w[g];
+    VGArgs& A = As[g]; VGOut& O = Os[g]; SortJobs& ab = abs_[g]; SortJobs& ba = bas_[g]; SegJobs& sj = sjs[g];
+    memset(&A, 0, sizeof A); memset(&O, 0, sizeof O); memset(&ab, 0, sizeof ab); memset(&ba, 0, sizeof ba); memset(&sj, 0, sizeof sj);
     PipeState* st = w.st;
-    A.in[c] = (stage == 0) ? nullptr : cw.vg_xyz[0];
-    A.n_in[c] = (stage == 0) ? &st->vg[0][c].n_in : &st->vg[0][c].n_out;
-    A.st[c] = &st->vg[stage][c];
-    A.keys[c] = cw.keyA;
-    A.ticket[c] = &st->tickets[0 + c];
-    SortJob j; j.kin = cw.keyA; j.kout = cw.keyB; j.vin = cw.idxA; j.vout = cw.idxB; j.n = &st->vg[stage][c].n_in; j.nbits = &st->vg[stage][c].nbits;
-    j.hist = cw.hist; j.ticket = &st->tickets[2 + c];
-    ab.j[c] = j;
-    SortJob k = j; k.kin = cw.keyB; k.kout = cw.keyA; k.vin = cw.idxB; k.vout = cw.idxA;
-    ba.j[c] = k;
-    SegJob g; g.keys = cw.keyA; g.n = &st->vg[stage][c].n_finite; g.seg_start = cw.seg_start; g.nseg = &st->vg[stage][c].n_out; g.blk = cw.segblk; g.ticket = &st->tickets[4 + c];
-    sj.j[c] = g;
-    O.in[c] = A.in[c]; O.keys[c] = cw.keyA; O.idx[c] = cw.idxA; O.seg_start[c] = cw.seg_start; O.st[c] = &st->vg[stage][c];
-    O.out[c] = cw.vg_xyz[stage]; O.cell[c] = cw.vg_cell[stage]; O.cnt[c] = cw.vg_cnt[stage];
-    if (cw.cap > cap) cap = cw.cap;
+    for (int c = 0; c < ncloud; c++) {
+      const CloudWS& cw = w.c[c];
+      A.in[c] = (stage == 0) ? nullptr : cw.vg_xyz[0];
+      A.n_in[c] = (stage == 0) ? &st->vg[0][c].n_in : &st->vg[0][c].n_out;
+      A.st[c] = &st->vg[stage][c];
+      A.keys[c] = cw.keyA;
+      A.ticket[c] = &st->tickets[0 + c];
+      SortJob j; j.kin = cw.keyA; j.kout = cw.keyB; j.vin = cw.idxA; j.vout = cw.idxB; j.n = &st->vg[stage][c].n_in; j.nbits = &st->vg[stage][c].nbits;
+      j.hist = cw.hist; j.ticket = &st->tickets[2 + c];
+      ab.j[c] = j;
+      SortJob k = j; k.kin = cw.keyB; k.kout = cw.keyA; k.vin = cw.idxB; k.vout = cw.idxA;
+      ba.j[c] = k;
+      SegJob sg; sg.keys = cw.keyA; sg.n = &st->vg[stage][c].n_finite; sg.seg_start = cw.seg_start; sg.nseg = &st->vg[stage][c].n_out; sg.blk = cw.segblk; sg.ticket = &st->tickets[4 + c];
+      sj.j[c] = sg;
+      O.in[c] = A.in[c]; O.keys[c] = cw.keyA; O.idx[c] = cw.idxA; O.seg_start[c] = cw.seg_start; O.st[c] = &st->vg[stage][c];
+      O.out[c] = cw.vg_xyz[stage]; O.cell[c] = cw.vg_cell[stage]; O.cnt[c] = cw.vg_cnt[stage];
+      if (cw.cap > cap) cap = cw.cap;
+    }
+    for (int c = ncloud; c < 2; c++) { A.in[c] = A.in[0]; A.n_in[c] = A.n_in[0]; A.st[c] = A.st[0]; A.keys[c] = A.keys[0]; A.ticket[c] = A.ticket[0]; }
+    A.call = &st->call; O.call = &st->call; A.emulate = b.p.emulate_pcl_overflow;
   }
-  for (int c = ncloud; c < 2; c++) { A.in[c] = A.in[0]; A.n_in[c] = A.n_in[0]; A.st[c] = A.st[0]; A.keys[c] = A.keys[0]; A.ticket[c] = A.ticket[0]; }
-  A.call = &w.st->call; O.call = &w.st->call; A.emulate = w.p.emulate_pcl_overflow;
+  const VGArgs* dA = b.tab->put(As.data(), G); const VGOut* dO = b.tab->put(Os.data(), G);
+  const SortJobs* dab = b.tab->put(abs_.data(), G); const SortJobs* dba = b.tab->put(bas_.data(), G); const SegJobs* dsj = b.tab->put(sjs.data(), G);
   int nb_mm = (cap + 256 * 8 - 1) / (256 * 8);
   if (nb_mm > 592) nb_mm = 592;
   if (nb_mm < 1) nb_mm = 1;
-  vg_minmax_kernel<<<dim3(nb_mm, ncloud), 256, 0, s>>>(A);
-  vg_keys_kernel<<<dim3((cap + 255) / 256, ncloud), 256, 0, s>>>(A);
+  vg_minmax_kernel<<<dim3(nb_mm, ncloud, G), 256, 0, s>>>(dA);
+  vg_keys_kernel<<<dim3((cap + 255) / 256, ncloud, G), 256, 0, s>>>(dA);
   if (launches) *launches += 2;
-  launch_sort(s, ab, ba, ncloud, cap, 4, launches);   // result back in keyA / idxA
-  launch_segments(s, sj, ncloud, cap, launches);
-  vg_centroid_kernel<<<dim3((cap + 127) / 128, ncloud), 128, 0, s>>>(O);
+  launch_sort(s, dab, dba, ncloud, G, cap, 4, launches);   // result back in keyA / idxA
+  launch_segments(s, dsj, ncloud, G, cap, launches);
+  vg_centroid_kernel<<<dim3((cap + 127) / 128, ncloud, G), 128, 0, s>>>(dO);
   if (launches) *launches += 1;
 }
 
