@@ -223,6 +223,7 @@ def run_ours(args):
         Tb = ctx.register_batch(srcs, tars, args.leaf)       # pinned host -> device, pipeline, result -> host
         e2e_s += time.perf_counter() - t0
         h2d_step, d2h_step = int(ctx.timing.h2d_bytes), int(ctx.timing.d2h_bytes)
+        h2d_ms_step = float(ctx.timing.h2d_ms)
         l2_flush()
     barrier()
     e2e_s = max_over_ranks(e2e_s)
@@ -271,7 +272,7 @@ def run_ours(args):
                     "note": "18 FP32 + 9 FP64 flop per moving point per hypothesis (SURVEY.md §8d) against 148 SM x 128 (64) lanes x 2 x max SM clock"},
         "wall_s_timed_region": round(t_wall, 3),
         "e2e": {"value": round(e2e_ms_per_reg, 5), "unit": "ms/registration", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
-                "api": "fccf_register_batch (pinned host buffers in, 4x4 out)", "timing": "host wall clock around the call, synchronised on both sides"},
+                "h2d_ms_per_step": round(h2d_ms_step, 3), "api": "fccf_register_batch (pinned host buffers in, 4x4 out)", "timing": "host wall clock around the call, synchronised on both sides"},
         "gpu_launches": int(launches + score_launches),
         "roofline": {"kernel": "score_warp_kernel (fine_verify-equivalent hypothesis scoring, one hypothesis per warp)", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,

@@ -255,6 +255,7 @@ fccf_ctx* fccf_create(int device, const fccf_params* params) {
   if (ctx->p.batch_lanes > 0) ctx->max_lanes = ctx->p.batch_lanes > 1024 ? 1024 : ctx->p.batch_lanes;
   if (const char* e = getenv("FCCF_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
   score_init_attributes();
+  cluster_init_attributes();
   Group* g = nullptr;
   if (group_create(ctx, &g) != FCCF_OK) { delete ctx; return nullptr; }
   ctx->groups.push_back(g);
@@ -515,12 +516,14 @@ static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, co
   if (n_pairs == 0) { if (timing) *timing = acc; return FCCF_OK; }
   const int nl = std::min(ctx->max_lanes, n_pairs);
   const int nchunks = (n_pairs + nl - 1) / nl;
-  const int ngroups = nchunks > 1 ? 2 : 1;
+  int max_groups = 2;
+  if (const char* e = getenv("FCCF_GROUPS")) { max_groups = atoi(e); if (max_groups < 1) max_groups = 1; if (max_groups > 8) max_groups = 8; }
+  const int ngroups = std::min(nchunks, max_groups);
   size_t nmax = 0;
   for (int b = 0; b < n_pairs; b++) { if ((!src[b] && n_src[b]) || (!tar[b] && n_tar[b])) { ctx->err = "bad argument"; return FCCF_ERR_ARG; } nmax = std::max(nmax, std::max(n_src[b], n_tar[b])); }
   while ((int)ctx->groups.size() < ngroups) { Group* g = nullptr; int rc = group_create(ctx, &g); if (rc) return rc; ctx->groups.push_back(g); }
   for (int gi = 0; gi < ngroups; gi++) {
-    int used = (gi == 0) ? nl : std::min(nl, n_pairs - nl);
+    int used = std::min(nl, n_pairs - gi * nl);
     for (int l = 0; l < used; l++) { int rc = ensure_capacity(ctx, ctx->groups[gi], l, nmax, nmax); if (rc) return rc; }
   }
   // device time of the whole batch: an event on group 0's stream before the first enqueue, and one

@@ -37,9 +37,8 @@ __global__ void __launch_bounds__(256) cluster_prep_kernel(const ClArgs* __restr
   const ClArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int n = st->hyp_off[3];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *A.nbits = 34;
-  if (i >= n) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *A.nbits = 34;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
   const float* q = A.hyp_qt + (size_t)i * 8;
   q4 Q; Q.w = q[0]; Q.x = q[1]; Q.y = q[2]; Q.z = q[3];
   f3 ax = quat_rotate(Q, mk3(1, 0, 0));
@@ -52,19 +51,21 @@ __global__ void __launch_bounds__(256) cluster_prep_kernel(const ClArgs* __restr
   if (x != x) k = 0xffffffffu;
   else { u32 b = __float_as_uint(x); k = (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
   A.keys[i] = ((u64)ty << 32) | (u64)k;
+  }
 }
 
 __global__ void __launch_bounds__(256) cluster_xs_kernel(const ClArgs* __restrict__ AB) {
   const ClArgs& A = AB[blockIdx.z];
   const int n = A.st->hyp_off[3];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  float x = A.hyp_qt[(size_t)A.order[k] * 8 + 4];
-  A.xs[k] = (x != x) ? CUDART_INF_F : x;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    float x = A.hyp_qt[(size_t)A.order[k] * 8 + 4];
+    A.xs[k] = (x != x) ? CUDART_INF_F : x;
+  }
 }
 
-__device__ __forceinline__ bool cl_neigh(const float* qi, const float* ai, double ni, const float* qj, const float* aj, double nj, float r2, float ang_cut, float* dist) {
-  float d0 = qi[4] - qj[4], d1 = qi[5] - qj[5], d2 = qi[6] - qj[6];
+// ti/tj: translations (3 floats), ai/aj: rotated x axes (3 floats), ni/nj: their double norms
+__device__ __forceinline__ bool cl_neigh(const float* ti, const float* ai, double ni, const float* tj, const float* aj, double nj, float r2, float ang_cut, float* dist) {
+  float d0 = ti[0] - tj[0], d1 = ti[1] - tj[1], d2 = ti[2] - tj[2];
   float d = 0.f; d += d0 * d0; d += d1 * d1; d += d2 * d2;    // flann::L2_Simple
   if (!(d < r2)) return false;
   if (dist) *dist = d;
@@ -111,6 +112,10 @@ __device__ void cl_emit_centre(const float* qt, const int* mem, int m, float* ou
   }
 }
 
+#define CL_SMEM_N 3072        // pools up to this many hypotheses are clustered out of shared memory
+#define CL_SMEM_BYTES (CL_SMEM_N * 52)
+extern __shared__ __align__(16) unsigned char cl_dyn[];
+
 __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict__ AB) {
   const ClArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
@@ -118,8 +123,6 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n = st->n_hyp[ty], base = st->hyp_off[ty], tnum = st->hyp_off[3];
   const float* qt = A.hyp_qt + (size_t)base * 8;
-  const float* ax = A.hyp_ax + (size_t)base * 4;
-  const double* an = A.hyp_an + base;
   float* centre = A.centre + (size_t)ty * FCCF_MAXCENTRE * 8;
   __shared__ int s_flag, s_K, s_E;
   __shared__ unsigned long long s_sort[40];
@@ -139,15 +142,37 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
     }
     return;
   }
-  const float* xs = A.xs + base;
-  const u32* order = A.order + base;   // values are global indices; local = value - base
-  int* state = A.state + base; int* size = A.size + base; int* seeds = A.seeds + base; int* perm = A.perm + base; int* key = A.key + base;
+  // Working set of the pool: translations, rotated x axes and their norms, the x-sorted order, the seed
+  // state and the sort arrays.  Pools of up to CL_SMEM_N hypotheses keep all of it in shared memory (the
+  // greedy rounds poll `state` of every earlier neighbour); larger pools work on the global arrays.
+  const bool sm = n <= CL_SMEM_N;
+  const double* an; const float* tr; const float* ax; const float* xs; const int* order; int ts, as, obase;
+  int* state; int* key; int* perm;
+  if (sm) {
+    double* d_an = (double*)cl_dyn;
+    float* d_tr = (float*)(d_an + CL_SMEM_N); float* d_ax = d_tr + 3 * CL_SMEM_N; float* d_xs = d_ax + 3 * CL_SMEM_N;
+    int* d_ord = (int*)(d_xs + CL_SMEM_N); state = d_ord + CL_SMEM_N; key = state + CL_SMEM_N; perm = key + CL_SMEM_N;
+    for (int i = t; i < n; i += 1024) {
+      const float* q = qt + (size_t)i * 8; const float* a = A.hyp_ax + (size_t)(base + i) * 4;
+      d_tr[3 * i] = q[4]; d_tr[3 * i + 1] = q[5]; d_tr[3 * i + 2] = q[6];
+      d_ax[3 * i] = a[0]; d_ax[3 * i + 1] = a[1]; d_ax[3 * i + 2] = a[2];
+      d_an[i] = A.hyp_an[base + i];
+      d_xs[i] = A.xs[base + i];
+      d_ord[i] = (int)A.order[base + i] - base;
+    }
+    an = d_an; tr = d_tr; ax = d_ax; xs = d_xs; order = d_ord; ts = 3; as = 3; obase = 0;
+  } else {
+    an = A.hyp_an + base; tr = qt + 4; ax = A.hyp_ax + (size_t)base * 4; xs = A.xs + base; order = (const int*)(A.order + base); ts = 8; as = 4; obase = base;
+    state = A.state + base; key = A.key + base; perm = A.perm + base;
+  }
+  int* size = A.size + base; int* seeds = A.seeds + base;
   const double rad = (double)A.rad;
   const float r2 = (float)(rad * rad);
   const double rr = rad * 1.0001 + 1e-6;
   for (int i = t; i < n; i += 1024) state[i] = (i == n - 1) ? 2 : 0;
   __syncthreads();
 #define CL_MARK(k) if (ty == 0 && t == 0) st->prof[k] = clock64();
+#define CL_NEIGH(i, j, dp) cl_neigh(tr + (size_t)(i) * ts, ax + (size_t)(i) * as, an[i], tr + (size_t)(j) * ts, ax + (size_t)(j) * as, an[j], r2, A.ang_cut, dp)
   CL_MARK(0)
   int rounds = 0;
   // ---- greedy seeding as parallel rounds ----
@@ -156,14 +181,14 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
     __syncthreads();
     for (int i = t; i < n; i += 1024) {
       if (((volatile int*)state)[i] != 0) continue;
-      int lo, hi; cl_window(xs, n, qt[(size_t)i * 8 + 4], rr, lo, hi);
+      int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
       bool found_seed = false, all_dec = true;
       for (int k = lo; k < hi; k++) {
-        int j = (int)order[k] - base;
+        int j = order[k] - obase;
         if (j >= i) continue;
         int sj = ((volatile int*)state)[j];
         if (sj == 2) continue;
-        if (cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, an[i], qt + (size_t)j * 8, ax + (size_t)j * 4, an[j], r2, A.ang_cut, nullptr)) {
+        if (CL_NEIGH(i, j, nullptr)) {
           if (sj == 1) { found_seed = true; break; }
           all_dec = false;
         }
@@ -200,21 +225,24 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   }
   const int K = s_K;
   if (t == 0) st->n_seeds[ty] = K;
-  for (int k = t; k < K; k += 1024) {
+  // cluster sizes: one warp per seed, the window split over its lanes
+  for (int k = warp; k < K; k += 32) {
     int i = seeds[k];
-    int lo, hi; cl_window(xs, n, qt[(size_t)i * 8 + 4], rr, lo, hi);
+    int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
     int cnt = 0;
-    for (int kk = lo; kk < hi; kk++) {
-      int j = (int)order[kk] - base;
-      if (cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, an[i], qt + (size_t)j * 8, ax + (size_t)j * 4, an[j], r2, A.ang_cut, nullptr)) cnt++;
+    for (int kk = lo + lane; kk < hi; kk += 32) {
+      int j = order[kk] - obase;
+      if (CL_NEIGH(i, j, nullptr)) cnt++;
     }
-    size[k] = cnt; key[k] = cnt; perm[k] = k;
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) { size[k] = cnt; key[k] = cnt; perm[k] = k; }
   }
   __syncthreads();
   CL_MARK(2)
   // ---- range_cluster: exchange sort by size ----
   block_exchange_sort(key, perm, K, s_sort);
   __syncthreads();
+  if (sm) { for (int k = t; k < K; k += 1024) { A.key[base + k] = key[k]; A.perm[base + k] = perm[k]; } }   // debug blobs read the global copies
   CL_MARK(3)
   // ---- adaptive cut-off walk (FCCF.cpp:1123-1229) ----
   if (t == 0) {
@@ -240,11 +268,11 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   for (int e = warp; e < E; e += 32) {
     int k = s_emit[e]; int i = seeds[k]; int m = size[k];
     if (m > CL_WSCR || m == 0) continue;
-    int lo, hi; cl_window(xs, n, qt[(size_t)i * 8 + 4], rr, lo, hi);
+    int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
     int cntw = 0;
     for (int k0 = lo; k0 < hi; k0 += 32) {
       int kk = k0 + lane; bool ok = false; float d = 0.f; int j = -1;
-      if (kk < hi) { j = (int)order[kk] - base; ok = cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, an[i], qt + (size_t)j * 8, ax + (size_t)j * 4, an[j], r2, A.ang_cut, &d); }
+      if (kk < hi) { j = order[kk] - obase; ok = CL_NEIGH(i, j, &d); }
       unsigned b = __ballot_sync(0xffffffffu, ok);
       if (ok) { int p = cntw + __popc(b & ((1u << lane) - 1u)); s_mem[warp][p] = j; s_md[warp][p] = d; }
       cntw += __popc(b);
@@ -278,12 +306,12 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
     int k = s_emit[e]; int i = seeds[k]; int m = size[k];
     if (m == 0) { if (t == 0) { float* o = centre + (size_t)e * 8; float nanv = CUDART_NAN_F; for (int u = 0; u < 8; u++) o[u] = nanv; } continue; }
     if (m <= CL_WSCR) continue;
-    int lo, hi; cl_window(xs, n, qt[(size_t)i * 8 + 4], rr, lo, hi);
+    int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
     if (t == 0) s_cnt = 0;
     __syncthreads();
     for (int k0 = lo; k0 < hi; k0 += 1024) {
       int kk = k0 + t; bool ok = false; float d = 0.f; int j = -1;
-      if (kk < hi) { j = (int)order[kk] - base; ok = cl_neigh(qt + (size_t)i * 8, ax + (size_t)i * 4, an[i], qt + (size_t)j * 8, ax + (size_t)j * 4, an[j], r2, A.ang_cut, &d); }
+      if (kk < hi) { j = order[kk] - obase; ok = CL_NEIGH(i, j, &d); }
       unsigned b = __ballot_sync(0xffffffffu, ok);
       if (lane == 0) s_w2[warp] = __popc(b);
       __syncthreads();
@@ -306,6 +334,8 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   CL_MARK(6)
 }
 
+void cluster_init_attributes() { cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES); }
+
 void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches) {
   const int G = b.G;
   std::vector<ClArgs> As(G); std::vector<SortJobs> abs_(G), bas_(G);
@@ -327,12 +357,12 @@ void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches) {
   }
   const ClArgs* dA = b.tab->put(As.data(), G);
   const SortJobs* dab = b.tab->put(abs_.data(), G); const SortJobs* dba = b.tab->put(bas_.data(), G);
-  cluster_prep_kernel<<<dim3((cap + 255) / 256, 1, G), 256, 0, s>>>(dA);
+  cluster_prep_kernel<<<dim3(grid_x((cap + 255) / 256, G), 1, G), 256, 0, s>>>(dA);
   if (launches) *launches += 1;
   // 34-bit keys: 6 passes of 6 bits (even pass count: result back in ckeyA / cidxA)
   launch_sort(s, dab, dba, 1, G, cap, 6, launches);
-  cluster_xs_kernel<<<dim3((cap + 255) / 256, 1, G), 256, 0, s>>>(dA);
-  cluster_kernel<<<dim3(3, 1, G), 1024, 0, s>>>(dA);
+  cluster_xs_kernel<<<dim3(grid_x((cap + 255) / 256, G), 1, G), 256, 0, s>>>(dA);
+  cluster_kernel<<<dim3(3, 1, G), 1024, CL_SMEM_BYTES, s>>>(dA);
   if (launches) *launches += 2;
 }
 

@@ -124,6 +124,16 @@ struct ArgTable {
   }
 };
 
+// grid.x of a launch whose CTAs stride over up to nb_cap blocks of work per job, when G lanes x njobs
+// jobs share the launch: the element counts are device-side, so grids are sized for capacity, and a
+// batched launch must not drown the GPU in CTAs that only find out that they have nothing to do.
+inline int grid_x(int nb_cap, int G, int njobs = 1) {
+  int lim = 4096 / (G * njobs);
+  if (lim < 8) lim = 8;
+  if (nb_cap < 1) nb_cap = 1;
+  return nb_cap < lim ? nb_cap : lim;
+}
+
 // Stable LSD radix sort of (key,value) pairs with a device-side element count and key width;
 // `np` passes of ceil(nbits/np) <= 8 bits.  Result ends in (kout,vout) of the last pass; the
 // launcher ping-pongs between the two buffer sets given in `a` and `b` (np even: result in a).
@@ -206,6 +216,7 @@ struct Batch {                // the lanes one batched launch sequence covers
 
 // copies calls[lane] into every lane's state block and resets the per-registration counters
 void launch_init_state(cudaStream_t s, const Batch& b, const CallArgs* d_calls, uint64_t* launches);
+void cluster_init_attributes();
 void score_init_attributes();   // one-time function attributes (not allowed inside a stream capture)
 // VoxelGrid stage `stage` (0: on raw clouds, 1: on the stage-0 output) for both clouds
 void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uint64_t* launches);

@@ -480,7 +480,8 @@ void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJo
   }
   const ScArgs* dA = tab.put(As.data(), G);
   const SortJobs* dab = tab.put(abs_.data(), G); const SortJobs* dba = tab.put(bas_.data(), G); const SegJobs* dsj = tab.put(sjs.data(), G);
-  int nb = (cap + 255) / 256; if (nb > 1184) nb = 1184; if (nb < 1) nb = 1;
+  int nb = (cap + 255) / 256; if (nb > 1184) nb = 1184;
+  nb = grid_x(nb, G);
   score_setup_kernel<<<dim3(1, 1, G), 32, 0, s>>>(dA);
   score_bbox_kernel<<<dim3(nb, 1, G), 256, 0, s>>>(dA);
   score_keys_kernel<<<dim3(nb, 1, G), 256, 0, s>>>(dA);
@@ -488,6 +489,7 @@ void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJo
   launch_sort(s, dab, dba, 1, G, cap, 4, launches);
   launch_segments(s, dsj, 1, G, cap, launches);
   int nbh = (cap_hash + 255) / 256; if (nbh > 1184) nbh = 1184;
+  nbh = grid_x(nbh, G);
   score_table_kernel<<<dim3(nbh, 1, G), 256, 0, s>>>(dA);
   score_insert_kernel<<<dim3(nb, 1, G), 256, 0, s>>>(dA);
   if (launches) *launches += 2;

@@ -29,97 +29,101 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restric
   const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
-  if ((int)blockIdx.x >= nact || pass >= rs_active(*j.nbits, np)) return;
+  if (pass >= rs_active(*j.nbits, np)) return;
   const int t = threadIdx.x;
   __shared__ u32 h[256];
   __shared__ int s_last;
-  h[t] = 0;
-  __syncthreads();
   const int bpp = rs_bpp(*j.nbits, np), shift = pass * bpp;
   const u32 mask = (1u << bpp) - 1u;
-  const int base = blockIdx.x * RS_TILE;
+  for (int tile = blockIdx.x; tile < nact; tile += gridDim.x) {
+    h[t] = 0;
+    __syncthreads();
+    const int base = tile * RS_TILE;
 #pragma unroll
-  for (int r = 0; r < RS_I; r++) {
-    int i = base + r * RS_T + t;
-    if (i < n) atomicAdd(&h[(u32)(j.kin[i] >> shift) & mask], 1u);
+    for (int r = 0; r < RS_I; r++) {
+      int i = base + r * RS_T + t;
+      if (i < n) atomicAdd(&h[(u32)(j.kin[i] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    j.hist[(size_t)tile * 256 + t] = h[t];
+    __threadfence();
+    __syncthreads();
+    if (t == 0) s_last = (atomicAdd(j.ticket, 1) == nact - 1);
+    __syncthreads();
+    if (!s_last) continue;
+    __threadfence();
+    // last tile: hist[b][d] -> exclusive prefix over tiles; row nact = exclusive prefix over digits
+    u32 run = 0;
+    for (int b = 0; b < nact; b++) {
+      u32 v = __ldcg(&j.hist[(size_t)b * 256 + t]);
+      j.hist[(size_t)b * 256 + t] = run;
+      run += v;
+    }
+    h[t] = run;
+    __syncthreads();
+    if (t == 0) {
+      u32 acc = 0;
+      for (int d = 0; d < 256; d++) { u32 v = h[d]; h[d] = acc; acc += v; }
+      *j.ticket = 0;
+    }
+    __syncthreads();
+    j.hist[(size_t)nact * 256 + t] = h[t];
+    __syncthreads();
   }
-  __syncthreads();
-  j.hist[(size_t)blockIdx.x * 256 + t] = h[t];
-  __threadfence();
-  __syncthreads();
-  if (t == 0) s_last = (atomicAdd(j.ticket, 1) == nact - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // last tile: hist[b][d] -> exclusive prefix over tiles; row nact = exclusive prefix over digits
-  u32 run = 0;
-  for (int b = 0; b < nact; b++) {
-    u32 v = __ldcg(&j.hist[(size_t)b * 256 + t]);
-    j.hist[(size_t)b * 256 + t] = run;
-    run += v;
-  }
-  h[t] = run;
-  __syncthreads();
-  if (t == 0) {
-    u32 acc = 0;
-    for (int d = 0; d < 256; d++) { u32 v = h[d]; h[d] = acc; acc += v; }
-    *j.ticket = 0;
-  }
-  __syncthreads();
-  j.hist[(size_t)nact * 256 + t] = h[t];
 }
 
 __global__ void __launch_bounds__(RS_T) rs_scatter_kernel(const SortJobs* __restrict__ JB, int pass, int np, int identity) {
   const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
-  if ((int)blockIdx.x >= nact || pass >= rs_active(*j.nbits, np)) return;
+  if (pass >= rs_active(*j.nbits, np)) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   __shared__ unsigned short cnt[RS_I * 8][256];
   __shared__ u32 gbase[256];
-  for (int k = t; k < RS_I * 8 * 256; k += RS_T) (&cnt[0][0])[k] = 0;
   const int bpp = rs_bpp(*j.nbits, np), shift = pass * bpp;
   const u32 mask = (1u << bpp) - 1u;
-  const int base = blockIdx.x * RS_TILE;
-  gbase[t] = j.hist[(size_t)blockIdx.x * 256 + t] + j.hist[(size_t)nact * 256 + t];
-  __syncthreads();
-  u64 key[RS_I]; u32 val[RS_I]; int dig[RS_I]; int rk[RS_I];
+  for (int tile = blockIdx.x; tile < nact; tile += gridDim.x) {
+    for (int k = t; k < RS_I * 8 * 256; k += RS_T) (&cnt[0][0])[k] = 0;
+    const int base = tile * RS_TILE;
+    gbase[t] = j.hist[(size_t)tile * 256 + t] + j.hist[(size_t)nact * 256 + t];
+    __syncthreads();
+    u64 key[RS_I]; u32 val[RS_I]; int dig[RS_I]; int rk[RS_I];
 #pragma unroll
-  for (int r = 0; r < RS_I; r++) {
-    int i = base + r * RS_T + t;
-    bool valid = i < n;
-    unsigned am = __ballot_sync(0xffffffffu, valid);
-    dig[r] = -1; rk[r] = 0; key[r] = 0; val[r] = 0;
-    if (valid) {
-      key[r] = j.kin[i];
-      val[r] = identity ? (u32)i : j.vin[i];
-      dig[r] = (int)((u32)(key[r] >> shift) & mask);
-      unsigned peers = __match_any_sync(am, dig[r]);
-      rk[r] = __popc(peers & ((1u << lane) - 1u));
-      if (lane == __ffs(peers) - 1) cnt[r * 8 + warp][dig[r]] = (unsigned short)__popc(peers);
+    for (int r = 0; r < RS_I; r++) {
+      int i = base + r * RS_T + t;
+      bool valid = i < n;
+      unsigned am = __ballot_sync(0xffffffffu, valid);
+      dig[r] = -1; rk[r] = 0; key[r] = 0; val[r] = 0;
+      if (valid) {
+        key[r] = j.kin[i];
+        val[r] = identity ? (u32)i : j.vin[i];
+        dig[r] = (int)((u32)(key[r] >> shift) & mask);
+        unsigned peers = __match_any_sync(am, dig[r]);
+        rk[r] = __popc(peers & ((1u << lane) - 1u));
+        if (lane == __ffs(peers) - 1) cnt[r * 8 + warp][dig[r]] = (unsigned short)__popc(peers);
+      }
     }
-  }
-  __syncthreads();
-  {
-    u32 run = 0;
+    __syncthreads();
+    {
+      u32 run = 0;
 #pragma unroll 8
-    for (int e = 0; e < RS_I * 8; e++) { u32 c = cnt[e][t]; cnt[e][t] = (unsigned short)run; run += c; }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RS_I; r++) {
-    if (dig[r] >= 0) {
-      u32 pos = gbase[dig[r]] + cnt[r * 8 + warp][dig[r]] + rk[r];
-      j.kout[pos] = key[r];
-      j.vout[pos] = val[r];
+      for (int e = 0; e < RS_I * 8; e++) { u32 c = cnt[e][t]; cnt[e][t] = (unsigned short)run; run += c; }
     }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_I; r++) {
+      if (dig[r] >= 0) {
+        u32 pos = gbase[dig[r]] + cnt[r * 8 + warp][dig[r]] + rk[r];
+        j.kout[pos] = key[r];
+        j.vout[pos] = val[r];
+      }
+    }
+    __syncthreads();
   }
 }
 
 void launch_sort(cudaStream_t s, const SortJobs* ab, const SortJobs* ba, int njobs, int G, int cap, int np, uint64_t* launches) {
-  int nb = (cap + RS_TILE - 1) / RS_TILE;
-  if (nb < 1) nb = 1;
-  dim3 grid(nb, njobs, G);
+  dim3 grid(grid_x((cap + RS_TILE - 1) / RS_TILE, G, njobs), njobs, G);
   for (int p = 0; p < np; p++) {
     const SortJobs* J = (p & 1) ? ba : ab;
     rs_hist_kernel<<<grid, RS_T, 0, s>>>(J, p, np);
@@ -139,75 +143,76 @@ __global__ void __launch_bounds__(RS_T) seg_count_kernel(const SegJobs* __restri
   const int nact = (n + RS_TILE - 1) / RS_TILE;
   const int t = threadIdx.x;
   if (nact == 0) { if (blockIdx.x == 0 && t == 0) { *j.nseg = 0; j.seg_start[0] = 0; } return; }
-  if ((int)blockIdx.x >= nact) return;
   __shared__ int s_cnt[RS_T / 32];
   __shared__ int s_last;
-  const int base = blockIdx.x * RS_TILE;
-  int c = 0;
-#pragma unroll
-  for (int r = 0; r < RS_I; r++) { int i = base + r * RS_T + t; if (i < n && seg_is_head(j.keys, i)) c++; }
-  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((t & 31) == 0) s_cnt[t >> 5] = c;
-  __syncthreads();
-  if (t == 0) {
-    int tot = 0;
-    for (int w = 0; w < RS_T / 32; w++) tot += s_cnt[w];
-    j.blk[blockIdx.x] = (u32)tot;
-    __threadfence();
-    s_last = (atomicAdd(j.ticket, 1) == nact - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // exclusive scan over the tile counts (chunks of RS_T with a carry)
   __shared__ u32 sc[RS_T];
   __shared__ u32 carry;
-  if (t == 0) carry = 0;
-  __syncthreads();
-  for (int b0 = 0; b0 < nact; b0 += RS_T) {
-    int b = b0 + t;
-    u32 v = (b < nact) ? __ldcg(&j.blk[b]) : 0u;
-    sc[t] = v;
+  for (int tile = blockIdx.x; tile < nact; tile += gridDim.x) {
+    const int base = tile * RS_TILE;
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < RS_I; r++) { int i = base + r * RS_T + t; if (i < n && seg_is_head(j.keys, i)) c++; }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((t & 31) == 0) s_cnt[t >> 5] = c;
     __syncthreads();
-    for (int o = 1; o < RS_T; o <<= 1) { u32 a = (t >= o) ? sc[t - o] : 0u; __syncthreads(); sc[t] += a; __syncthreads(); }
-    if (b < nact) j.blk[b] = carry + sc[t] - v;
+    if (t == 0) {
+      int tot = 0;
+      for (int w = 0; w < RS_T / 32; w++) tot += s_cnt[w];
+      j.blk[tile] = (u32)tot;
+      __threadfence();
+      s_last = (atomicAdd(j.ticket, 1) == nact - 1);
+    }
     __syncthreads();
-    if (t == RS_T - 1) carry += sc[t];
+    if (!s_last) continue;
+    __threadfence();
+    // exclusive scan over the tile counts (chunks of RS_T with a carry)
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nact; b0 += RS_T) {
+      int b = b0 + t;
+      u32 v = (b < nact) ? __ldcg(&j.blk[b]) : 0u;
+      sc[t] = v;
+      __syncthreads();
+      for (int o = 1; o < RS_T; o <<= 1) { u32 a = (t >= o) ? sc[t - o] : 0u; __syncthreads(); sc[t] += a; __syncthreads(); }
+      if (b < nact) j.blk[b] = carry + sc[t] - v;
+      __syncthreads();
+      if (t == RS_T - 1) carry += sc[t];
+      __syncthreads();
+    }
+    if (t == 0) { *j.nseg = (int)carry; j.seg_start[carry] = n; *j.ticket = 0; }
     __syncthreads();
   }
-  if (t == 0) { *j.nseg = (int)carry; j.seg_start[carry] = n; *j.ticket = 0; }
 }
 
 __global__ void __launch_bounds__(RS_T) seg_write_kernel(const SegJobs* __restrict__ JB) {
   const SegJob& j = JB[blockIdx.z].j[blockIdx.y];
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
-  if ((int)blockIdx.x >= nact) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   __shared__ int s_w[RS_T / 32];
   __shared__ int s_run;
-  if (t == 0) s_run = (int)j.blk[blockIdx.x];
-  __syncthreads();
-  const int base = blockIdx.x * RS_TILE;
-  for (int r = 0; r < RS_I; r++) {
-    int i = base + r * RS_T + t;
-    bool head = (i < n) && seg_is_head(j.keys, i);
-    unsigned b = __ballot_sync(0xffffffffu, head);
-    if (lane == 0) s_w[warp] = __popc(b);
+  for (int tile = blockIdx.x; tile < nact; tile += gridDim.x) {
+    if (t == 0) s_run = (int)j.blk[tile];
     __syncthreads();
-    int off = s_run;
-    for (int w = 0; w < warp; w++) off += s_w[w];
-    if (head) j.seg_start[off + __popc(b & ((1u << lane) - 1u))] = i;
-    __syncthreads();
-    if (t == 0) { int tot = 0; for (int w = 0; w < RS_T / 32; w++) tot += s_w[w]; s_run += tot; }
-    __syncthreads();
+    const int base = tile * RS_TILE;
+    for (int r = 0; r < RS_I; r++) {
+      int i = base + r * RS_T + t;
+      bool head = (i < n) && seg_is_head(j.keys, i);
+      unsigned b = __ballot_sync(0xffffffffu, head);
+      if (lane == 0) s_w[warp] = __popc(b);
+      __syncthreads();
+      int off = s_run;
+      for (int w = 0; w < warp; w++) off += s_w[w];
+      if (head) j.seg_start[off + __popc(b & ((1u << lane) - 1u))] = i;
+      __syncthreads();
+      if (t == 0) { int tot = 0; for (int w = 0; w < RS_T / 32; w++) tot += s_w[w]; s_run += tot; }
+      __syncthreads();
+    }
   }
 }
 
 void launch_segments(cudaStream_t s, const SegJobs* jobs, int njobs, int G, int cap, uint64_t* launches) {
-  int nb = (cap + RS_TILE - 1) / RS_TILE;
-  if (nb < 1) nb = 1;
-  dim3 grid(nb, njobs, G);
+  dim3 grid(grid_x((cap + RS_TILE - 1) / RS_TILE, G, njobs), njobs, G);
   seg_count_kernel<<<grid, RS_T, 0, s>>>(jobs);
   seg_write_kernel<<<grid, RS_T, 0, s>>>(jobs);
   if (launches) *launches += 2;

@@ -95,21 +95,25 @@ __global__ void __launch_bounds__(256) vg_keys_kernel(const VGArgs* __restrict__
   const int c = blockIdx.y;
   const VGState* st = A.st[c];
   const int n = st->n_in;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   const float* p = A.in[c] ? A.in[c] : A.call->raw[c];
-  float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
-  u64 key;
-  if (!(isfinite(x) && isfinite(y) && isfinite(z))) key = (u64)st->total;
-  else if (st->bail) key = (u64)i;
-  else {
-    float inv = st->inv;
-    int i0 = (int)(floorf(x * inv) - (float)st->minb[0]);
-    int i1 = (int)(floorf(y * inv) - (float)st->minb[1]);
-    int i2 = (int)(floorf(z * inv) - (float)st->minb[2]);
-    key = (u64)((long long)i0 + (long long)i1 * st->div[0] + (long long)i2 * st->div[0] * st->div[1]);
+  const float inv = st->inv;
+  const int bail = st->bail;
+  const float mb0 = (float)st->minb[0], mb1 = (float)st->minb[1], mb2 = (float)st->minb[2];
+  const long long d0 = st->div[0], d01 = st->div[0] * st->div[1];
+  const u64 total = (u64)st->total;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+    u64 key;
+    if (!(isfinite(x) && isfinite(y) && isfinite(z))) key = total;
+    else if (bail) key = (u64)i;
+    else {
+      int i0 = (int)(floorf(x * inv) - mb0);
+      int i1 = (int)(floorf(y * inv) - mb1);
+      int i2 = (int)(floorf(z * inv) - mb2);
+      key = (u64)((long long)i0 + (long long)i1 * d0 + (long long)i2 * d01);
+    }
+    A.keys[c][i] = key;
   }
-  A.keys[c][i] = key;
 }
 
 struct VGOut {
@@ -130,20 +134,20 @@ __global__ void __launch_bounds__(128) vg_centroid_kernel(const VGOut* __restric
   const int c = blockIdx.y;
   VGState* st = A.st[c];
   const int nseg = st->n_out;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nseg) return;
-  const int b = A.seg_start[c][s], e = A.seg_start[c][s + 1];
   const float* p = A.in[c] ? A.in[c] : A.call->raw[c];
   const u32* idx = A.idx[c];
-  float sx = 0.f, sy = 0.f, sz = 0.f;
-  for (int k = b; k < e; k++) {
-    u32 i = idx[k];
-    sx += p[3 * i]; sy += p[3 * i + 1]; sz += p[3 * i + 2];
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += gridDim.x * blockDim.x) {
+    const int b = A.seg_start[c][s], e = A.seg_start[c][s + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int k = b; k < e; k++) {
+      u32 i = idx[k];
+      sx += p[3 * i]; sy += p[3 * i + 1]; sz += p[3 * i + 2];
+    }
+    float fn = (float)(e - b);
+    A.out[c][3 * s] = sx / fn; A.out[c][3 * s + 1] = sy / fn; A.out[c][3 * s + 2] = sz / fn;
+    A.cell[c][s] = (long long)A.keys[c][b];
+    A.cnt[c][s] = e - b;
   }
-  float fn = (float)(e - b);
-  A.out[c][3 * s] = sx / fn; A.out[c][3 * s + 1] = sy / fn; A.out[c][3 * s + 2] = sz / fn;
-  A.cell[c][s] = (long long)A.keys[c][b];
-  A.cnt[c][s] = e - b;
 }
 
 struct InitArgs { PipeState* st; };
@@ -209,13 +213,12 @@ void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uin
   const SortJobs* dab = b.tab->put(abs_.data(), G); const SortJobs* dba = b.tab->put(bas_.data(), G); const SegJobs* dsj = b.tab->put(sjs.data(), G);
   int nb_mm = (cap + 256 * 8 - 1) / (256 * 8);
   if (nb_mm > 592) nb_mm = 592;
-  if (nb_mm < 1) nb_mm = 1;
-  vg_minmax_kernel<<<dim3(nb_mm, ncloud, G), 256, 0, s>>>(dA);
-  vg_keys_kernel<<<dim3((cap + 255) / 256, ncloud, G), 256, 0, s>>>(dA);
+  vg_minmax_kernel<<<dim3(grid_x(nb_mm, G, ncloud), ncloud, G), 256, 0, s>>>(dA);
+  vg_keys_kernel<<<dim3(grid_x((cap + 255) / 256, G, ncloud), ncloud, G), 256, 0, s>>>(dA);
   if (launches) *launches += 2;
   launch_sort(s, dab, dba, ncloud, G, cap, 4, launches);   // result back in keyA / idxA
   launch_segments(s, dsj, ncloud, G, cap, launches);
-  vg_centroid_kernel<<<dim3((cap + 127) / 128, ncloud, G), 128, 0, s>>>(dO);
+  vg_centroid_kernel<<<dim3(grid_x((cap + 127) / 128, G, ncloud), ncloud, G), 128, 0, s>>>(dO);
   if (launches) *launches += 1;
 }
 
