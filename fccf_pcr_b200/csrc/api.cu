@@ -52,8 +52,8 @@ struct GraphRec { int G = 0; cudaGraphExec_t exec = nullptr; int launches = 0; }
 // pipeline is launched once with grid.z = G and serves G independent registrations (most stages of one
 // registration are single-CTA, order-dependent greedy loops, so G of them fill the other SMs), and the
 // whole sequence is one CUDA graph per G.  A context owns group 0 (single-pair and stage entry points
-// use its lane 0) and a second group for fccf_register_batch*, which double-buffers: while one group
-// computes, the other receives its clouds.
+// use its lane 0) and up to three more groups for fccf_register_batch*, which rotates through them:
+// while some groups compute, the next one receives its clouds (FCCF_GROUPS overrides the count).
 struct Group {
   cudaStream_t stream = nullptr;
   std::vector<Lane> lanes;
@@ -504,7 +504,7 @@ static int register_one(fccf_ctx* ctx, const float* src, size_t n_src, const flo
 }
 
 // Batch of independent pairs: chunks of up to max_lanes pairs, each chunk one batched launch sequence
-// on a group; two groups alternate so that the H2D of one chunk overlaps the compute of the other.
+// on a group; the groups rotate so that the H2D of one chunk overlaps the compute of the others.
 // timing: device times summed over the chunks (each covers its whole chunk), total_ms = device time
 // of the whole batch, stage_ms[7] = host wall clock.
 static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, const size_t* n_src, const float* const* tar, const size_t* n_tar,
@@ -516,7 +516,7 @@ static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, co
   if (n_pairs == 0) { if (timing) *timing = acc; return FCCF_OK; }
   const int nl = std::min(ctx->max_lanes, n_pairs);
   const int nchunks = (n_pairs + nl - 1) / nl;
-  int max_groups = 2;
+  int max_groups = 4;
   if (const char* e = getenv("FCCF_GROUPS")) { max_groups = atoi(e); if (max_groups < 1) max_groups = 1; if (max_groups > 8) max_groups = 8; }
   const int ngroups = std::min(nchunks, max_groups);
   size_t nmax = 0;

@@ -383,7 +383,7 @@ void launch_quick_verify(cudaStream_t s, const Batch& b, uint64_t* launches) {
   }
   const QvArgs* dA = b.tab->put(As.data(), G);
   static int occ = -1;
-  if (occ < 0) { const char* e = getenv("FCCF_QV_OCC"); occ = e ? atoi(e) : 3; }
+  if (occ < 0) { const char* e = getenv("FCCF_QV_OCC"); occ = e ? atoi(e) : 4; }
   dim3 grid((3 * FCCF_MAXCENTRE + 3) / 4, 1, G);
   if (occ <= 2) quick_verify_kernel<2><<<grid, 128, 0, s>>>(dA);
   else if (occ == 3) quick_verify_kernel<3><<<grid, 128, 0, s>>>(dA);
