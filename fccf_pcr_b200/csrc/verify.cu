@@ -9,6 +9,12 @@
 // [J; sqrt(D)] y = [r; 0]; every "sum over rows" is one xor-butterfly over the warp (all lanes end
 // with the same bits), the Householder QR runs column by column on those register rows.  FP64
 // throughout — this is the FP64-pipe stage of the path.
+//
+// In the pipeline the refinement is LAZY: the ranking score is the pre-refinement one (Q16) and only
+// the fine_verify_number best centres per type are read again, so quick_verify_kernel associates and
+// scores every centre, rank_top_kernel ranks them, and refine_top_kernel runs the refinement for the
+// <= 3 x 4 selected ones — instead of ~150 solves of up to 50 iterations per registration.  The
+// stand-alone entry point fccf_quick_verify still refines every hypothesis it is given.
 #include "fccf_dev.cuh"
 #include "fccf_internal.h"
 #include <cstdlib>
@@ -242,6 +248,9 @@ __device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
 }
 
 // quick_verify for one hypothesis by one warp.  planes: stride 8 floats (c, n, size, -).
+// REFINE=false: association and score only (T is left as given); iters_out gets -2 where a refinement
+// would have run.
+template <bool REFINE>
 __device__ float quick_verify_warp(float T[16], const float* pl1, int F1, const float* pl2, int F2, float ang_cut, float dist_thr,
                                    float required, int lane, int* npair_out, int* pairs_out, int* iters_out) {
   // integer-truncating size sums (FCCF.cpp:693,707)
@@ -294,7 +303,8 @@ __device__ float quick_verify_warp(float T[16], const float* pl1, int F1, const 
   if (pairs_out && R.active && !(lane & 1)) { pairs_out[2 * k] = src; pairs_out[2 * k + 1] = bsel; }
   if (npair_out && lane == 0) *npair_out = np;
   int iters = -1;
-  if ((float)np >= required) {
+  if (!REFINE && (float)np >= required) iters = -2;
+  if (REFINE && (float)np >= required) {
     double x[7];
     iters = lm_refine_warp(R, lane, x);
     q4 q; q.w = (float)x[3]; q.x = (float)x[0]; q.y = (float)x[1]; q.z = (float)x[2];   // FCCF.cpp:231-236
@@ -324,8 +334,13 @@ struct QvArgs {
   float ang_cut, dist_thr, required, fine_number;   // ang_cut: cosine cut of quick_verify_angel_threshold (strict <)
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) quick_verify_kernel(const QvArgs* __restrict__ AB) {
+// Plane association and score of every cluster centre (FCCF.cpp:1468-1492 without the refinement): one
+// warp per centre.  The score that ranks the centres is computed from the pairs found BEFORE the
+// refinement (Q16), and only the fine_verify_number best centres per type are ever read again
+// (FCCF.cpp:1499-1544), so the Levenberg-Marquardt refinement — by far the most expensive part of
+// quick_verify — runs only for those (refine_top_kernel), with bit-identical results for everything the
+// path consumes.
+__global__ void __launch_bounds__(128) quick_verify_kernel(const QvArgs* __restrict__ AB) {
   const QvArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int lane = threadIdx.x & 31;
@@ -336,17 +351,17 @@ __global__ void __launch_bounds__(128, MINB) quick_verify_kernel(const QvArgs* _
   q4 q; q.w = c[0]; q.x = c[1]; q.y = c[2]; q.z = c[3];
   m3 Rm = quat_to_matrix(q);   // FCCF.cpp:1470-1489
   float T[16] = {Rm.m[0][0], Rm.m[0][1], Rm.m[0][2], c[4], Rm.m[1][0], Rm.m[1][1], Rm.m[1][2], c[5], Rm.m[2][0], Rm.m[2][1], Rm.m[2][2], c[6], 0.f, 0.f, 0.f, 1.f};
-  float s = quick_verify_warp(T, &st->ft[0].plane[0][0], st->ft[0].F, &st->ft[1].plane[0][0], st->ft[1].F, A.ang_cut, A.dist_thr, A.required, lane,
-                              A.qv_npair + wid, A.qv_pairs + (size_t)wid * 32, A.qv_iters + wid);
+  float s = quick_verify_warp<false>(T, &st->ft[0].plane[0][0], st->ft[0].F, &st->ft[1].plane[0][0], st->ft[1].F, A.ang_cut, A.dist_thr, A.required, lane,
+                                     A.qv_npair + wid, A.qv_pairs + (size_t)wid * 32, A.qv_iters + wid);
   if (lane < 16) A.qv_T[(size_t)wid * 16 + lane] = T[lane];
   if (lane == 0) A.qv_score[wid] = s;
 }
 
-// score_range + top-k (FCCF.cpp:1494-1544): one CTA per type
+// score_range + top-k (FCCF.cpp:1494-1544): one CTA per type ranks the centres
 __global__ void __launch_bounds__(256) rank_top_kernel(const QvArgs* __restrict__ AB) {
   const QvArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
-  const int t = threadIdx.x, lane = t & 31, ty = blockIdx.x;
+  const int t = threadIdx.x, ty = blockIdx.x;
   __shared__ float s_key[FCCF_MAXCENTRE];
   __shared__ int s_perm[FCCF_MAXCENTRE];
   __shared__ unsigned long long s_sort[40];
@@ -361,14 +376,27 @@ __global__ void __launch_bounds__(256) rank_top_kernel(const QvArgs* __restrict_
   if (amax > FCCF_TOPK) amax = FCCF_TOPK;
   int nt = C < amax ? C : amax;
   for (int k = t; k < C; k += 256) A.rank_perm[ty * FCCF_MAXCENTRE + k] = s_perm[k];
-  if (t < 32) {
-    for (int k = 0; k < nt; k++) {
-      int ci = s_perm[k];
-      if (lane < 16) A.top_T[((size_t)ty * FCCF_TOPK + k) * 16 + lane] = A.qv_T[((size_t)ty * FCCF_MAXCENTRE + ci) * 16 + lane];
-      if (lane == 0) { A.top_s1[ty * FCCF_TOPK + k] = s_key[k]; A.top_centre[ty * FCCF_TOPK + k] = ci; }
-    }
-    if (lane == 0) st->n_top[ty] = nt;
-  }
+  if (t < nt) { A.top_s1[ty * FCCF_TOPK + t] = s_key[t]; A.top_centre[ty * FCCF_TOPK + t] = s_perm[t]; }
+  if (t == 0) st->n_top[ty] = nt;
+}
+
+// quick_verify with the Ceres refinement for the selected centres: one warp per (type, rank)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) refine_top_kernel(const QvArgs* __restrict__ AB) {
+  const QvArgs& A = AB[blockIdx.z];
+  PipeState* st = A.st;
+  const int lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int ty = slot / FCCF_TOPK, k = slot - ty * FCCF_TOPK;
+  if (ty >= 3 || k >= st->n_top[ty]) return;
+  const int wid = ty * FCCF_MAXCENTRE + A.top_centre[slot];
+  const float* c = A.centre + (size_t)wid * 8;
+  q4 q; q.w = c[0]; q.x = c[1]; q.y = c[2]; q.z = c[3];
+  m3 Rm = quat_to_matrix(q);
+  float T[16] = {Rm.m[0][0], Rm.m[0][1], Rm.m[0][2], c[4], Rm.m[1][0], Rm.m[1][1], Rm.m[1][2], c[5], Rm.m[2][0], Rm.m[2][1], Rm.m[2][2], c[6], 0.f, 0.f, 0.f, 1.f};
+  quick_verify_warp<true>(T, &st->ft[0].plane[0][0], st->ft[0].F, &st->ft[1].plane[0][0], st->ft[1].F, A.ang_cut, A.dist_thr, A.required, lane,
+                          nullptr, nullptr, A.qv_iters + wid);
+  if (lane < 16) { A.top_T[(size_t)slot * 16 + lane] = T[lane]; A.qv_T[(size_t)wid * 16 + lane] = T[lane]; }
 }
 
 void launch_quick_verify(cudaStream_t s, const Batch& b, uint64_t* launches) {
@@ -383,13 +411,14 @@ void launch_quick_verify(cudaStream_t s, const Batch& b, uint64_t* launches) {
   }
   const QvArgs* dA = b.tab->put(As.data(), G);
   static int occ = -1;
-  if (occ < 0) { const char* e = getenv("FCCF_QV_OCC"); occ = e ? atoi(e) : 4; }
-  dim3 grid((3 * FCCF_MAXCENTRE + 3) / 4, 1, G);
-  if (occ <= 2) quick_verify_kernel<2><<<grid, 128, 0, s>>>(dA);
-  else if (occ == 3) quick_verify_kernel<3><<<grid, 128, 0, s>>>(dA);
-  else quick_verify_kernel<4><<<grid, 128, 0, s>>>(dA);
+  if (occ < 0) { const char* e = getenv("FCCF_QV_OCC"); occ = e ? atoi(e) : 2; }
+  quick_verify_kernel<<<dim3((3 * FCCF_MAXCENTRE + 3) / 4, 1, G), 128, 0, s>>>(dA);
   rank_top_kernel<<<dim3(3, 1, G), 256, 0, s>>>(dA);
-  if (launches) *launches += 2;
+  dim3 grid((3 * FCCF_TOPK + 3) / 4, 1, G);
+  if (occ <= 2) refine_top_kernel<2><<<grid, 128, 0, s>>>(dA);
+  else if (occ == 3) refine_top_kernel<3><<<grid, 128, 0, s>>>(dA);
+  else refine_top_kernel<4><<<grid, 128, 0, s>>>(dA);
+  if (launches) *launches += 3;
 }
 
 // stand-alone: n hypotheses (row-major 4x4, updated in place) against two plane tables (F x 8)
@@ -400,7 +429,7 @@ __global__ void __launch_bounds__(128) quick_verify_list_kernel(const __grid_con
   if (wid >= A.n) return;
   float T[16];
   for (int i = 0; i < 16; i++) T[i] = A.T[(size_t)wid * 16 + i];
-  float s = quick_verify_warp(T, A.pl1, A.f1, A.pl2, A.f2, A.ang_cut, A.dist_thr, A.required, lane, A.npair ? A.npair + wid : nullptr,
+  float s = quick_verify_warp<true>(T, A.pl1, A.f1, A.pl2, A.f2, A.ang_cut, A.dist_thr, A.required, lane, A.npair ? A.npair + wid : nullptr,
                               A.pairs ? A.pairs + (size_t)wid * 32 : nullptr, A.iters ? A.iters + wid : nullptr);
   if (lane < 16) A.T[(size_t)wid * 16 + lane] = T[lane];
   if (lane == 0) A.score[wid] = s;

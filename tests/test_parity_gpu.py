@@ -134,11 +134,20 @@ def test_hypotheses_clusters_and_scores(ctx, runs, case):
         a, b = ctx.blob("top_T%d" % t).reshape(-1, 4, 4), o.blob("top_T%d" % t).reshape(-1, 4, 4)
         for Ta, Tb in zip(a, b):
             assert scenes.rotation_error_deg(Ta, Tb) <= 0.01 and scenes.translation_error(Ta, Tb) <= 1e-3
-        # every refined cluster centre: the Levenberg-Marquardt trajectories are FP64 on both sides but
-        # libm (sin/cos/pow) differs in the last ulp, which ill-conditioned (wrong) hypotheses amplify
+        # The library refines only the centres that are read again (the fine_verify_number best per type by
+        # the pre-refinement score, FCCF.cpp:1499-1544); the others keep their unrefined matrix and
+        # qv_iters == -2.  For the refined ones qv_T is the oracle's refined matrix, for the rest the
+        # oracle's centre before refinement is not kept, so only the selected ones are compared.
         a, b = ctx.blob("qv_T%d" % t).reshape(-1, 4, 4), o.blob("qv_T%d" % t).reshape(-1, 4, 4)
-        ok = [scenes.rotation_error_deg(Ta, Tb) <= 0.01 and scenes.translation_error(Ta, Tb) <= 1e-3 for Ta, Tb in zip(a, b)]
-        assert len(ok) == 0 or sum(ok) >= 0.9 * len(ok), "type %d: only %d of %d refined centres agree" % (t, sum(ok), len(ok))
+        sel = ctx.blob("top_centre%d" % t)
+        np.testing.assert_array_equal(sel, o.blob("top_centre%d" % t))
+        it_g, it_o = ctx.blob("qv_iters%d" % t), o.blob("qv_iters%d" % t)
+        for ci in range(len(a)):
+            if ci in sel:
+                assert scenes.rotation_error_deg(a[ci], b[ci]) <= 0.01 and scenes.translation_error(a[ci], b[ci]) <= 1e-3
+                assert (it_g[ci] >= 0) == (it_o[ci] >= 0)
+            else:
+                assert it_g[ci] in (-1, -2) and (it_g[ci] == -2) == (it_o[ci] >= 0)
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%d-seed%d-leaf%g" % c)
