@@ -206,6 +206,7 @@ static int ensure_capacity(fccf_ctx* ctx, Group* g, int li, size_t n0, size_t n1
   add(8 * ch); add(8 * ch); add(4 * ch); add(4 * ch); add(nbh * 1024);
   for (int k = 0; k < 5; k++) add(4 * ch);
   add(8 * ch); add(8 * ch);
+  add(4 * (size_t)cluster_nbl_ints()); add(4 * (size_t)cluster_deg_ints());
   size_t nc = 3 * FCCF_MAXCENTRE, ntop = 3 * FCCF_TOPK;
   add(nc * 32); add(nc * 64); add(nc * 4); add(nc * 4); add(nc * 128); add(nc * 4); add(nc * 4);
   add(ntop * 64); add(ntop * 4); add(ntop * 4); add(ntop * 4);
@@ -221,6 +222,7 @@ static int ensure_capacity(fccf_ctx* ctx, Group* g, int li, size_t n0, size_t n1
   h.ckeyA = a.take<u64>(ch); h.ckeyB = a.take<u64>(ch); h.cidxA = a.take<u32>(ch); h.cidxB = a.take<u32>(ch); h.chist = a.take<u32>(nbh * 256);
   h.c_state = a.take<int>(ch); h.c_size = a.take<int>(ch); h.c_seeds = a.take<int>(ch); h.c_perm = a.take<int>(ch); h.c_key = a.take<int>(ch);
   h.c_members = a.take<int>(2 * ch); h.c_mdist = a.take<float>(2 * ch);
+  h.c_nbl = a.take<int>((size_t)cluster_nbl_ints()); h.c_deg = a.take<int>((size_t)cluster_deg_ints());
   h.centre = a.take<float>(nc * 8); h.qv_T = a.take<float>(nc * 16); h.qv_score = a.take<float>(nc); h.qv_npair = a.take<int>(nc);
   h.qv_pairs = a.take<int>(nc * 32); h.qv_iters = a.take<int>(nc); h.rank_perm = a.take<int>(nc);
   h.top_T = a.take<float>(ntop * 16); h.top_s1 = a.take<float>(ntop); h.top_s2 = a.take<float>(ntop); h.top_centre = a.take<int>(ntop);
@@ -515,32 +517,42 @@ static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, co
   fccf_timing acc; memset(&acc, 0, sizeof acc);
   if (n_pairs == 0) { if (timing) *timing = acc; return FCCF_OK; }
   const int nl = std::min(ctx->max_lanes, n_pairs);
-  const int nchunks = (n_pairs + nl - 1) / nl;
+  // Chunk sizes.  Host inputs: the copies of a chunk are what the next launch sequence waits for, and the
+  // compute of the LAST chunk is the only part of the batch that no copy overlaps, so the tail tapers
+  // (nl, ..., nl, nl/2, nl/4, nl/4).  Device-resident inputs: full chunks.
+  std::vector<int> chunk;
+  for (int rem = n_pairs; rem > 0;) {
+    int c = std::min(nl, rem);
+    if (host_in && nl >= 16 && !getenv("FCCF_NO_TAPER")) c = std::min(nl, std::max(nl / 4, rem / 2));
+    if (c > rem) c = rem;
+    chunk.push_back(c); rem -= c;
+  }
+  const int nchunks = (int)chunk.size();
   int max_groups = 4;
   if (const char* e = getenv("FCCF_GROUPS")) { max_groups = atoi(e); if (max_groups < 1) max_groups = 1; if (max_groups > 8) max_groups = 8; }
   const int ngroups = std::min(nchunks, max_groups);
   size_t nmax = 0;
   for (int b = 0; b < n_pairs; b++) { if ((!src[b] && n_src[b]) || (!tar[b] && n_tar[b])) { ctx->err = "bad argument"; return FCCF_ERR_ARG; } nmax = std::max(nmax, std::max(n_src[b], n_tar[b])); }
   while ((int)ctx->groups.size() < ngroups) { Group* g = nullptr; int rc = group_create(ctx, &g); if (rc) return rc; ctx->groups.push_back(g); }
-  for (int gi = 0; gi < ngroups; gi++) {
-    int used = std::min(nl, n_pairs - gi * nl);
-    for (int l = 0; l < used; l++) { int rc = ensure_capacity(ctx, ctx->groups[gi], l, nmax, nmax); if (rc) return rc; }
-  }
+  for (int k = 0; k < nchunks; k++)
+    for (int l = 0; l < chunk[k]; l++) { int rc = ensure_capacity(ctx, ctx->groups[k % ngroups], l, nmax, nmax); if (rc) return rc; }
   // device time of the whole batch: an event on group 0's stream before the first enqueue, and one
-  // after it has waited for the last sequence of the other group
+  // after it has waited for the last sequence of the other groups
   Group* Z = ctx->groups[0];
   auto t0 = std::chrono::steady_clock::now();
   CK(cudaEventRecord(Z->sev[6], Z->stream));
   int worst = FCCF_OK;
   float enq_ms = 0.f;
+  int p0 = 0;
   for (int k = 0; k < nchunks; k++) {
     Group* g = ctx->groups[k % ngroups];
     if (g->busy) { int rc = group_finish(ctx, g, T_out, &acc); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc; if (rc) worst = rc; }
-    const int p0 = k * nl, G = std::min(nl, n_pairs - p0);
+    const int G = chunk[k];
     auto te0 = std::chrono::steady_clock::now();
     int rc = group_enqueue(ctx, g, G, p0, src + p0, n_src + p0, tar + p0, n_tar + p0, leaf, host_in);
     enq_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - te0).count();
     if (rc) return rc;
+    p0 += G;
   }
   if (getenv("FCCF_DEBUG_TIMING")) fprintf(stderr, "[fccf] batch of %d in %d chunk(s): host enqueue %.3f ms total\n", n_pairs, nchunks, enq_ms);
   for (int gi = 1; gi < ngroups; gi++) if (ctx->groups[gi]->busy) CK(cudaStreamWaitEvent(Z->stream, ctx->groups[gi]->ev[4], 0));

@@ -31,6 +31,7 @@ struct ClArgs {
   float thr_n, ang_cut, rad, sel_num;   // ang_cut: cosine cut of cluster_angel_threshold (strict <)
   int* nbits;                       // device word: key width for the sort
   int cap_hyp;
+  int* nbl; int* deg;               // 3 x CL_SMEM_N x CL_NB neighbour lists and 3 x CL_SMEM_N neighbour counts (shared-memory pools)
 };
 
 __global__ void __launch_bounds__(256) cluster_prep_kernel(const ClArgs* __restrict__ AB) {
@@ -69,6 +70,14 @@ __device__ __forceinline__ bool cl_neigh(const float* ti, const float* ai, doubl
   float d = 0.f; d += d0 * d0; d += d1 * d1; d += d2 * d2;    // flann::L2_Simple
   if (!(d < r2)) return false;
   if (dist) *dist = d;
+  return angle_lt(normal_cos_n(ai[0], ai[1], ai[2], ni, aj[0], aj[1], aj[2], nj), ang_cut);   // compute_normal_angel(...) < 2 degrees (FCCF.cpp:1110)
+}
+__device__ __forceinline__ float cl_dist2(const float* ti, const float* tj) {
+  float d0 = ti[0] - tj[0], d1 = ti[1] - tj[1], d2 = ti[2] - tj[2];
+  float d = 0.f; d += d0 * d0; d += d1 * d1; d += d2 * d2;    // flann::L2_Simple
+  return d;
+}
+__device__ __forceinline__ bool cl_angle_ok(const float* ai, double ni, const float* aj, double nj, float ang_cut) {
   return angle_lt(normal_cos_n(ai[0], ai[1], ai[2], ni, aj[0], aj[1], aj[2], nj), ang_cut);   // compute_normal_angel(...) < 2 degrees (FCCF.cpp:1110)
 }
 __device__ __forceinline__ void cl_window(const float* xs, int n, float x, double rr, int& lo, int& hi) {
@@ -112,6 +121,8 @@ __device__ void cl_emit_centre(const float* qt, const int* mem, int m, float* ou
   }
 }
 
+#define CL_NB 24               // neighbours listed per hypothesis
+#define CL_CAND 64             // radius candidates collected per hypothesis before the angle test
 #define CL_SMEM_N 3072        // pools up to this many hypotheses are clustered out of shared memory
 #define CL_SMEM_BYTES (CL_SMEM_N * 52)
 extern __shared__ __align__(16) unsigned char cl_dyn[];
@@ -175,27 +186,95 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
 #define CL_NEIGH(i, j, dp) cl_neigh(tr + (size_t)(i) * ts, ax + (size_t)(i) * as, an[i], tr + (size_t)(j) * ts, ax + (size_t)(j) * as, an[j], r2, A.ang_cut, dp)
   CL_MARK(0)
   int rounds = 0;
+  // ---- neighbour lists (shared-memory pools) ----
+  // Every thread finds ALL neighbours of its (<= 3) hypotheses once: a cheap float pass over the x-window
+  // collects the candidates inside the radius, then the FP64 angle test runs on the compacted candidates
+  // (so that the lanes of a warp do it together instead of diverging on ~5 % of the window).  Lists of up
+  // to CL_NB neighbours are kept (nbl), the count always (deg; bit 30: no list); the seeding rounds, the
+  // cluster sizes and the centre averaging below read them instead of re-scanning windows.
+  int* nbl = A.nbl + (size_t)ty * CL_SMEM_N * CL_NB; int* deg = A.deg + (size_t)ty * CL_SMEM_N;
+  if (sm) {
+#pragma unroll 1
+    for (int u = 0; u < 3; u++) {
+      const int i = t + u * 1024;
+      if (i >= n) continue;
+      int lo, hi; cl_window(xs, n, tr[(size_t)i * 3], rr, lo, hi);
+      const float ti[3] = {tr[(size_t)i * 3], tr[(size_t)i * 3 + 1], tr[(size_t)i * 3 + 2]};
+      int cand[CL_CAND]; int c = 0;
+      for (int k = lo; k < hi; k++) {
+        int j = order[k];
+        if (cl_dist2(ti, tr + (size_t)j * 3) < r2) { if (c < CL_CAND) cand[c] = j; c++; }
+      }
+      int m = 0; bool listed = c <= CL_CAND;
+      if (listed) {
+        for (int q = 0; q < c; q++) {
+          int j = cand[q];
+          if (cl_angle_ok(ax + (size_t)i * 3, an[i], ax + (size_t)j * 3, an[j], A.ang_cut)) { if (m < CL_NB) nbl[(size_t)i * CL_NB + m] = j; m++; }
+        }
+        listed = m <= CL_NB;
+      } else {
+        for (int k = lo; k < hi; k++) { int j = order[k]; if (CL_NEIGH(i, j, nullptr)) m++; }
+      }
+      deg[i] = listed ? m : (m | 0x40000000);
+    }
+    __syncthreads();
+  }
   // ---- greedy seeding as parallel rounds ----
+  // A hypothesis is a seed iff none of its EARLIER neighbours is one (FCCF.cpp:1084-1121 in index order).
   while (true) {
     if (t == 0) s_flag = 0;
     __syncthreads();
-    for (int i = t; i < n; i += 1024) {
-      if (((volatile int*)state)[i] != 0) continue;
-      int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
-      bool found_seed = false, all_dec = true;
-      for (int k = lo; k < hi; k++) {
-        int j = order[k] - obase;
-        if (j >= i) continue;
-        int sj = ((volatile int*)state)[j];
-        if (sj == 2) continue;
-        if (CL_NEIGH(i, j, nullptr)) {
-          if (sj == 1) { found_seed = true; break; }
-          all_dec = false;
+    if (sm) {
+#pragma unroll 1
+      for (int u = 0; u < 3; u++) {
+        const int i = t + u * 1024;
+        if (i >= n || ((volatile int*)state)[i] != 0) continue;
+        bool found_seed = false, all_dec = true;
+        const int dg = deg[i];
+        if (!(dg & 0x40000000)) {
+          for (int c = 0; c < dg; c++) {
+            int j = nbl[(size_t)i * CL_NB + c];
+            if (j >= i) continue;
+            int sj = ((volatile int*)state)[j];
+            if (sj == 1) { found_seed = true; break; }
+            if (sj == 0) all_dec = false;
+          }
+        } else {
+          int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
+          for (int k = lo; k < hi; k++) {
+            int j = order[k] - obase;
+            if (j >= i) continue;
+            int sj = ((volatile int*)state)[j];
+            if (sj == 2) continue;
+            if (CL_NEIGH(i, j, nullptr)) {
+              if (sj == 1) { found_seed = true; break; }
+              all_dec = false;
+            }
+          }
         }
+        if (found_seed) state[i] = 2;
+        else if (all_dec) state[i] = 1;
+        else s_flag = 1;
       }
-      if (found_seed) state[i] = 2;
-      else if (all_dec) state[i] = 1;
-      else s_flag = 1;
+    } else {
+      for (int i = t; i < n; i += 1024) {
+        if (((volatile int*)state)[i] != 0) continue;
+        int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
+        bool found_seed = false, all_dec = true;
+        for (int k = lo; k < hi; k++) {
+          int j = order[k] - obase;
+          if (j >= i) continue;
+          int sj = ((volatile int*)state)[j];
+          if (sj == 2) continue;
+          if (CL_NEIGH(i, j, nullptr)) {
+            if (sj == 1) { found_seed = true; break; }
+            all_dec = false;
+          }
+        }
+        if (found_seed) state[i] = 2;
+        else if (all_dec) state[i] = 1;
+        else s_flag = 1;
+      }
     }
     __syncthreads();
     rounds++;
@@ -225,7 +304,11 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   }
   const int K = s_K;
   if (t == 0) st->n_seeds[ty] = K;
-  // cluster sizes: one warp per seed, the window split over its lanes
+  // cluster sizes: the neighbour count of the seed (shared-memory pools), else one warp per seed with
+  // the window split over its lanes
+  if (sm) {
+    for (int k = t; k < K; k += 1024) { int cnt = deg[seeds[k]] & 0x3fffffff; size[k] = cnt; key[k] = cnt; perm[k] = k; }
+  } else
   for (int k = warp; k < K; k += 32) {
     int i = seeds[k];
     int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
@@ -270,6 +353,10 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
     if (m > CL_WSCR || m == 0) continue;
     int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
     int cntw = 0;
+    if (sm && !(deg[i] & 0x40000000)) {     // members from the neighbour list (m <= CL_NB <= 32), distances recomputed
+      if (lane < m) { int j = nbl[(size_t)i * CL_NB + lane]; s_mem[warp][lane] = j; s_md[warp][lane] = cl_dist2(tr + (size_t)i * 3, tr + (size_t)j * 3); }
+      lo = hi;
+    }
     for (int k0 = lo; k0 < hi; k0 += 32) {
       int kk = k0 + lane; bool ok = false; float d = 0.f; int j = -1;
       if (kk < hi) { j = order[kk] - obase; ok = CL_NEIGH(i, j, &d); }
@@ -334,6 +421,8 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   CL_MARK(6)
 }
 
+int cluster_nbl_ints() { return 3 * CL_SMEM_N * CL_NB; }
+int cluster_deg_ints() { return 3 * CL_SMEM_N; }
 void cluster_init_attributes() { cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES); }
 
 void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches) {
@@ -349,7 +438,7 @@ void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches) {
     A.state = h.c_state; A.size = h.c_size; A.seeds = h.c_seeds; A.perm = h.c_perm; A.key = h.c_key; A.members = h.c_members; A.mdist = h.c_mdist;
     A.centre = h.centre;
     A.thr_n = b.p.cluster_number_threshold; A.ang_cut = b.cuts.cluster_lt; A.rad = b.p.cluster_distance_threshold; A.sel_num = b.p.seclct_cluster_number;
-    A.nbits = &st->tickets[20]; A.cap_hyp = h.cap_hyp;
+    A.nbits = &st->tickets[20]; A.cap_hyp = h.cap_hyp; A.nbl = h.c_nbl; A.deg = h.c_deg;
     if (h.cap_hyp > cap) cap = h.cap_hyp;
     SortJob j; j.kin = h.ckeyA; j.kout = h.ckeyB; j.vin = h.cidxA; j.vout = h.cidxB; j.n = &st->hyp_off[3]; j.nbits = &st->tickets[20]; j.hist = h.chist; j.ticket = &st->tickets[21];
     ab.j[0] = j; ab.j[1] = j; ab.j[2] = j;

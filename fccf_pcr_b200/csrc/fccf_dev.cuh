@@ -236,7 +236,7 @@ __device__ void warp_exchange_sort(K* key, int* perm, int n, Less less) {
 __device__ __forceinline__ unsigned ord_key(int v) { return (unsigned)v ^ 0x80000000u; }
 __device__ __forceinline__ unsigned ord_key(float f) { unsigned b = __float_as_uint(f + 0.0f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 template <typename K>
-__device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long* s_scratch) {
+__device__ void block_exchange_sort_passes(K* key, int* perm, int n, unsigned long long* s_scratch) {
   const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, warp = t >> 5, nw = nt >> 5;
   unsigned long long* s_w = s_scratch;                 // [32] exclusive prefix max over warps
   unsigned long long* s_tot = s_scratch + 32;          // [1]  chunk maximum
@@ -292,6 +292,77 @@ __device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long
     if (t == 0) { key[i] = *s_ck; perm[i] = *s_cp; }
     __syncthreads();
   }
+}
+
+// Pipelined form: positions are cut into tiles of XS_B; pass i works on tile q in global step q + i, so
+// pass i+1 trails pass i by one tile and every compare/swap sees exactly the values of the sequential
+// loops; one thread per pass (cur/perm in registers), one barrier per step.  Only the first
+// P = #{key > min key} passes can move anything (afterwards key[P..n) holds only minimum keys), so the
+// whole sort takes ceil(n / XS_B) + P steps instead of P passes of several barriers each.  Keys need a
+// total order (ints, non-NaN floats).
+#define XS_B 4
+template <typename K>
+__device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long* s_scratch) {
+  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, warp = t >> 5, nw = nt >> 5;
+  if (n < 2) return;
+  // P: number of keys above the minimum
+  unsigned* s_u = (unsigned*)s_scratch;              // [32] + [1]
+  unsigned mn = 0xffffffffu;
+  for (int j = t; j < n; j += nt) mn = min(mn, ord_key(key[j]));
+  for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if (lane == 0) s_u[warp] = mn;
+  __syncthreads();
+  if (warp == 0) { unsigned v = lane < nw ? s_u[lane] : 0xffffffffu; for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o)); if (lane == 0) s_u[32] = v; }
+  __syncthreads();
+  mn = s_u[32];
+  __syncthreads();
+  int cnt = 0;
+  for (int j = t; j < n; j += nt) cnt += (ord_key(key[j]) > mn) ? 1 : 0;
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) s_u[warp] = (unsigned)cnt;
+  __syncthreads();
+  if (warp == 0) { unsigned v = lane < nw ? s_u[lane] : 0u; for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); if (lane == 0) s_u[32] = v; }
+  __syncthreads();
+  int P = (int)s_u[32];
+  __syncthreads();
+  if (P > n - 1) P = n - 1;
+  if (P <= 0) return;
+  if (P > 3 * nt) { block_exchange_sort_passes(key, perm, n, s_scratch); return; }
+  // passes owned by this thread: t, t + nt, t + 2 nt.  Only the warps that own a pass take part in the
+  // step loop (named barrier 1 over nact threads); the rest wait at the closing block barrier.
+  const int nact = P >= nt ? nt : ((P + 31) & ~31);
+  const int nslot = (P + nt - 1) / nt;
+  if (t < nact) {
+    K cur[3]; int curp[3];
+#pragma unroll
+    for (int u = 0; u < 3; u++) { cur[u] = K(); curp[u] = 0; }
+    const int qmax = (n - 1) / XS_B;
+    const int last = qmax + P - 1;
+    for (int s = 0; s <= last; s++) {
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int i = t + u * nt;
+        if (u < nslot && i < P) {
+          const int q = s - i, q0 = (i + 1) / XS_B;
+          if (q >= q0 && q <= qmax) {
+            if (q == q0) { cur[u] = key[i]; curp[u] = perm[i]; }
+            const int jb = q * XS_B;
+            K v[XS_B];
+#pragma unroll
+            for (int e = 0; e < XS_B; e++) { const int j = jb + e; if (j > i && j < n) v[e] = key[j]; }
+#pragma unroll
+            for (int e = 0; e < XS_B; e++) {
+              const int j = jb + e;
+              if (j > i && j < n && cur[u] < v[e]) { const int vp = perm[j]; key[j] = cur[u]; perm[j] = curp[u]; cur[u] = v[e]; curp[u] = vp; }
+            }
+            if (q == qmax) { key[i] = cur[u]; perm[i] = curp[u]; }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(nact) : "memory");
+    }
+  }
+  __syncthreads();
 }
 
 }  // namespace fccf

@@ -193,6 +193,7 @@ struct HypWS {
   int* c_seeds;              // compacted seed ids (per type region)
   int* c_perm; int* c_key;
   int* c_members; float* c_mdist;   // scratch for emitted clusters
+  int* c_nbl; int* c_deg;           // neighbour lists / counts of the shared-memory clustering path
   float* centre;             // 3 x FCCF_MAXCENTRE x 8 (qw qx qy qz tx ty tz pad)
   float* qv_T;               // 3 x FCCF_MAXCENTRE x 16 refined
   float* qv_score;           // 3 x FCCF_MAXCENTRE
@@ -217,6 +218,8 @@ struct Batch {                // the lanes one batched launch sequence covers
 // copies calls[lane] into every lane's state block and resets the per-registration counters
 void launch_init_state(cudaStream_t s, const Batch& b, const CallArgs* d_calls, uint64_t* launches);
 void cluster_init_attributes();
+int cluster_nbl_ints();
+int cluster_deg_ints();
 void score_init_attributes();   // one-time function attributes (not allowed inside a stream capture)
 // VoxelGrid stage `stage` (0: on raw clouds, 1: on the stage-0 output) for both clouds
 void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uint64_t* launches);

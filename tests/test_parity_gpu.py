@@ -4,6 +4,8 @@ inputs.  Bars (BASELINE.json north_star): voxel keys, per-voxel counts, pair lis
 0.01 degree and 1 mm.  Every call goes through the C-ABI; nothing here reads /root/reference."""
 import math
 
+import os
+
 import numpy as np
 import pytest
 
@@ -300,6 +302,29 @@ def test_quick_verify_stage(ctx, orc):
     assert agree >= 0.9 * len(Ts)
 
 
+def test_golden_fixture(ctx):
+    """The CUDA path against the committed fixture (stored clouds + oracle results; no oracle call here)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pair_indoor_8k.npz"))
+    T = ctx.register(g["src"], g["tar"], float(g["leaf"]))
+    for name in g.files:
+        if not name.startswith("blob_"):
+            continue
+        want, got = g[name], ctx.blob(name[5:])
+        if name[5:].startswith("fv_counts"):
+            continue     # row order inside a hypothesis is sorted on both sides, compared in test_hypotheses_clusters_and_scores
+        assert want.shape == got.shape, name
+        if want.dtype.kind in "iu":
+            np.testing.assert_array_equal(got, want, err_msg=name)
+        elif name[5:].startswith("top_T"):
+            for Ta, Tb in zip(got.reshape(-1, 4, 4), want.reshape(-1, 4, 4)):
+                assert scenes.rotation_error_deg(Ta, Tb) <= 0.01 and scenes.translation_error(Ta, Tb) <= 1e-3
+        elif name[5:].startswith("face_plane"):
+            assert _rel_rows(got, want, 7, [[0, 1, 2], [3, 4, 5], [6]]) <= 1e-5
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-4, err_msg=name)
+    assert scenes.rotation_error_deg(T, g["T_oracle"]) <= 0.01 and scenes.translation_error(T, g["T_oracle"]) <= 1e-3
+
+
 def test_degenerate_inputs(ctx, oracle_mod):
     src, tar, _ = scenes.make_pair("indoor", 20000, 7)
     o = oracle_mod.Oracle()
@@ -335,6 +360,68 @@ def test_outdoor_scaled_parameters(oracle_mod):
         assert np.array_equal(c.blob(name), o.blob(name)), name
     _check_inlier_counts(c, o)
     assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
+    c.close()
+
+
+def _voxelgrid_properties(c, xyz, leaf):
+    """Size-independent properties of the VoxelGrid stage: cells strictly ascending, counts sum to the
+    number of finite points, every centroid inside its cell's bounding interval of the input."""
+    out, cell, cnt = c.voxelgrid(xyz, leaf)
+    assert len(out) == len(cell) == len(cnt) > 0
+    assert np.all(np.diff(cell) > 0)
+    assert int(cnt.sum()) == int(np.isfinite(xyz).all(axis=1).sum())
+    assert np.all(out.min(axis=0) >= xyz.min(axis=0) - 1e-4) and np.all(out.max(axis=0) <= xyz.max(axis=0) + 1e-4)
+    # idempotence up to rounding at cell faces (Q2): a second pass keeps the number of cells within 0.1 %
+    out2, cell2, cnt2 = c.voxelgrid(out, leaf)
+    assert abs(len(out2) - len(out)) <= max(2, len(out) // 1000)
+    return out, cell, cnt
+
+
+def test_full_size_outdoor_2M(oracle_mod):
+    """BASELINE config 3 at full size: 2M + 2M outdoor points, leaf 0.5, scaled plane / fine-verify voxels.
+    The oracle still finishes in seconds at this size, so the integer stages are compared bit for bit."""
+    import fccf_pcr_b200 as fccf
+
+    src, tar, Tgt = scenes.make_pair("outdoor", 2_000_000, 3)
+    prm = dict(face_voxel_size=4.0, fine_verify_voxel_size=2.0)
+    c = fccf.Context(0, **prm)
+    Tg = c.register(src, tar, 0.5)
+    o = oracle_mod.Oracle(**prm)
+    To = o.register(src, tar, 0.5)
+    for name in ["vg1_cell1", "vg1_cnt2", "vg2_cnt1", "vox_key1", "vox_cnt2", "merge_label1", "merge_label2", "base1", "base2", "matches", "n_hyp", "n_centres"]:
+        assert np.array_equal(c.blob(name), o.blob(name)), name
+    _check_inlier_counts(c, o)
+    assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
+    assert np.array_equal(c.register(src, tar, 0.5), Tg)                 # replay of the captured graph: same bits
+    _voxelgrid_properties(c, src, 0.5)
+    c.close()
+
+
+@pytest.mark.parametrize("leaf", [0.1, 0.5])
+def test_full_size_10M(leaf, oracle_mod):
+    """BASELINE config 5 shape: 10M + 10M points, two leaves of the sweep: size-independent properties, and
+    (the oracle's own cost here is the 10M-point sort, a few seconds) the integer stages against the oracle.
+    Leaf 0.5 with the reference's fixed 1 m plane voxels is the near-degenerate case Q14: a handful of planar
+    voxels, reproduced as it is."""
+    import fccf_pcr_b200 as fccf
+
+    src, tar, Tgt = scenes.make_pair("indoor", 10_000_000, 5)
+    c = fccf.Context(0)
+    _voxelgrid_properties(c, src, leaf)
+    T = c.register(src, tar, leaf)
+    assert c.timing.n_launches > 0 and c.timing.h2d_bytes == 240_000_000
+    assert np.array_equal(c.register(src, tar, leaf), T, equal_nan=True)
+    # linearity of the per-voxel counts: the pipeline's second VoxelGrid pass is count-preserving
+    assert int(c.blob("vg2_cnt1").sum()) == len(c.blob("vg1_cnt1"))
+    o = oracle_mod.Oracle()
+    To = o.register(src, tar, leaf)
+    for name in ["vg1_cell1", "vg1_cnt1", "vg2_cell2", "vg2_cnt2", "vox_key1", "vox_cnt2", "merge_label1", "merge_label2", "base1", "base2", "matches", "n_hyp", "n_centres"]:
+        assert np.array_equal(c.blob(name), o.blob(name)), name
+    assert np.array_equal(np.isnan(T), np.isnan(To))
+    if not np.isnan(To).any():
+        assert scenes.rotation_error_deg(T, To) <= 0.01 and scenes.translation_error(T, To) <= 1e-3
+    if leaf < 0.4:
+        assert scenes.rotation_error_deg(T, Tgt) < 1.0 and scenes.translation_error(T, Tgt) < 0.08
     c.close()
 
 
