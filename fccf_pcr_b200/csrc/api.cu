@@ -210,7 +210,7 @@ static int ensure_capacity(fccf_ctx* ctx, Group* g, int li, size_t n0, size_t n1
   size_t nc = 3 * FCCF_MAXCENTRE, ntop = 3 * FCCF_TOPK;
   add(nc * 32); add(nc * 64); add(nc * 4); add(nc * 4); add(nc * 128); add(nc * 4); add(nc * 4);
   add(ntop * 64); add(ntop * 4); add(ntop * 4); add(ntop * 4);
-  size_t fv_bytes = score_ws_layout(nullptr, nullptr, cap, (int)ntop);
+  size_t fv_bytes = score_ws_layout(nullptr, nullptr, cap, 48);   // 48 counter rows: hypotheses in flight of the global-table kernel
   add(fv_bytes);
   bytes += 8192;
   CK(cudaMalloc(&L->hyp_arena.base, bytes));
@@ -226,7 +226,7 @@ static int ensure_capacity(fccf_ctx* ctx, Group* g, int li, size_t n0, size_t n1
   h.centre = a.take<float>(nc * 8); h.qv_T = a.take<float>(nc * 16); h.qv_score = a.take<float>(nc); h.qv_npair = a.take<int>(nc);
   h.qv_pairs = a.take<int>(nc * 32); h.qv_iters = a.take<int>(nc); h.rank_perm = a.take<int>(nc);
   h.top_T = a.take<float>(ntop * 16); h.top_s1 = a.take<float>(ntop); h.top_s2 = a.take<float>(ntop); h.top_centre = a.take<int>(ntop);
-  score_ws_layout(&h.fv, a.take<char>(fv_bytes), cap, (int)ntop);
+  score_ws_layout(&h.fv, a.take<char>(fv_bytes), cap, 48);
   L->cap_pts = cap;
   return FCCF_OK;
 }
@@ -877,10 +877,10 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
     off.push_back((int)pairs.size() / 2);
     if (stem == "qv_pairs") put(pairs.data(), pairs.size() * 4, FCCF_I32); else put(off.data(), off.size() * 4, FCCF_I32);
   }
-  else if (stem == "top_T" && ti >= 0) { out = fetch(ctx->L0().h.top_T + (size_t)ti * FCCF_TOPK * 16, (size_t)st.n_top[ti] * 64); dt = FCCF_F32; }
-  else if (stem == "top_s1" && ti >= 0) { out = fetch(ctx->L0().h.top_s1 + (size_t)ti * FCCF_TOPK, (size_t)st.n_top[ti] * 4); dt = FCCF_F32; }
-  else if (stem == "top_s2" && ti >= 0) { out = fetch(ctx->L0().h.top_s2 + (size_t)ti * FCCF_TOPK, (size_t)st.n_top[ti] * 4); dt = FCCF_F32; }
-  else if (stem == "top_centre" && ti >= 0) { out = fetch(ctx->L0().h.top_centre + (size_t)ti * FCCF_TOPK, (size_t)st.n_top[ti] * 4); dt = FCCF_I32; }
+  else if (stem == "top_T" && ti >= 0) { out = fetch(ctx->L0().h.top_T + (size_t)ti * fccf_topk(ctx->p) * 16, (size_t)st.n_top[ti] * 64); dt = FCCF_F32; }
+  else if (stem == "top_s1" && ti >= 0) { out = fetch(ctx->L0().h.top_s1 + (size_t)ti * fccf_topk(ctx->p), (size_t)st.n_top[ti] * 4); dt = FCCF_F32; }
+  else if (stem == "top_s2" && ti >= 0) { out = fetch(ctx->L0().h.top_s2 + (size_t)ti * fccf_topk(ctx->p), (size_t)st.n_top[ti] * 4); dt = FCCF_F32; }
+  else if (stem == "top_centre" && ti >= 0) { out = fetch(ctx->L0().h.top_centre + (size_t)ti * fccf_topk(ctx->p), (size_t)st.n_top[ti] * 4); dt = FCCF_I32; }
   else if ((stem == "fv_counts" || stem == "fv_off") && ti >= 0) {
     // per-voxel (s,t) of every fine-verified hypothesis of this type, rows sorted lexicographically
     ScoreWS ws = ctx->L0().h.fv; ws.ss = &ctx->L0().d_st->fv; ws.status = &ctx->L0().d_st->status;
@@ -890,7 +890,7 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
     std::vector<int> all, off;
     for (int k = 0; k < st.n_top[ti]; k++) {
       CK(cudaMemsetAsync(d_n, 0, 4, ctx->stream));
-      launch_score_dump(ctx->stream, ctx->p, ctx->L0().h.top_T + ((size_t)ti * FCCF_TOPK + k) * 16, ctx->L0().c[1].sub, ws, d_rows, cap_rows, d_n, ctx->itab, &ctx->launches);
+      launch_score_dump(ctx->stream, ctx->p, ctx->L0().h.top_T + ((size_t)ti * fccf_topk(ctx->p) + k) * 16, ctx->L0().c[1].sub, ws, d_rows, cap_rows, d_n, ctx->itab, &ctx->launches);
       int n = 0; CK(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream));
       n = std::min(n, cap_rows);
       std::vector<int> rows(5 * (size_t)n); if (n) CK(cudaMemcpy(rows.data(), d_rows, (size_t)n * 20, cudaMemcpyDeviceToHost));

@@ -15,10 +15,19 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include <chrono>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "fccf.h"
 
-// ---- minimal PLY reader: ascii / binary_little_endian / binary_big_endian, vertex x y z --------
-// (pcl::io::loadPLYFile<pcl::PointXYZ>, FCCF.cpp:1655/1661: other properties are ignored)
+// ---- PLY reader: ascii / binary_little_endian / binary_big_endian, vertex x y z ------------------
+// (pcl::io::loadPLYFile<pcl::PointXYZ>, FCCF.cpp:1655/1661: other properties are ignored).
+// Fast path: the file is memory-mapped; a binary little-endian file whose vertex element
+// is exactly float x, y, z is handed to the library IN PLACE (the packed triples of the mapping are the
+// host buffer of fccf_register, no parse, no copy); other binary layouts are gathered with one strided
+// pass; ascii bodies are parsed with strtof straight out of the mapping.
 struct PlyProp { std::string type, name; int size; };
 static int ply_type_size(const std::string& t) {
   if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
@@ -39,52 +48,94 @@ static double ply_read_scalar(const unsigned char* p, const std::string& t, bool
   if (t == "int" || t == "int32") { int32_t v; memcpy(&v, b, 4); return v; }
   uint32_t v; memcpy(&v, b, 4); return v;
 }
-static bool load_ply_xyz(const std::string& path, std::vector<float>& xyz) {
-  std::ifstream f(path.c_str(), std::ios::binary);
-  if (!f.good()) return false;
-  std::string line;
-  if (!std::getline(f, line) || line.substr(0, 3) != "ply") return false;
-  int fmt = -1;  // 0 ascii, 1 little, 2 big
-  long long nvert = -1; bool in_vertex = false, vertex_first = true, seen_element = false;
-  std::vector<PlyProp> props;
-  while (std::getline(f, line)) {
+struct Cloud {
+  const float* xyz = nullptr; size_t n = 0;   // packed float32 triples
+  std::vector<float> own;                     // storage when the file had to be converted
+  void* map = nullptr; size_t map_len = 0;    // the mapping (kept while xyz may point into it)
+  bool in_place = false;
+  ~Cloud() { if (map) munmap(map, map_len); }
+};
+static bool load_ply_xyz(const std::string& path, Cloud& out) {
+  int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) return false;
+  struct stat sb;
+  if (fstat(fd, &sb) != 0 || sb.st_size < 4) { close(fd); return false; }
+  size_t len = (size_t)sb.st_size;
+  void* m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return false;
+  out.map = m; out.map_len = len;
+  madvise(m, len, MADV_SEQUENTIAL);
+  const char* base = (const char*)m; const char* end = base + len; const char* p = base;
+  auto next_line = [&](std::string& line) -> bool {
+    if (p >= end) return false;
+    const char* q = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* e = q ? q : end;
+    line.assign(p, e);
     if (!line.empty() && line[line.size() - 1] == '\r') line.erase(line.size() - 1);
+    p = q ? q + 1 : end;
+    return true;
+  };
+  std::string line;
+  if (!next_line(line) || line.substr(0, 3) != "ply") return false;
+  int fmt = -1;  // 0 ascii, 1 little, 2 big
+  long long nvert = -1; bool in_vertex = false, vertex_first = true, seen_element = false, ended = false;
+  std::vector<PlyProp> props;
+  while (next_line(line)) {
     std::istringstream ss(line); std::string tok; ss >> tok;
     if (tok == "format") { std::string k; ss >> k; fmt = (k == "ascii") ? 0 : (k == "binary_little_endian" ? 1 : (k == "binary_big_endian" ? 2 : -1)); }
     else if (tok == "element") { std::string nm; long long cnt; ss >> nm >> cnt; in_vertex = (nm == "vertex"); if (in_vertex) { nvert = cnt; vertex_first = !seen_element; } seen_element = true; }
     else if (tok == "property" && in_vertex) {
       std::string ty; ss >> ty;
       if (ty == "list") return false;
-      PlyProp p; p.type = ty; ss >> p.name; p.size = ply_type_size(ty);
-      if (p.size == 0) return false;
-      props.push_back(p);
-    } else if (tok == "end_header") break;
+      PlyProp pr; pr.type = ty; ss >> pr.name; pr.size = ply_type_size(ty);
+      if (pr.size == 0) return false;
+      props.push_back(pr);
+    } else if (tok == "end_header") { ended = true; break; }
   }
-  if (fmt < 0 || nvert < 0 || !vertex_first) return false;
+  if (!ended || fmt < 0 || nvert < 0 || !vertex_first) return false;
   int ix = -1, iy = -1, iz = -1, stride = 0; std::vector<int> offs;
   for (size_t i = 0; i < props.size(); i++) { offs.push_back(stride); stride += props[i].size; if (props[i].name == "x") ix = (int)i; if (props[i].name == "y") iy = (int)i; if (props[i].name == "z") iz = (int)i; }
   if (ix < 0 || iy < 0 || iz < 0) return false;
-  xyz.resize((size_t)nvert * 3);
+  out.n = (size_t)nvert;
   if (fmt == 0) {
-    std::vector<double> row(props.size());
+    out.own.resize((size_t)nvert * 3);
+    const size_t np = props.size();
+    std::string body(p, (size_t)(end - p));      // NUL-terminated copy: strtod must not run off the mapping
+    p = body.c_str(); end = p + body.size();
     for (long long v = 0; v < nvert; v++) {
-      for (size_t k = 0; k < props.size(); k++) if (!(f >> row[k])) return false;
-      xyz[3 * v] = (float)row[ix]; xyz[3 * v + 1] = (float)row[iy]; xyz[3 * v + 2] = (float)row[iz];
-    }
-  } else {
-    bool swap = (fmt == 2);   // host is little endian
-    std::vector<unsigned char> buf((size_t)nvert * stride);
-    f.read((char*)buf.data(), (std::streamsize)buf.size());
-    if ((size_t)f.gcount() != buf.size()) return false;
-    bool fast = !swap && props[ix].size == 4 && props[iy].size == 4 && props[iz].size == 4 && props[ix].type[0] == 'f' && props[iy].type[0] == 'f' && props[iz].type[0] == 'f';
-    for (long long v = 0; v < nvert; v++) {
-      const unsigned char* r = buf.data() + (size_t)v * stride;
-      if (fast) { memcpy(&xyz[3 * v], r + offs[ix], 4); memcpy(&xyz[3 * v + 1], r + offs[iy], 4); memcpy(&xyz[3 * v + 2], r + offs[iz], 4); }
-      else {
-        xyz[3 * v] = (float)ply_read_scalar(r + offs[ix], props[ix].type, swap);
-        xyz[3 * v + 1] = (float)ply_read_scalar(r + offs[iy], props[iy].type, swap);
-        xyz[3 * v + 2] = (float)ply_read_scalar(r + offs[iz], props[iz].type, swap);
+      for (size_t k = 0; k < np; k++) {
+        char* e2 = nullptr;
+        while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) p++;
+        if (p >= end) return false;
+        double val = strtod(p, &e2);
+        if (e2 == p) return false;
+        p = e2;
+        if ((int)k == ix) out.own[3 * v] = (float)val; else if ((int)k == iy) out.own[3 * v + 1] = (float)val; else if ((int)k == iz) out.own[3 * v + 2] = (float)val;
       }
+    }
+    out.xyz = out.own.data();
+  } else {
+    if ((size_t)(end - p) < (size_t)nvert * (size_t)stride) return false;
+    const unsigned char* body = (const unsigned char*)p;
+    bool swap = (fmt == 2);   // host is little endian
+    bool f3 = !swap && props[ix].size == 4 && props[iy].size == 4 && props[iz].size == 4 && props[ix].type[0] == 'f' && props[iy].type[0] == 'f' && props[iz].type[0] == 'f';
+    if (f3 && stride == 12 && offs[ix] == 0 && offs[iy] == 4 && offs[iz] == 8) {
+      // packed x y z float32: used in place.  The body may start at any byte offset of the mapping; the
+      // pointer is only handed to the library's host->device copy, never dereferenced as float here.
+      out.xyz = (const float*)(const void*)body; out.in_place = true;
+    } else {
+      out.own.resize((size_t)nvert * 3);
+      for (long long v = 0; v < nvert; v++) {
+        const unsigned char* r = body + (size_t)v * stride;
+        if (f3) { memcpy(&out.own[3 * v], r + offs[ix], 4); memcpy(&out.own[3 * v + 1], r + offs[iy], 4); memcpy(&out.own[3 * v + 2], r + offs[iz], 4); }
+        else {
+          out.own[3 * v] = (float)ply_read_scalar(r + offs[ix], props[ix].type, swap);
+          out.own[3 * v + 1] = (float)ply_read_scalar(r + offs[iy], props[iy].type, swap);
+          out.own[3 * v + 2] = (float)ply_read_scalar(r + offs[iz], props[iz].type, swap);
+        }
+      }
+      out.xyz = out.own.data();
     }
   }
   return true;
@@ -113,9 +164,11 @@ int main(int argc, char** argv) {
   }
   std::string fnameS = argv[1], fnameT = argv[2];
   float LeafSize = (float)std::atof(argv[3]);
-  std::vector<float> source, target;
+  Cloud source, target;
+  auto tl0 = std::chrono::steady_clock::now();
   if (!load_ply_xyz(fnameS, source)) { fprintf(stderr, "Couldn't read file \n"); return 0; }
   if (!load_ply_xyz(fnameT, target)) { fprintf(stderr, "Couldn't read file \n"); return 0; }
+  double load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl0).count();
   std::cout << "Leaf size : " << LeafSize << std::endl;
   fccf_params prm; fccf_default_params(&prm);
   // optional overrides after the three positional arguments: name=value
@@ -129,13 +182,14 @@ int main(int argc, char** argv) {
     else if (k == "fine_verify_number") prm.fine_verify_number = v;
     else if (k == "seclct_cluster_number") prm.seclct_cluster_number = v;
     else if (k == "emulate_pcl_overflow") prm.emulate_pcl_overflow = (int)v;
+    else if (k == "exhaustive" && v != 0.f) prm.fine_verify_number = 256;   // fine-verify every cluster centre
   }
   int dev = 0;
   if (const char* e = std::getenv("FCCF_DEVICE")) dev = std::atoi(e);
   fccf_ctx* ctx = fccf_create(dev, &prm);
   if (!ctx) { std::cerr << "FCCF: no usable CUDA device (this build has no CPU path)" << std::endl; return 3; }
   float T[16]; fccf_timing tm;
-  int rc = fccf_register(ctx, source.data(), source.size() / 3, target.data(), target.size() / 3, LeafSize, T, &tm);
+  int rc = fccf_register(ctx, source.xyz, source.n, target.xyz, target.n, LeafSize, T, &tm);
   if (rc != FCCF_OK && rc != FCCF_ERR_CAPACITY) { std::cerr << "FCCF: " << fccf_last_error(ctx) << std::endl; fccf_destroy(ctx); return 4; }
   if (rc == FCCF_ERR_CAPACITY) std::cerr << "FCCF: warning: " << fccf_last_error(ctx) << std::endl;
   std::cout << "Transformation: \n";
@@ -143,10 +197,22 @@ int main(int argc, char** argv) {
   std::cout << std::endl;
   // a second, warm run gives the steady-state timing (the first includes allocation and module load)
   fccf_timing tw; float T2[16];
-  if (std::getenv("FCCF_NO_WARM_TIMING") == nullptr && fccf_register(ctx, source.data(), source.size() / 3, target.data(), target.size() / 3, LeafSize, T2, &tw) == FCCF_OK) tm = tw;
+  if (std::getenv("FCCF_NO_WARM_TIMING") == nullptr && fccf_register(ctx, source.xyz, source.n, target.xyz, target.n, LeafSize, T2, &tw) == FCCF_OK) tm = tw;
   std::cout << "Time pipeline (computer_transform_guess, the reference's clock() region): " << tm.pipeline_ms << " ms" << std::endl;
   std::cout << "Time end-to-end (H2D " << tm.h2d_ms << " + downsample " << tm.downsample_ms << " + pipeline + D2H " << tm.d2h_ms << "): " << tm.total_ms << " ms, "
             << tm.n_launches << " kernel launches" << std::endl;
+  std::cout << "Time PLY load: " << load_ms << " ms (" << (source.in_place && target.in_place ? "memory-mapped, used in place" : "parsed") << ")" << std::endl;
+  // machine-readable record (the reference's dead writefile / dropped costTime, FCCF.cpp:1610-1644, 1685)
+  if (const char* lp = std::getenv("FCCF_LOG")) {
+    bool fresh = access(lp, F_OK) != 0;
+    if (FILE* f = fopen(lp, "a")) {
+      if (fresh) fprintf(f, "src,tar,leaf,n_src,n_tar,T00,T01,T02,T03,T10,T11,T12,T13,T20,T21,T22,T23,T30,T31,T32,T33,load_ms,h2d_ms,downsample_ms,pipeline_ms,d2h_ms,total_ms,kernel_launches\n");
+      fprintf(f, "%s,%s,%.9g,%zu,%zu", fnameS.c_str(), fnameT.c_str(), LeafSize, source.n, target.n);
+      for (int i = 0; i < 16; i++) fprintf(f, ",%.9g", T[i]);
+      fprintf(f, ",%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,%d\n", load_ms, tm.h2d_ms, tm.downsample_ms, tm.pipeline_ms, tm.d2h_ms, tm.total_ms, tm.n_launches);
+      fclose(f);
+    }
+  }
   fccf_destroy(ctx);
   return 0;
 }

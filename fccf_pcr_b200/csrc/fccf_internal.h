@@ -14,7 +14,10 @@ typedef unsigned int u32;
 #define FCCF_MAXBASE 120      // C(16,2)
 #define FCCF_MAXMATCH (FCCF_MAXBASE * FCCF_MAXBASE)
 #define FCCF_MAXCENTRE 256    // per roughness type
-#define FCCF_TOPK 16          // fine-verified hypotheses per type (reference: 4)
+#define FCCF_TOPK 256         // capacity: fine-verified hypotheses per type (reference default: 4; 256 = every centre, the
+                              // exhaustive-scoring mode of SURVEY.md f2: fine_verify_number >= FCCF_MAXCENTRE)
+// slots per type actually used: the top arrays are laid out [3][topk] with the run-time stride
+inline int fccf_topk(const fccf_params& p) { int k = (int)p.fine_verify_number; return k < 1 ? 1 : (k > FCCF_TOPK ? FCCF_TOPK : k); }
 
 // radix sort tile
 #define RS_T 256

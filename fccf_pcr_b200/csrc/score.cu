@@ -34,7 +34,7 @@ struct ScArgs {
   ScoreWS ws;
   const float* s1; const int* n1p; const int* n2p;
   const float* s2;
-  const float* T; int n_hyp; const int* n_top;   // n_top != nullptr: pipeline layout [3][FCCF_TOPK]
+  const float* T; int n_hyp; const int* n_top; int topk;   // n_top != nullptr: pipeline layout [3][topk]
   float* scores;
   int* rows; int cap_rows; int* nrows;
   float res;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_warp_kernel(const ScArgs*
   const float* __restrict__ s2 = A.s2;
   const float inv_tot = 0.f; (void)inv_tot;
   for (int h = blockIdx.x * SC_WARPS + warp; h < A.n_hyp; h += gridDim.x * SC_WARPS) {
-    if (A.n_top) { int ty = h / FCCF_TOPK, kk = h - ty * FCCF_TOPK; if (kk >= A.n_top[ty]) continue; }
+    if (A.n_top) { int ty = h / A.topk, kk = h - ty * A.topk; if (kk >= A.n_top[ty]) continue; }
     const float4* Tp = (const float4*)(A.T + (size_t)h * 16);
     const float4 r0 = __ldg(Tp), r1 = __ldg(Tp + 1), r2 = __ldg(Tp + 2);
     for (int i = lane; i < P.row_words; i += 32) row[i] = 0u;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_kernel(const ScArgs* __restr
     for (int k = 0; k < SC_NH; k++) {
       int h = h0 + k;
       bool a = h < A.n_hyp;
-      if (a && A.n_top) { int ty = h / FCCF_TOPK, kk = h - ty * FCCF_TOPK; a = kk < A.n_top[ty]; }
+      if (a && A.n_top) { int ty = h / A.topk, kk = h - ty * A.topk; a = kk < A.n_top[ty]; }
       if (a) actm |= 1u << k;
     }
     if (!actm) continue;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_dump_kernel(const ScArgs* __
 
 static void fill_common(ScArgs& A, const fccf_params& p, const ScoreWS& ws) {
   A.ws = ws; A.res = p.fine_verify_voxel_size; A.s1 = nullptr; A.n1p = nullptr; A.n2p = nullptr; A.s2 = nullptr; A.T = nullptr; A.n_hyp = 0; A.n_top = nullptr;
-  A.scores = nullptr; A.rows = nullptr; A.cap_rows = 0; A.nrows = nullptr;
+  A.topk = 1; A.scores = nullptr; A.rows = nullptr; A.cap_rows = 0; A.nrows = nullptr;
 }
 static bool is_pow2_res(float res) { int e; float m = frexpf(res, &e); return m == 0.5f && res > 0.f; }
 
@@ -575,7 +575,7 @@ void launch_score_best(cudaStream_t s, const float* d_scores, int n, long long i
 }
 
 // ---------------------------------------------------------------------------------------------
-struct FuseArgs { PipeState* st; const float* top_T; const float* top_s1; const float* top_s2; float fine_number; };
+struct FuseArgs { PipeState* st; const float* top_T; const float* top_s1; const float* top_s2; float fine_number; int topk; };
 
 // FCCF.cpp:1546-1606 + fuse_answer 1291-1368
 __global__ void fuse_kernel(const FuseArgs* __restrict__ AB) {
@@ -583,15 +583,15 @@ __global__ void fuse_kernel(const FuseArgs* __restrict__ AB) {
   PipeState* st = A.st;
   float score_sum = 0.f, score1_sum = 0.f, score2_sum = 0.f;
   for (int ty = 0; ty < 3; ty++)
-    for (int k = 0; k < st->n_top[ty]; k++) { score2_sum += A.top_s2[ty * FCCF_TOPK + k]; score1_sum += A.top_s1[ty * FCCF_TOPK + k]; }
+    for (int k = 0; k < st->n_top[ty]; k++) { score2_sum += A.top_s2[ty * A.topk + k]; score1_sum += A.top_s1[ty * A.topk + k]; }
   float best_best = 0.f;
   float hs_score[3]; q4 hs_q[3]; f3 hs_t[3];
   for (int ty = 0; ty < 3; ty++) {
     float best_score = 0.f;
     float tb[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     for (int k = 0; k < st->n_top[ty]; k++) {
-      float score = A.top_s1[ty * FCCF_TOPK + k] / score1_sum + A.top_s2[ty * FCCF_TOPK + k] / score2_sum;
-      if (score > best_score) { best_score = score; for (int i = 0; i < 12; i++) tb[i] = A.top_T[((size_t)ty * FCCF_TOPK + k) * 16 + i]; }
+      float score = A.top_s1[ty * A.topk + k] / score1_sum + A.top_s2[ty * A.topk + k] / score2_sum;
+      if (score > best_score) { best_score = score; for (int i = 0; i < 12; i++) tb[i] = A.top_T[((size_t)ty * A.topk + k) * 16 + i]; }
     }
     if (best_best < best_score) best_best = best_score;
     m3 R; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R.m[i][j] = tb[4 * i + j];
@@ -629,8 +629,8 @@ void launch_fine_verify_fuse(cudaStream_t s, const Batch& b, uint64_t* launches)
     ScoreWS ws = h.fv; ws.ss = &st->fv; ws.status = &st->status;
     jobs[g].s1 = w.c[0].sub; jobs[g].n1 = &st->oct[0].S; jobs[g].n2 = &st->oct[1].S; jobs[g].ws = ws;
     ScArgs& A = As[g]; fill_common(A, b.p, ws);
-    A.T = h.top_T; A.n_hyp = 3 * FCCF_TOPK; A.n_top = st->n_top; A.s2 = w.c[1].sub; A.scores = h.top_s2;
-    FuseArgs& F = Fs[g]; F.st = st; F.top_T = h.top_T; F.top_s1 = h.top_s1; F.top_s2 = h.top_s2; F.fine_number = b.p.fine_verify_number;
+    A.T = h.top_T; A.n_hyp = 3 * fccf_topk(b.p); A.n_top = st->n_top; A.topk = fccf_topk(b.p); A.s2 = w.c[1].sub; A.scores = h.top_s2;
+    FuseArgs& F = Fs[g]; F.st = st; F.top_T = h.top_T; F.top_s1 = h.top_s1; F.top_s2 = h.top_s2; F.fine_number = b.p.fine_verify_number; F.topk = fccf_topk(b.p);
   }
   launch_score_build(s, b.p, jobs.data(), G, *b.tab, launches);
   score_launch(s, As, *b.tab, launches);

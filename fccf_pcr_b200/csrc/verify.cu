@@ -331,6 +331,7 @@ struct QvArgs {
   PipeState* st;
   const float* centre; float* qv_T; float* qv_score; int* qv_npair; int* qv_pairs; int* qv_iters;
   int* rank_perm; float* top_T; float* top_s1; int* top_centre;
+  int topk;
   float ang_cut, dist_thr, required, fine_number;   // ang_cut: cosine cut of quick_verify_angel_threshold (strict <)
 };
 
@@ -373,10 +374,10 @@ __global__ void __launch_bounds__(256) rank_top_kernel(const QvArgs* __restrict_
   else if (t < 32) warp_exchange_sort(s_key, s_perm, C, [](float a, float b) { return a < b; });   // NaN keys have no total order: literal emulation
   __syncthreads();
   int amax = (int)A.fine_number;
-  if (amax > FCCF_TOPK) amax = FCCF_TOPK;
+  if (amax > A.topk) amax = A.topk;
   int nt = C < amax ? C : amax;
   for (int k = t; k < C; k += 256) A.rank_perm[ty * FCCF_MAXCENTRE + k] = s_perm[k];
-  if (t < nt) { A.top_s1[ty * FCCF_TOPK + t] = s_key[t]; A.top_centre[ty * FCCF_TOPK + t] = s_perm[t]; }
+  for (int k = t; k < nt; k += 256) { A.top_s1[ty * A.topk + k] = s_key[k]; A.top_centre[ty * A.topk + k] = s_perm[k]; }
   if (t == 0) st->n_top[ty] = nt;
 }
 
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(128, MINB) refine_top_kernel(const QvArgs* __r
   PipeState* st = A.st;
   const int lane = threadIdx.x & 31;
   const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int ty = slot / FCCF_TOPK, k = slot - ty * FCCF_TOPK;
+  const int ty = slot / A.topk, k = slot - ty * A.topk;
   if (ty >= 3 || k >= st->n_top[ty]) return;
   const int wid = ty * FCCF_MAXCENTRE + A.top_centre[slot];
   const float* c = A.centre + (size_t)wid * 8;
@@ -407,14 +408,14 @@ void launch_quick_verify(cudaStream_t s, const Batch& b, uint64_t* launches) {
     QvArgs& A = As[g];
     A.st = w.st; A.centre = h.centre; A.qv_T = h.qv_T; A.qv_score = h.qv_score; A.qv_npair = h.qv_npair; A.qv_pairs = h.qv_pairs; A.qv_iters = h.qv_iters;
     A.rank_perm = h.rank_perm; A.top_T = h.top_T; A.top_s1 = h.top_s1; A.top_centre = h.top_centre;
-    A.ang_cut = b.cuts.qv_lt; A.dist_thr = b.p.quick_verify_distance_threshold; A.required = b.p.required_optimize_plane; A.fine_number = b.p.fine_verify_number;
+    A.ang_cut = b.cuts.qv_lt; A.dist_thr = b.p.quick_verify_distance_threshold; A.required = b.p.required_optimize_plane; A.fine_number = b.p.fine_verify_number; A.topk = fccf_topk(b.p);
   }
   const QvArgs* dA = b.tab->put(As.data(), G);
   static int occ = -1;
   if (occ < 0) { const char* e = getenv("FCCF_QV_OCC"); occ = e ? atoi(e) : 2; }
   quick_verify_kernel<<<dim3((3 * FCCF_MAXCENTRE + 3) / 4, 1, G), 128, 0, s>>>(dA);
   rank_top_kernel<<<dim3(3, 1, G), 256, 0, s>>>(dA);
-  dim3 grid((3 * FCCF_TOPK + 3) / 4, 1, G);
+  dim3 grid((3 * fccf_topk(b.p) + 3) / 4, 1, G);
   if (occ <= 2) refine_top_kernel<2><<<grid, 128, 0, s>>>(dA);
   else if (occ == 3) refine_top_kernel<3><<<grid, 128, 0, s>>>(dA);
   else refine_top_kernel<4><<<grid, 128, 0, s>>>(dA);

