@@ -130,8 +130,8 @@ struct ArgTable {
 // grid.x of a launch whose CTAs stride over up to nb_cap blocks of work per job, when G lanes x njobs
 // jobs share the launch: the element counts are device-side, so grids are sized for capacity, and a
 // batched launch must not drown the GPU in CTAs that only find out that they have nothing to do.
-inline int grid_x(int nb_cap, int G, int njobs = 1) {
-  int lim = 4096 / (G * njobs);
+inline int grid_x(int nb_cap, int G, int njobs = 1, int budget = 4096) {
+  int lim = budget / (G * njobs);
   if (lim < 8) lim = 8;
   if (nb_cap < 1) nb_cap = 1;
   return nb_cap < lim ? nb_cap : lim;

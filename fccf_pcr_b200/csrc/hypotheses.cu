@@ -2,11 +2,14 @@
 // generation (FCCF.cpp:429-468 select_base, 1412-1427 match loop, 841-1018 computer_transform,
 // 1439-1462 matrix -> quaternion), as count -> scan -> emit so that every pool keeps the
 // reference's push_back order:
-//   pairs_match   one CTA: base pairs of both clouds (ordered ballot compaction of the 16x16
-//                 upper triangle), the B1 x B2 descriptor test, per-match hypothesis counts, and an
-//                 ordered scan of the counts per roughness type (three 21-bit fields of a u64)
-//   emit_hyp      one thread per matched (pair,pair): recomputes the two-Rodrigues rotation and
-//                 writes its hypotheses (3x4 + quaternion/translation) at their pool offsets
+//   base_pairs    one CTA: base pairs of both clouds (ordered ballot compaction of the 16x16 upper triangle)
+//   match_test    one thread per (pair of cloud 1, pair of cloud 2): the descriptor test
+//   match_compact one CTA: ordered list of the matched (pair,pair) indices
+//   hyp_count     one WARP per match: the (third plane of cloud 1) x (third plane of cloud 2) combinations
+//                 are split over the lanes in the reference's loop order, ballots count them
+//   match_scan    ordered scan of the counts per roughness type (three 21-bit fields of a u64)
+//   emit_hyp      one warp per match: every lane with a passing combination solves its translation and
+//                 writes the hypothesis (3x4 + quaternion/translation) at pool offset + ballot rank
 #include "fccf_dev.cuh"
 #include "fccf_internal.h"
 #include <vector>
@@ -15,7 +18,7 @@ namespace fccf {
 
 struct HypArgs {
   PipeState* st;
-  int* match_cnt; int* match_off;
+  int* match_cnt; int* match_off; int* mlist;     // mlist: ordered indices of the matched (pair,pair) entries
   float* hyp_T; float* hyp_qt;
   int cap_hyp;
   float tmin, tmax, rough, same_thr, third_thr, third_cut;   // third_cut: cosine cut of third_plane_normal_threshold (strict <)
@@ -27,10 +30,13 @@ __device__ __forceinline__ Plane load_plane(const FaceTable& f, int i) {
   return p;
 }
 
-// FCCF.cpp:841-1018.  EMIT=false: only count the hypotheses this match pushes.
+// FCCF.cpp:841-1018 for one matched pair of base pairs, by one warp.  EMIT=false: only count the
+// hypotheses this match pushes.  The rotation (two Rodrigues steps) is computed by every lane; the
+// third-plane combinations c = k3 * F2 + k2 (the reference's loop nest 936-1000) are tested 32 at a time,
+// and a combination's output slot is its ballot rank, i.e. the reference's push_back order.
 template <bool EMIT>
-__device__ int hyp_generate(const FaceTable& f1, const FaceTable& f2, int i11, int i12, int i21, int i22,
-                            float third_thr, float third_cut, float* outT, float* outQ) {
+__device__ int hyp_generate_warp(const FaceTable& f1, const FaceTable& f2, int i11, int i12, int i21, int i22,
+                                 float third_thr, float third_cut, float* outT, float* outQ, int lane) {
   Plane P11 = load_plane(f1, i11), P12 = load_plane(f1, i12), P21 = load_plane(f2, i21), P22 = load_plane(f2, i22);
   f3 n1 = P11.n, m1 = P12.n, n2 = P21.n, m2 = P22.n;
   f3 r1 = cross(n2, n1); normalize(r1);
@@ -55,46 +61,52 @@ __device__ int hyp_generate(const FaceTable& f1, const FaceTable& f2, int i11, i
   f3 n1cm1 = cross(n1, m1); normalize(n1cm1);
   f3 n2cm2 = cross(n2, m2); normalize(n2cm2);
   int count = 0;
-  const int F1 = f1.F, F2 = f2.F;
-  for (int k3 = 0; k3 < F1; k3++) {
-    if (k3 == i11 || k3 == i12) continue;
-    Plane P13 = load_plane(f1, k3);
-    if (!(fabsf(dot(n1cm1, P13.n)) > third_thr)) continue;
-    const double n13 = normal_norm(P13.n.x, P13.n.y, P13.n.z);
-    for (int k2 = 0; k2 < F2; k2++) {
-      if (k2 == i21 || k2 == i22) continue;
-      Plane P2 = load_plane(f2, k2);
-      f3 cn = tf_so3(T, P2.n);     // transformPointCloudWithNormals (FCCF.cpp:948), translation still 0
-      // compute_normal_angel(k1, k2) < third_plane_normal_threshold (FCCF.cpp:949,958) through its cosine cut
-      float c3 = normal_cos_n(P13.n.x, P13.n.y, P13.n.z, n13, cn.x, cn.y, cn.z, normal_norm(cn.x, cn.y, cn.z));
-      if (angle_lt(c3, third_cut) && fabsf(dot(n2cm2, cn)) > third_thr) {
-        if (EMIT) {
-          f3 c23 = tf_se3(T, P2.c);
-          f3 k1 = P13.n, kk2 = cn;
-          float d11 = dot(P11.c, n1), d12 = dot(P12.c, m1), d13 = dot(P13.c, k1);
-          float d21 = dot(P21.c, n2), d22 = dot(P22.c, m2), d23 = dot(c23, kk2);
-          f3 D = mk3(d11 - d21, d12 - d22, d13 - d23);
-          m3 Am; Am.m[0][0] = n1.x; Am.m[0][1] = n1.y; Am.m[0][2] = n1.z; Am.m[1][0] = m1.x; Am.m[1][1] = m1.y; Am.m[1][2] = m1.z;
-          Am.m[2][0] = k1.x; Am.m[2][1] = k1.y; Am.m[2][2] = k1.z;
-          m3 AT;
-#pragma unroll
-          for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) AT.m[i][j] = Am.m[j][i];
-          f3 Tt = mul3v(mul33(inverse33(mul33(AT, Am)), AT), D);
-          float* o = outT + (size_t)count * 12;
-#pragma unroll
-          for (int i = 0; i < 12; i++) o[i] = T[i];
-          o[3] = Tt.x; o[7] = Tt.y; o[11] = Tt.z;
-          float* oq = outQ + (size_t)count * 8;
-          oq[0] = q.w; oq[1] = q.x; oq[2] = q.y; oq[3] = q.z; oq[4] = Tt.x; oq[5] = Tt.y; oq[6] = Tt.z; oq[7] = 0.f;
+  const int F1 = f1.F, F2 = f2.F, NC = F1 * F2;
+  for (int cb = 0; cb < NC; cb += 32) {
+    const int c = cb + lane;
+    bool ok = false;
+    Plane P13, P2; f3 cn = mk3(0, 0, 0);
+    if (c < NC) {
+      const int k3 = c / F2, k2 = c - k3 * F2;
+      if (k3 != i11 && k3 != i12 && k2 != i21 && k2 != i22) {
+        P13 = load_plane(f1, k3);
+        if (fabsf(dot(n1cm1, P13.n)) > third_thr) {
+          const double n13 = normal_norm(P13.n.x, P13.n.y, P13.n.z);
+          P2 = load_plane(f2, k2);
+          cn = tf_so3(T, P2.n);     // transformPointCloudWithNormals (FCCF.cpp:948), translation still 0
+          // compute_normal_angel(k1, k2) < third_plane_normal_threshold (FCCF.cpp:949,958) through its cosine cut
+          float c3 = normal_cos_n(P13.n.x, P13.n.y, P13.n.z, n13, cn.x, cn.y, cn.z, normal_norm(cn.x, cn.y, cn.z));
+          ok = angle_lt(c3, third_cut) && fabsf(dot(n2cm2, cn)) > third_thr;
         }
-        count++;
       }
     }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (EMIT && ok) {
+      const int slot = count + __popc(bal & ((1u << lane) - 1u));
+      f3 c23 = tf_se3(T, P2.c);
+      f3 k1 = P13.n, kk2 = cn;
+      float d11 = dot(P11.c, n1), d12 = dot(P12.c, m1), d13 = dot(P13.c, k1);
+      float d21 = dot(P21.c, n2), d22 = dot(P22.c, m2), d23 = dot(c23, kk2);
+      f3 D = mk3(d11 - d21, d12 - d22, d13 - d23);
+      m3 Am; Am.m[0][0] = n1.x; Am.m[0][1] = n1.y; Am.m[0][2] = n1.z; Am.m[1][0] = m1.x; Am.m[1][1] = m1.y; Am.m[1][2] = m1.z;
+      Am.m[2][0] = k1.x; Am.m[2][1] = k1.y; Am.m[2][2] = k1.z;
+      m3 AT;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) AT.m[i][j] = Am.m[j][i];
+      f3 Tt = mul3v(mul33(inverse33(mul33(AT, Am)), AT), D);
+      float* o = outT + (size_t)slot * 12;
+#pragma unroll
+      for (int i = 0; i < 12; i++) o[i] = T[i];
+      o[3] = Tt.x; o[7] = Tt.y; o[11] = Tt.z;
+      float* oq = outQ + (size_t)slot * 8;
+      oq[0] = q.w; oq[1] = q.x; oq[2] = q.y; oq[3] = q.z; oq[4] = Tt.x; oq[5] = Tt.y; oq[6] = Tt.z; oq[7] = 0.f;
+    }
+    count += __popc(bal);
   }
   if (count == 0) {
-    if (EMIT) {
+    if (EMIT && lane == 0) {
       float sa = P11.size, sb = P12.size, sc = P21.size, sd = P22.size;
       float sx = (P11.c.x * sa + P12.c.x * sb) / (sa + sb);
       float sy = (P11.c.y * sa + P12.c.y * sb) / (sa + sb);
@@ -150,20 +162,58 @@ __global__ void __launch_bounds__(256) base_pairs_kernel(const HypArgs* __restri
 }
 
 // ---- match loop (FCCF.cpp:1415-1427): one thread per (pair of cloud 1, pair of cloud 2): descriptor test
-// (included angle within 5 degrees, same roughness type) and the number of hypotheses the match pushes ----
-__global__ void __launch_bounds__(128) match_count_kernel(const HypArgs* __restrict__ AB) {
+// (included angle within 5 degrees, same roughness type).  match_cnt: 0 / 1 = matched (counted later) ----
+__global__ void __launch_bounds__(128) match_test_kernel(const HypArgs* __restrict__ AB) {
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int B1 = st->base[0].B, B2 = st->base[1].B;
   const int NM = B1 * B2;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= NM) return;
-  int i1 = idx / B2, i2 = idx - i1 * B2;
   const BaseTable &b1 = st->base[0], &b2 = st->base[1];
-  int cnt = 0;
-  if (fabsf(b1.angle[i1] - b2.angle[i2]) < A.same_thr && b1.type[i1] == b2.type[i2] && b1.type[i1] < 3)
-    cnt = hyp_generate<false>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_cut, nullptr, nullptr);
-  A.match_cnt[idx] = cnt;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < NM; idx += gridDim.x * blockDim.x) {
+    int i1 = idx / B2, i2 = idx - i1 * B2;
+    A.match_cnt[idx] = (fabsf(b1.angle[i1] - b2.angle[i2]) < A.same_thr && b1.type[i1] == b2.type[i2] && b1.type[i1] < 3) ? 1 : 0;
+  }
+}
+
+// ---- ordered list of the matched entries (one CTA) ----
+__global__ void __launch_bounds__(1024) match_compact_kernel(const HypArgs* __restrict__ AB) {
+  const HypArgs& A = AB[blockIdx.z];
+  PipeState* st = A.st;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ int s_w[32];
+  __shared__ int s_run;
+  const int NM = st->base[0].B * st->base[1].B;
+  if (t == 0) s_run = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < NM; i0 += 1024) {
+    int idx = i0 + t;
+    bool m = idx < NM && A.match_cnt[idx] != 0;
+    unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_run;
+    for (int w2 = 0; w2 < warp; w2++) off += s_w[w2];
+    if (m) A.mlist[off + __popc(bal & ((1u << lane) - 1u))] = idx;
+    __syncthreads();
+    if (t == 0) { int tot = 0; for (int w2 = 0; w2 < 32; w2++) tot += s_w[w2]; s_run += tot; }
+    __syncthreads();
+  }
+  if (t == 0) { st->n_match = NM; st->tickets[22] = s_run; }     // tickets[22]: number of matched entries
+}
+
+// ---- hypotheses per match: one warp per matched entry ----
+__global__ void __launch_bounds__(128) hyp_count_kernel(const HypArgs* __restrict__ AB) {
+  const HypArgs& A = AB[blockIdx.z];
+  PipeState* st = A.st;
+  const int lane = threadIdx.x & 31;
+  const int B2 = st->base[1].B, M = st->tickets[22];
+  const BaseTable &b1 = st->base[0], &b2 = st->base[1];
+  for (int m = blockIdx.x * 4 + (threadIdx.x >> 5); m < M; m += gridDim.x * 4) {
+    const int idx = A.mlist[m];
+    const int i1 = idx / B2, i2 = idx - i1 * B2;
+    int cnt = hyp_generate_warp<false>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_cut, nullptr, nullptr, lane);
+    if (lane == 0) A.match_cnt[idx] = cnt;
+  }
 }
 
 // ---- ordered scan of the counts per type: pool offsets in the reference's push_back order ----
@@ -209,18 +259,17 @@ __global__ void __launch_bounds__(1024) match_scan_kernel(const HypArgs* __restr
 __global__ void __launch_bounds__(128) emit_hyp_kernel(const HypArgs* __restrict__ AB) {
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
-  const int B2 = st->base[1].B;
-  const int NM = st->n_match;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= NM) return;
+  const int lane = threadIdx.x & 31;
+  const int B2 = st->base[1].B, M = st->tickets[22];
   if (st->hyp_off[3] == 0) return;
-  int cnt = A.match_cnt[idx];
-  if (cnt <= 0) return;
-  int i1 = idx / B2, i2 = idx - i1 * B2;
   const BaseTable &b1 = st->base[0], &b2 = st->base[1];
-  int ty = b1.type[i1];
-  size_t off = (size_t)st->hyp_off[ty] + A.match_off[idx];
-  hyp_generate<true>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_cut, A.hyp_T + off * 12, A.hyp_qt + off * 8);
+  for (int m = blockIdx.x * 4 + (threadIdx.x >> 5); m < M; m += gridDim.x * 4) {
+    const int idx = A.mlist[m];
+    const int i1 = idx / B2, i2 = idx - i1 * B2;
+    const int ty = b1.type[i1];
+    const size_t off = (size_t)st->hyp_off[ty] + A.match_off[idx];
+    hyp_generate_warp<true>(st->ft[0], st->ft[1], b1.i[i1], b1.j[i1], b2.i[i2], b2.j[i2], A.third_thr, A.third_cut, A.hyp_T + off * 12, A.hyp_qt + off * 8, lane);
+  }
 }
 
 void launch_hypotheses(cudaStream_t s, const Batch& b, uint64_t* launches) {
@@ -229,16 +278,20 @@ void launch_hypotheses(cudaStream_t s, const Batch& b, uint64_t* launches) {
   for (int g = 0; g < G; g++) {
     const Work& w = b.w[g]; const HypWS& h = w.h;
     HypArgs& A = As[g];
-    A.st = w.st; A.match_cnt = h.match_cnt; A.match_off = h.match_off; A.hyp_T = h.hyp_T; A.hyp_qt = h.hyp_qt; A.cap_hyp = h.cap_hyp;
+    A.st = w.st; A.match_cnt = h.match_cnt; A.match_off = h.match_off; A.mlist = h.c_state;   // c_state is free until clustering
+    A.hyp_T = h.hyp_T; A.hyp_qt = h.hyp_qt; A.cap_hyp = h.cap_hyp;
     A.tmin = b.p.included_angle_min_threshold; A.tmax = b.p.included_angle_max_threshold; A.rough = b.p.rough_threshold_gl;
     A.same_thr = b.p.included_angle_same_threshold; A.third_thr = b.p.third_plane_threshold; A.third_cut = b.cuts.third_lt;
   }
   const HypArgs* dA = b.tab->put(As.data(), G);
+  const int nbw = grid_x((FCCF_MAXMATCH + 3) / 4, G);     // warp-per-match kernels: 4 warps per CTA, strided over the list
   base_pairs_kernel<<<dim3(1, 1, G), 256, 0, s>>>(dA);
-  match_count_kernel<<<dim3((FCCF_MAXMATCH + 127) / 128, 1, G), 128, 0, s>>>(dA);
+  match_test_kernel<<<dim3(grid_x((FCCF_MAXMATCH + 127) / 128, G), 1, G), 128, 0, s>>>(dA);
+  match_compact_kernel<<<dim3(1, 1, G), 1024, 0, s>>>(dA);
+  hyp_count_kernel<<<dim3(nbw, 1, G), 128, 0, s>>>(dA);
   match_scan_kernel<<<dim3(1, 1, G), 1024, 0, s>>>(dA);
-  emit_hyp_kernel<<<dim3((FCCF_MAXMATCH + 127) / 128, 1, G), 128, 0, s>>>(dA);
-  if (launches) *launches += 4;
+  emit_hyp_kernel<<<dim3(nbw, 1, G), 128, 0, s>>>(dA);
+  if (launches) *launches += 6;
 }
 
 }  // namespace fccf

@@ -39,10 +39,21 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restric
     h[t] = 0;
     __syncthreads();
     const int base = tile * RS_TILE;
+    // keys of one tile are spatially coherent (long runs of equal digits): one shared-memory atomic per
+    // distinct digit of a warp row instead of one per key
+    u64 kk[RS_I];
+#pragma unroll
+    for (int r = 0; r < RS_I; r++) { int i = base + r * RS_T + t; kk[r] = (i < n) ? j.kin[i] : 0ull; }
 #pragma unroll
     for (int r = 0; r < RS_I; r++) {
       int i = base + r * RS_T + t;
-      if (i < n) atomicAdd(&h[(u32)(j.kin[i] >> shift) & mask], 1u);
+      bool valid = i < n;
+      unsigned am = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        u32 d = (u32)(kk[r] >> shift) & mask;
+        unsigned peers = __match_any_sync(am, d);
+        if ((t & 31) == __ffs(peers) - 1) atomicAdd(&h[d], (u32)__popc(peers));
+      }
     }
     __syncthreads();
     j.hist[(size_t)tile * 256 + t] = h[t];
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restric
   }
 }
 
-__global__ void __launch_bounds__(RS_T) rs_scatter_kernel(const SortJobs* __restrict__ JB, int pass, int np, int identity) {
+__global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __restrict__ JB, int pass, int np, int identity) {
   const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;

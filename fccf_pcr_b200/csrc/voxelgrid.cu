@@ -139,9 +139,16 @@ __global__ void __launch_bounds__(128) vg_centroid_kernel(const VGOut* __restric
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += gridDim.x * blockDim.x) {
     const int b = A.seg_start[c][s], e = A.seg_start[c][s + 1];
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    for (int k = b; k < e; k++) {
-      u32 i = idx[k];
-      sx += p[3 * i]; sy += p[3 * i + 1]; sz += p[3 * i + 2];
+    // the sum is sequential (in index order, like pcl::CentroidPoint) but the gathers are not: eight points
+    // of the cell are fetched at once before they are added
+    for (int k = b; k < e; k += 8) {
+      u32 id[8]; float x[8], y[8], z[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) id[u] = (k + u < e) ? idx[k + u] : 0u;
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (k + u < e) { x[u] = p[3 * (size_t)id[u]]; y[u] = p[3 * (size_t)id[u] + 1]; z[u] = p[3 * (size_t)id[u] + 2]; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (k + u < e) { sx += x[u]; sy += y[u]; sz += z[u]; }
     }
     float fn = (float)(e - b);
     A.out[c][3 * s] = sx / fn; A.out[c][3 * s + 1] = sy / fn; A.out[c][3 * s + 2] = sz / fn;
@@ -218,7 +225,7 @@ void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uin
   if (launches) *launches += 2;
   launch_sort(s, dab, dba, ncloud, G, cap, 4, launches);   // result back in keyA / idxA
   launch_segments(s, dsj, ncloud, G, cap, launches);
-  vg_centroid_kernel<<<dim3(grid_x((cap + 127) / 128, G, ncloud), ncloud, G), 128, 0, s>>>(dO);
+  vg_centroid_kernel<<<dim3(grid_x((cap + 127) / 128, G, ncloud, 16384), ncloud, G), 128, 0, s>>>(dO);   // more CTAs per lane: fewer lanes in flight, their clouds stay in L2 while they are gathered from
   if (launches) *launches += 1;
 }
 
