@@ -39,21 +39,10 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restric
     h[t] = 0;
     __syncthreads();
     const int base = tile * RS_TILE;
-    // keys of one tile are spatially coherent (long runs of equal digits): one shared-memory atomic per
-    // distinct digit of a warp row instead of one per key
-    u64 kk[RS_I];
-#pragma unroll
-    for (int r = 0; r < RS_I; r++) { int i = base + r * RS_T + t; kk[r] = (i < n) ? j.kin[i] : 0ull; }
 #pragma unroll
     for (int r = 0; r < RS_I; r++) {
       int i = base + r * RS_T + t;
-      bool valid = i < n;
-      unsigned am = __ballot_sync(0xffffffffu, valid);
-      if (valid) {
-        u32 d = (u32)(kk[r] >> shift) & mask;
-        unsigned peers = __match_any_sync(am, d);
-        if ((t & 31) == __ffs(peers) - 1) atomicAdd(&h[d], (u32)__popc(peers));
-      }
+      if (i < n) atomicAdd(&h[(u32)(j.kin[i] >> shift) & mask], 1u);
     }
     __syncthreads();
     j.hist[(size_t)tile * 256 + t] = h[t];
@@ -65,10 +54,12 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restric
     __threadfence();
     // last tile: hist[b][d] -> exclusive prefix over tiles; row nact = exclusive prefix over digits
     u32 run = 0;
-    for (int b = 0; b < nact; b++) {
-      u32 v = __ldcg(&j.hist[(size_t)b * 256 + t]);
-      j.hist[(size_t)b * 256 + t] = run;
-      run += v;
+    for (int b0 = 0; b0 < nact; b0 += 8) {      // eight independent loads in flight per thread
+      u32 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = (b0 + u < nact) ? __ldcg(&j.hist[(size_t)(b0 + u) * 256 + t]) : 0u;
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (b0 + u < nact) { j.hist[(size_t)(b0 + u) * 256 + t] = run; run += v[u]; }
     }
     h[t] = run;
     __syncthreads();
@@ -89,45 +80,71 @@ __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __r
   const int nact = (n + RS_TILE - 1) / RS_TILE;
   if (pass >= rs_active(*j.nbits, np)) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  __shared__ unsigned short cnt[RS_I * 8][256];
-  __shared__ u32 gbase[256];
+  // cnt: per (round, warp) row digit counters during the ranking; afterwards the same memory stages the
+  // tile in digit order (2048 keys + 2048 values = 24 KB) so that the global writes are coalesced runs
+  __shared__ __align__(16) unsigned char s_raw[RS_I * 8 * 256 * 2];
+  unsigned short (*cnt)[256] = (unsigned short (*)[256])s_raw;
+  u64* skey = (u64*)s_raw; u32* sval = (u32*)(s_raw + RS_TILE * 8);
+  __shared__ u32 gbase[256];      // global offset of the digit, minus the digit's start inside the tile
+  __shared__ u32 dstart[256];     // start of the digit inside the tile
+  __shared__ u32 s_ws[RS_T / 32];
   const int bpp = rs_bpp(*j.nbits, np), shift = pass * bpp;
   const u32 mask = (1u << bpp) - 1u;
   for (int tile = blockIdx.x; tile < nact; tile += gridDim.x) {
-    for (int k = t; k < RS_I * 8 * 256; k += RS_T) (&cnt[0][0])[k] = 0;
+    for (int k = t; k < RS_I * 8 * 256 / 2; k += RS_T) ((u32*)s_raw)[k] = 0u;
     const int base = tile * RS_TILE;
-    gbase[t] = j.hist[(size_t)tile * 256 + t] + j.hist[(size_t)nact * 256 + t];
+    const u32 gb = j.hist[(size_t)tile * 256 + t] + j.hist[(size_t)nact * 256 + t];
     __syncthreads();
     u64 key[RS_I]; u32 val[RS_I]; int dig[RS_I]; int rk[RS_I];
+    // all loads of the tile first (eight keys and values in flight per thread), then the ranking
+#pragma unroll
+    for (int r = 0; r < RS_I; r++) {
+      int i = base + r * RS_T + t;
+      key[r] = (i < n) ? j.kin[i] : 0ull;
+      val[r] = (i < n) ? (identity ? (u32)i : j.vin[i]) : 0u;
+    }
 #pragma unroll
     for (int r = 0; r < RS_I; r++) {
       int i = base + r * RS_T + t;
       bool valid = i < n;
       unsigned am = __ballot_sync(0xffffffffu, valid);
-      dig[r] = -1; rk[r] = 0; key[r] = 0; val[r] = 0;
+      dig[r] = -1; rk[r] = 0;
       if (valid) {
-        key[r] = j.kin[i];
-        val[r] = identity ? (u32)i : j.vin[i];
         dig[r] = (int)((u32)(key[r] >> shift) & mask);
-        unsigned peers = __match_any_sync(am, dig[r]);
+        // lanes of this warp row with the same digit: one ballot per digit bit
+        unsigned peers = am;
+        for (int bb = 0; bb < bpp; bb++) { unsigned bal = __ballot_sync(am, (dig[r] >> bb) & 1); peers &= ((dig[r] >> bb) & 1) ? bal : ~bal; }
         rk[r] = __popc(peers & ((1u << lane) - 1u));
         if (lane == __ffs(peers) - 1) cnt[r * 8 + warp][dig[r]] = (unsigned short)__popc(peers);
       }
     }
     __syncthreads();
-    {
-      u32 run = 0;
+    // digit t: exclusive prefix over the (round, warp) rows, then over the digits of the tile
+    u32 run = 0;
 #pragma unroll 8
-      for (int e = 0; e < RS_I * 8; e++) { u32 c = cnt[e][t]; cnt[e][t] = (unsigned short)run; run += c; }
-    }
+    for (int e = 0; e < RS_I * 8; e++) { u32 c = cnt[e][t]; cnt[e][t] = (unsigned short)run; run += c; }
+    u32 inc = run;
+    for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+    if (lane == 31) s_ws[warp] = inc;
     __syncthreads();
+    u32 woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_ws[w];
+    const u32 ds = woff + inc - run;
+    dstart[t] = ds; gbase[t] = gb - ds;
+    __syncthreads();
+    int lp[RS_I];
 #pragma unroll
-    for (int r = 0; r < RS_I; r++) {
-      if (dig[r] >= 0) {
-        u32 pos = gbase[dig[r]] + cnt[r * 8 + warp][dig[r]] + rk[r];
-        j.kout[pos] = key[r];
-        j.vout[pos] = val[r];
-      }
+    for (int r = 0; r < RS_I; r++) lp[r] = (dig[r] >= 0) ? (int)(dstart[dig[r]] + cnt[r * 8 + warp][dig[r]] + rk[r]) : -1;
+    __syncthreads();                 // every read of cnt is done: the memory becomes the staging area
+#pragma unroll
+    for (int r = 0; r < RS_I; r++) if (lp[r] >= 0) { skey[lp[r]] = key[r]; sval[lp[r]] = val[r]; }
+    __syncthreads();
+    const int ntile = min(RS_TILE, n - base);
+    for (int q = t; q < ntile; q += RS_T) {
+      const u64 k = skey[q];
+      const u32 pos = gbase[(u32)(k >> shift) & mask] + (u32)q;
+      j.kout[pos] = k;
+      j.vout[pos] = sval[q];
     }
     __syncthreads();
   }
