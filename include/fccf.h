@@ -44,7 +44,7 @@ typedef struct fccf_params {
   float seclct_cluster_number;                                        /* :171 */
   float rough_threshold_gl;                                           /* :175 */
   int emulate_pcl_overflow; /* 1: reproduce pcl::VoxelGrid's int32 bail-out (output = input) */
-  int batch_lanes;          /* registrations kept in flight by fccf_register_batch* (0: default 8) */
+  int batch_lanes;          /* registrations per batched launch sequence of fccf_register_batch* (0: default 64); fixed at fccf_create */
   int reserved[2];
 } fccf_params;
 
@@ -83,10 +83,13 @@ int fccf_register(fccf_ctx* ctx, const float* src_xyz, size_t n_src, const float
 int fccf_register_device(fccf_ctx* ctx, const float* d_src_xyz, size_t n_src, const float* d_tar_xyz, size_t n_tar,
                          float leaf, float T_out[16], fccf_timing* timing);
 
-/* Batch of independent pairs (BASELINE config 4): pair b uses src[b]/tar[b]; T_out is B x 16.  Up to
- * params.batch_lanes registrations are in flight at once (one stream + workspace each); results are
- * bit-identical to fccf_register on each pair.  timing: per-stage device times summed over the pairs,
- * total_ms = device time of the whole batch (CUDA events spanning every lane), stage_ms[7] = host wall clock. */
+/* Batch of independent pairs (BASELINE config 4): pair b uses src[b]/tar[b]; T_out is B x 16.  The batch
+ * is cut into chunks of up to params.batch_lanes pairs; a chunk runs as ONE launch sequence (every kernel
+ * launched once for all its pairs, one CUDA graph), and up to four chunks rotate on their own streams so
+ * that the host->device copies of one overlap the compute of the others.  Results are bit-identical to
+ * fccf_register on each pair.  timing: device times summed over the chunks (each figure covers its whole
+ * chunk; divide by the number of pairs for the amortised per-registration figure), total_ms = device time
+ * of the whole batch (CUDA events spanning every chunk), stage_ms[7] = host wall clock of the call. */
 int fccf_register_batch(fccf_ctx* ctx, int n_pairs, const float* const* src_xyz, const size_t* n_src,
                         const float* const* tar_xyz, const size_t* n_tar, float leaf, float* T_out, fccf_timing* timing);
 /* Same with every cloud already resident in device memory (arrays of device pointers, held on the host). */
@@ -122,6 +125,9 @@ int fccf_score_best(fccf_ctx* ctx, size_t index_base, int64_t* packed_host, int6
 /* Per-voxel overlap counts of hypothesis `hyp` of the last fccf_score_hypotheses call: rows of
  * (Lx, Ly, Lz, s, t) for voxels holding both static and moving points; returns rows in *n_rows. */
 int fccf_score_counts(fccf_ctx* ctx, size_t hyp, int32_t* rows, size_t cap_rows, size_t* n_rows);
+
+/* Exhaustive scoring: set params.fine_verify_number >= 256 — every cluster centre is refined
+ * and fine-verified instead of the reference's 4 per type; no separate entry point is needed. */
 
 /* replaces: quick_verify + ceres_refine (FCCF.cpp:680-783, 210-249) for H hypotheses given two plane
  * tables (F x 7 floats: centroid, normal, point size).  T is updated in place (refined);
