@@ -62,24 +62,38 @@ __device__ int hyp_generate_warp(const FaceTable& f1, const FaceTable& f2, int i
   f3 n2cm2 = cross(n2, m2); normalize(n2cm2);
   int count = 0;
   const int F1 = f1.F, F2 = f2.F, NC = F1 * F2;
+  // Per-plane parts of the combination test, once per match: lane l < 16 holds candidate l of cloud 1
+  // (normal, its double norm, "far enough from n1 x m1") and candidate l of cloud 2 (rotated normal, its
+  // double norm, "far enough from n2 x m2"); the combinations fetch them with shuffles.
+  f3 a_n = mk3(0, 0, 0), b_n = mk3(0, 0, 0); double a_nn = 1.0, b_nn = 1.0; int a_ok = 0, b_ok = 0;
+  if (lane < F1) {
+    a_n = mk3(f1.plane[lane][3], f1.plane[lane][4], f1.plane[lane][5]);
+    a_nn = normal_norm(a_n.x, a_n.y, a_n.z);
+    a_ok = (lane != i11 && lane != i12 && fabsf(dot(n1cm1, a_n)) > third_thr) ? 1 : 0;
+  }
+  if (lane < F2) {
+    b_n = tf_so3(T, mk3(f2.plane[lane][3], f2.plane[lane][4], f2.plane[lane][5]));     // transformPointCloudWithNormals (FCCF.cpp:948), translation still 0
+    b_nn = normal_norm(b_n.x, b_n.y, b_n.z);
+    b_ok = (lane != i21 && lane != i22 && fabsf(dot(n2cm2, b_n)) > third_thr) ? 1 : 0;
+  }
   for (int cb = 0; cb < NC; cb += 32) {
     const int c = cb + lane;
+    const int cc = c < NC ? c : 0;
+    const int k3 = cc / F2, k2 = cc - k3 * F2;
+    const f3 pn = mk3(__shfl_sync(0xffffffffu, a_n.x, k3), __shfl_sync(0xffffffffu, a_n.y, k3), __shfl_sync(0xffffffffu, a_n.z, k3));
+    const double n13 = __shfl_sync(0xffffffffu, a_nn, k3);
+    const int ok3 = __shfl_sync(0xffffffffu, a_ok, k3);
+    const f3 cn = mk3(__shfl_sync(0xffffffffu, b_n.x, k2), __shfl_sync(0xffffffffu, b_n.y, k2), __shfl_sync(0xffffffffu, b_n.z, k2));
+    const double n2n = __shfl_sync(0xffffffffu, b_nn, k2);
+    const int ok2 = __shfl_sync(0xffffffffu, b_ok, k2);
     bool ok = false;
-    Plane P13, P2; f3 cn = mk3(0, 0, 0);
-    if (c < NC) {
-      const int k3 = c / F2, k2 = c - k3 * F2;
-      if (k3 != i11 && k3 != i12 && k2 != i21 && k2 != i22) {
-        P13 = load_plane(f1, k3);
-        if (fabsf(dot(n1cm1, P13.n)) > third_thr) {
-          const double n13 = normal_norm(P13.n.x, P13.n.y, P13.n.z);
-          P2 = load_plane(f2, k2);
-          cn = tf_so3(T, P2.n);     // transformPointCloudWithNormals (FCCF.cpp:948), translation still 0
-          // compute_normal_angel(k1, k2) < third_plane_normal_threshold (FCCF.cpp:949,958) through its cosine cut
-          float c3 = normal_cos_n(P13.n.x, P13.n.y, P13.n.z, n13, cn.x, cn.y, cn.z, normal_norm(cn.x, cn.y, cn.z));
-          ok = angle_lt(c3, third_cut) && fabsf(dot(n2cm2, cn)) > third_thr;
-        }
-      }
+    if (c < NC && ok3 && ok2) {
+      // compute_normal_angel(k1, k2) < third_plane_normal_threshold (FCCF.cpp:949,958) through its cosine cut
+      float c3 = normal_cos_n(pn.x, pn.y, pn.z, n13, cn.x, cn.y, cn.z, n2n);
+      ok = angle_lt(c3, third_cut);
     }
+    Plane P13, P2;
+    if (EMIT && ok) { P13 = load_plane(f1, k3); P2 = load_plane(f2, k2); }
     const unsigned bal = __ballot_sync(0xffffffffu, ok);
     if (EMIT && ok) {
       const int slot = count + __popc(bal & ((1u << lane) - 1u));
