@@ -504,3 +504,36 @@ def test_exhaustive_scoring_mode(oracle_mod):
     assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
     assert scenes.rotation_error_deg(Tg, Tgt) < 1.0 and scenes.translation_error(Tg, Tgt) < 0.08
     c.close()
+
+
+def test_batch_mixed_sizes_nan_and_parameter_changes(oracle_mod):
+    """Batches whose pairs differ in size (capacity growth drops the captured graphs), contain non-finite
+    points and an empty cloud, and a parameter change between calls (graphs re-captured): every matrix equals
+    the single-pair call, which equals the oracle."""
+    import fccf_pcr_b200 as fccf
+
+    rng = np.random.default_rng(5)
+    pairs = [scenes.make_pair("indoor", n, s)[:2] for n, s in ((20000, 7), (50000, 1), (3000, 9), (20000, 8), (35000, 4))]
+    src_nan = pairs[0][0].copy(); src_nan[rng.integers(0, len(src_nan), 50)] = np.nan; src_nan[7, 1] = np.inf
+    pairs.append((src_nan, pairs[0][1]))
+    pairs.append((np.zeros((0, 3), np.float32), pairs[1][1]))          # empty source cloud
+    c = fccf.Context(0, batch_lanes=3)                                 # 7 pairs -> chunks of 3, 3, 1 over rotating groups
+    Tb = c.register_batch([p[0] for p in pairs], [p[1] for p in pairs], 0.1)
+    o = oracle_mod.Oracle()
+    for k, (a, b) in enumerate(pairs):
+        Ts = c.register(a, b, 0.1)
+        assert np.array_equal(Tb[k], Ts, equal_nan=True), k
+        To = o.register(a, b, 0.1)
+        assert np.array_equal(np.isnan(Ts), np.isnan(To)), k
+        if not np.isnan(To).any() and np.any(To[:3, :3]):
+            assert scenes.rotation_error_deg(Ts, To) <= 0.01 and scenes.translation_error(Ts, To) <= 1e-3, k
+    # parameter change: the captured graphs hold the old values and must be rebuilt
+    c.set_params(select_plane_number=7, cluster_distance_threshold=0.5)
+    o2 = oracle_mod.Oracle(select_plane_number=7, cluster_distance_threshold=0.5)
+    T1 = c.register(pairs[1][0], pairs[1][1], 0.1)
+    To = o2.register(pairs[1][0], pairs[1][1], 0.1)
+    assert np.array_equal(c.blob("n_hyp"), o2.blob("n_hyp")) and np.array_equal(c.blob("n_centres"), o2.blob("n_centres"))
+    assert scenes.rotation_error_deg(T1, To) <= 0.01 and scenes.translation_error(T1, To) <= 1e-3
+    Tb2 = c.register_batch([pairs[1][0], pairs[3][0]], [pairs[1][1], pairs[3][1]], 0.1)
+    assert np.array_equal(Tb2[0], T1)
+    c.close()
