@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_warp_kernel(const ScArgs*
     const float4 r0 = __ldg(Tp), r1 = __ldg(Tp + 1), r2 = __ldg(Tp + 2);
     for (int i = lane; i < P.row_words; i += 32) row[i] = 0u;
     __syncwarp();
-#pragma unroll 2
+#pragma unroll 4
     for (int i = lane; i < n2; i += 32) {
       const float px = s2[3 * i], py = s2[3 * i + 1], pz = s2[3 * i + 2];
       // pcl::transformPointCloud (SSE order): x*c0 + (y*c1 + (z*c2 + c3))
