@@ -114,6 +114,21 @@ def default_params(**over):
     return p
 
 
+class HostBatch:
+    """Host clouds of a batch with their C argument arrays (see Context.prepare_batch)."""
+
+    def __init__(self, srcs, tars):
+        self.n = n = len(srcs)
+        self.srcs = [np.ascontiguousarray(a, np.float32) for a in srcs]      # keeps the buffers alive
+        self.tars = [np.ascontiguousarray(a, np.float32) for a in tars]
+        fp = C.POINTER(C.c_float)
+        self.sp = (fp * n)(*[_f(a) for a in self.srcs])
+        self.tp = (fp * n)(*[_f(a) for a in self.tars])
+        self.ns = (C.c_size_t * n)(*[len(a) for a in self.srcs])
+        self.nt = (C.c_size_t * n)(*[len(a) for a in self.tars])
+        self.T = np.zeros((n, 16), np.float32)
+
+
 class Context:
     """One registration context on one GPU (fccf_ctx)."""
 
@@ -175,6 +190,15 @@ class Context:
         T = np.zeros((n, 16), np.float32)
         self._check(self.L.fccf_register_batch(self.h, n, sp, ns, tp, nt, C.c_float(leaf), _f(T), C.byref(self.timing)))
         return T.reshape(n, 4, 4)
+
+    def prepare_batch(self, srcs, tars):
+        """Argument block of fccf_register_batch for host clouds, built once: the pointer / size arrays a C
+        caller would hold anyway (building them through ctypes costs milliseconds for hundreds of pairs)."""
+        return HostBatch(srcs, tars)
+
+    def register_batch_prepared(self, hb, leaf):
+        self._check(self.L.fccf_register_batch(self.h, hb.n, hb.sp, hb.ns, hb.tp, hb.nt, C.c_float(leaf), _f(hb.T), C.byref(self.timing)))
+        return hb.T.reshape(hb.n, 4, 4)
 
     def register_batch_device(self, d_src_ptrs, n_srcs, d_tar_ptrs, n_tars, leaf):
         n = len(d_src_ptrs)
