@@ -28,11 +28,9 @@ __device__ __forceinline__ double bfly(double v) {
   return v;
 }
 __device__ __forceinline__ void crossd(const double a[3], const double b[3], double o[3]) {
-  // explicit FMAs (the library is built with -fmad=false for the bit-exact float32 stages; the FP64
-  // refinement is tolerance-checked and the fused forms halve its dependent instruction chains)
-  o[0] = fma(a[1], b[2], -(a[2] * b[1])); o[1] = fma(a[2], b[0], -(a[0] * b[2])); o[2] = fma(a[0], b[1], -(a[1] * b[0]));
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
 }
-__device__ __forceinline__ double dot3d(const double a[3], const double b[3]) { return fma(a[0], b[0], fma(a[1], b[1], a[2] * b[2])); }
+__device__ __forceinline__ double dot3d(const double a[3], const double b[3]) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
 
 // f(q,a) = a + w*uv + u x uv, uv = 2 (u x a); Jacobian wrt (x,y,z,w)
 __device__ __forceinline__ void rot_with_jac(const double q[4], const double a[3], double f[3], double J[3][4], bool want) {
@@ -40,7 +38,7 @@ __device__ __forceinline__ void rot_with_jac(const double q[4], const double a[3
   double uv[3]; crossd(u, a, uv); uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
   double c2[3]; crossd(u, uv, c2);
   #pragma unroll
-  for (int i = 0; i < 3; i++) f[i] = fma(w, uv[i], a[i]) + c2[i];
+  for (int i = 0; i < 3; i++) f[i] = (a[i] + w * uv[i]) + c2[i];
   if (!want) return;
   #pragma unroll
   for (int k = 0; k < 3; k++) {
@@ -48,7 +46,7 @@ __device__ __forceinline__ void rot_with_jac(const double q[4], const double a[3
     double Av[3]; crossd(e, a, Av); Av[0] *= 2; Av[1] *= 2; Av[2] *= 2;
     double t1[3], t2[3]; crossd(e, uv, t1); crossd(u, Av, t2);
     #pragma unroll
-    for (int i = 0; i < 3; i++) J[i][k] = fma(w, Av[i], t1[i]) + t2[i];
+    for (int i = 0; i < 3; i++) J[i][k] = w * Av[i] + t1[i] + t2[i];
   }
   #pragma unroll
   for (int i = 0; i < 3; i++) J[i][3] = uv[i];
@@ -87,7 +85,7 @@ __device__ __forceinline__ bool lm_eval(const LmRow& R, const double x[7], doubl
       // EigenQuaternionParameterization::ComputeJacobian (4x3)
       double Pm[4][3] = {{q[3], q[2], -q[1]}, {-q[2], q[3], q[0]}, {q[1], -q[0], q[3]}, {-q[0], -q[1], -q[2]}};
       #pragma unroll
-      for (int lc = 0; lc < 3; lc++) { double s = 0; for (int a = 0; a < 4; a++) s = fma(Ja[a], Pm[a][lc], s); J[lc] = s; }
+      for (int lc = 0; lc < 3; lc++) { double s = 0; for (int a = 0; a < 4; a++) s += Ja[a] * Pm[a][lc]; J[lc] = s; }
       #pragma unroll
       for (int lc = 0; lc < 3; lc++) J[3 + lc] = Ja[4 + lc];
       #pragma unroll
@@ -119,28 +117,28 @@ __device__ __forceinline__ bool lm_qr_solve(double A[6], double b, double B[6], 
   for (int k = 0; k < 6; k++) {
     double mk = (lane >= k) ? A[k] : 0.0;
     double ak = aug ? B[k] : 0.0;
-    double nrm = sqrt(bfly(fma(mk, mk, ak * ak)));
+    double nrm = sqrt(bfly(mk * mk + ak * ak));
     if (nrm == 0.0) return false;
     double akk = __shfl_sync(0xffffffffu, A[k], k);
     double alpha = (akk > 0) ? -nrm : nrm;
     double v0 = akk - alpha;
     double vm = (lane == k) ? v0 : mk;     // Householder vector entries of this lane's rows
     double va = ak;
-    double vtv = bfly(fma(vm, vm, va * va));
+    double vtv = bfly(vm * vm + va * va);
     if (vtv == 0.0) return false;
     double beta = 2.0 / vtv;
     #pragma unroll
     for (int j = k + 1; j < 6; j++) {
-      double s = bfly(fma(vm, A[j], va * (aug ? B[j] : 0.0)));
+      double s = bfly(vm * A[j] + va * (aug ? B[j] : 0.0));
       s *= beta;
-      A[j] = fma(-s, vm, A[j]);
-      if (aug) B[j] = fma(-s, va, B[j]);
+      A[j] -= s * vm;
+      if (aug) B[j] -= s * va;
     }
     {
-      double s = bfly(fma(vm, b, va * bb));
+      double s = bfly(vm * b + va * bb);
       s *= beta;
-      b = fma(-s, vm, b);
-      if (aug) bb = fma(-s, va, bb);
+      b -= s * vm;
+      if (aug) bb -= s * va;
     }
     if (lane == k) A[k] = alpha;
   }
@@ -149,7 +147,7 @@ __device__ __forceinline__ bool lm_qr_solve(double A[6], double b, double B[6], 
   for (int k = 5; k >= 0; k--) {
     double s = b;
     #pragma unroll
-    for (int j = k + 1; j < 6; j++) s = fma(-A[j], y[j], s);
+    for (int j = k + 1; j < 6; j++) s -= A[j] * y[j];
     s = s / A[k];
     y[k] = __shfl_sync(0xffffffffu, s, k);
     ok = ok && isfinite(y[k]);

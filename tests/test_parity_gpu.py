@@ -537,3 +537,44 @@ def test_batch_mixed_sizes_nan_and_parameter_changes(oracle_mod):
     Tb2 = c.register_batch([pairs[1][0], pairs[3][0]], [pairs[1][1], pairs[3][1]], 0.1)
     assert np.array_equal(Tb2[0], T1)
     c.close()
+
+
+def test_large_hypothesis_pool_global_memory_clustering(oracle_mod):
+    """A pool of more than 3072 hypotheses takes the clustering kernel's global-memory path (no shared-memory
+    working set, no neighbour lists): seeds, sizes, sort and centres against the oracle."""
+    import fccf_pcr_b200 as fccf
+
+    prm = dict(third_plane_threshold=0.05, included_angle_same_threshold=15.0)
+    src, tar, _ = scenes.make_pair("indoor", 100000, 21)
+    o = oracle_mod.Oracle(**prm)
+    To = o.register(src, tar, 0.1)
+    c = fccf.Context(0, **prm)
+    Tg = c.register(src, tar, 0.1)
+    assert int(c.blob("n_hyp")[0]) > 3072
+    for name in ["matches", "n_hyp", "n_centres", "cluster_num", "cluster_seed_sorted0", "cluster_size_sorted0", "cluster_seed_sorted2", "cluster_size_sorted2",
+                 "top_centre0", "top_centre2"]:
+        assert np.array_equal(c.blob(name), o.blob(name)), name
+    assert _rel_rows(c.blob("centre0"), o.blob("centre0"), 7, [[0, 1, 2, 3], [4, 5, 6]]) <= 1e-4
+    assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
+    c.close()
+
+
+def test_batch_of_outdoor_pairs(oracle_mod):
+    """Batched launch sequences on outdoor clouds (thousands of planar voxels per cloud: the 256-thread
+    face-growing CTAs of batched launches sweep them in many chunks): bit-identical to the single calls,
+    integer stages equal to the oracle."""
+    import fccf_pcr_b200 as fccf
+
+    prm = dict(face_voxel_size=4.0, fine_verify_voxel_size=2.0)
+    pairs = [scenes.make_pair("outdoor", 300000, s)[:2] for s in (3, 4, 5, 6, 7, 8, 9, 10)]
+    c = fccf.Context(0, batch_lanes=8, **prm)
+    Tb = c.register_batch([p[0] for p in pairs], [p[1] for p in pairs], 0.5)
+    o = oracle_mod.Oracle(**prm)
+    for k in (0, 1, 7):
+        Ts = c.register(pairs[k][0], pairs[k][1], 0.5)
+        assert np.array_equal(Tb[k], Ts, equal_nan=True), k
+        To = o.register(pairs[k][0], pairs[k][1], 0.5)
+        for name in ["vox_cnt1", "merge_label1", "merge_label2", "face_id1", "base1", "base2", "matches", "n_hyp", "n_centres"]:
+            assert np.array_equal(c.blob(name), o.blob(name)), (k, name)
+        assert scenes.rotation_error_deg(Ts, To) <= 0.01 and scenes.translation_error(Ts, To) <= 1e-3, k
+    c.close()
