@@ -449,7 +449,7 @@ void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches) {
   cluster_prep_kernel<<<dim3(grid_x((cap + 255) / 256, G), 1, G), 256, 0, s>>>(dA);
   if (launches) *launches += 1;
   // 34-bit keys: 6 passes of 6 bits (even pass count: result back in ckeyA / cidxA)
-  launch_sort(s, dab, dba, 1, G, cap, 6, launches);
+  launch_sort(s, dab, dba, 1, G, cap, 6, 8, launches);
   cluster_xs_kernel<<<dim3(grid_x((cap + 255) / 256, G), 1, G), 256, 0, s>>>(dA);
   cluster_kernel<<<dim3(3, 1, G), 1024, CL_SMEM_BYTES, s>>>(dA);
   if (launches) *launches += 2;

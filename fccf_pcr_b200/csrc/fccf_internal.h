@@ -92,14 +92,14 @@ struct PipeState {
 };
 
 struct SortJob {
-  const u64* kin; u64* kout; const u32* vin; u32* vout;   // pass 0 uses the element index as value
+  const void* kin; void* kout; const u32* vin; u32* vout;   // keys: u32 or u64 (launch_sort's key_bytes); pass 0 uses the element index as value
   const int* n; const int* nbits;
   u32* hist;     // [(nblocks_cap + 1) * 256]
   int* ticket;
 };
 struct SortJobs { SortJob j[3]; };
 struct SegJob {
-  const u64* keys; const int* n; int* seg_start; int* nseg; u32* blk; int* ticket;
+  const void* keys; const int* n; int* seg_start; int* nseg; u32* blk; int* ticket;
 };
 struct SegJobs { SegJob j[3]; };
 
@@ -141,9 +141,9 @@ inline int grid_x(int nb_cap, int G, int njobs = 1, int budget = 4096) {
 // `np` passes of ceil(nbits/np) <= 8 bits.  Result ends in (kout,vout) of the last pass; the
 // launcher ping-pongs between the two buffer sets given in `a` and `b` (np even: result in a).
 // jobs_ab / jobs_ba: device tables of G entries.
-void launch_sort(cudaStream_t s, const SortJobs* jobs_ab, const SortJobs* jobs_ba, int njobs, int G, int cap, int np, uint64_t* launches);
+void launch_sort(cudaStream_t s, const SortJobs* jobs_ab, const SortJobs* jobs_ba, int njobs, int G, int cap, int np, int key_bytes, uint64_t* launches);
 // segment heads of a sorted key array: seg_start[0..nseg], nseg
-void launch_segments(cudaStream_t s, const SegJobs* jobs, int njobs, int G, int cap, uint64_t* launches);
+void launch_segments(cudaStream_t s, const SegJobs* jobs, int njobs, int G, int cap, int key_bytes, uint64_t* launches);
 
 // per-cloud device buffers
 struct CloudWS {

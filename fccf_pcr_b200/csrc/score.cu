@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) score_keys_kernel(const ScArgs* __restric
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int l[3];
     sc_lattice(ss, res, A.s1[3 * i], A.s1[3 * i + 1], A.s1[3 * i + 2], l);
-    A.ws.keyA[i] = (u64)sc_compact(ss, l);
+    ((u32*)A.ws.keyA)[i] = sc_compact(ss, l);
   }
 }
 
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) score_table_kernel(const ScArgs* __restri
   if (P.mode == 0) for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (P.cells + 1) / 2; i += gridDim.x * blockDim.x) ((u32*)A.ws.dense)[i] = 0xffffffffu;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nocc; v += gridDim.x * blockDim.x) {
     int b = A.ws.seg_start[v], e = A.ws.seg_start[v + 1];
-    A.ws.vkey[v] = (u32)A.ws.keyA[b];
+    A.ws.vkey[v] = ((const u32*)A.ws.keyA)[b];
     A.ws.s_cnt[v] = e - b;
   }
 }
@@ -486,8 +486,8 @@ void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJo
   score_bbox_kernel<<<dim3(nb, 1, G), 256, 0, s>>>(dA);
   score_keys_kernel<<<dim3(nb, 1, G), 256, 0, s>>>(dA);
   if (launches) *launches += 3;
-  launch_sort(s, dab, dba, 1, G, cap, 4, launches);
-  launch_segments(s, dsj, 1, G, cap, launches);
+  launch_sort(s, dab, dba, 1, G, cap, 4, 4, launches);
+  launch_segments(s, dsj, 1, G, cap, 4, launches);
   int nbh = (cap_hash + 255) / 256; if (nbh > 1184) nbh = 1184;
   nbh = grid_x(nbh, G);
   score_table_kernel<<<dim3(nbh, 1, G), 256, 0, s>>>(dA);

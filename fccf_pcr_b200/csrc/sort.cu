@@ -16,17 +16,26 @@
 
 namespace fccf {
 
-// Passes that do work: keys of up to 16 bits (every indoor-scale voxel grid) need only the first two of
-// the launched passes — the rest exit at once, and the result is where an even pass count leaves it.
-__device__ __forceinline__ int rs_active(int nbits, int np) { return (np >= 4 && (np & 1) == 0 && nbits <= 16) ? 2 : np; }
+// Passes that do work: ceil(nbits / 8) rounded up to an even count (so that the result lands where an even
+// pass count leaves it) — keys of up to 16 bits (every indoor-scale voxel grid) need only the first two of
+// the launched passes; the rest exit at once.  np (launched passes, even) must cover the widest key the
+// caller can produce: 4 for 32-bit keys, 6 for the 34-bit cluster keys, 8 for 64-bit cell keys.
+__device__ __forceinline__ int rs_active(int nbits, int np) {
+  int na = (nbits + 7) / 8;
+  if (na < 2) na = 2;
+  na += na & 1;
+  return ((np & 1) || na > np) ? np : na;
+}
 __device__ __forceinline__ int rs_bpp(int nbits, int np) {
   int na = rs_active(nbits, np);
   int b = (nbits + na - 1) / na;
   return b < 1 ? 1 : (b > 8 ? 8 : b);
 }
 
+template <typename KT>
 __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restrict__ JB, int pass, int np) {
   const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
+  const KT* __restrict__ kin = (const KT*)j.kin;
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
   if (pass >= rs_active(*j.nbits, np)) return;
@@ -42,7 +51,7 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restric
 #pragma unroll
     for (int r = 0; r < RS_I; r++) {
       int i = base + r * RS_T + t;
-      if (i < n) atomicAdd(&h[(u32)(j.kin[i] >> shift) & mask], 1u);
+      if (i < n) atomicAdd(&h[(u32)(kin[i] >> shift) & mask], 1u);
     }
     __syncthreads();
     j.hist[(size_t)tile * 256 + t] = h[t];
@@ -74,8 +83,10 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restric
   }
 }
 
+template <typename KT>
 __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __restrict__ JB, int pass, int np, int identity) {
   const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
+  const KT* __restrict__ kin = (const KT*)j.kin; KT* __restrict__ kout = (KT*)j.kout;
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
   if (pass >= rs_active(*j.nbits, np)) return;
@@ -84,7 +95,7 @@ __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __r
   // tile in digit order (2048 keys + 2048 values = 24 KB) so that the global writes are coalesced runs
   __shared__ __align__(16) unsigned char s_raw[RS_I * 8 * 256 * 2];
   unsigned short (*cnt)[256] = (unsigned short (*)[256])s_raw;
-  u64* skey = (u64*)s_raw; u32* sval = (u32*)(s_raw + RS_TILE * 8);
+  KT* skey = (KT*)s_raw; u32* sval = (u32*)(s_raw + RS_TILE * sizeof(KT));
   __shared__ u32 gbase[256];      // global offset of the digit, minus the digit's start inside the tile
   __shared__ u32 dstart[256];     // start of the digit inside the tile
   __shared__ u32 s_ws[RS_T / 32];
@@ -95,12 +106,12 @@ __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __r
     const int base = tile * RS_TILE;
     const u32 gb = j.hist[(size_t)tile * 256 + t] + j.hist[(size_t)nact * 256 + t];
     __syncthreads();
-    u64 key[RS_I]; u32 val[RS_I]; int dig[RS_I]; int rk[RS_I];
+    KT key[RS_I]; u32 val[RS_I]; int dig[RS_I]; int rk[RS_I];
     // all loads of the tile first (eight keys and values in flight per thread), then the ranking
 #pragma unroll
     for (int r = 0; r < RS_I; r++) {
       int i = base + r * RS_T + t;
-      key[r] = (i < n) ? j.kin[i] : 0ull;
+      key[r] = (i < n) ? kin[i] : (KT)0;
       val[r] = (i < n) ? (identity ? (u32)i : j.vin[i]) : 0u;
     }
 #pragma unroll
@@ -141,21 +152,26 @@ __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __r
     __syncthreads();
     const int ntile = min(RS_TILE, n - base);
     for (int q = t; q < ntile; q += RS_T) {
-      const u64 k = skey[q];
+      const KT k = skey[q];
       const u32 pos = gbase[(u32)(k >> shift) & mask] + (u32)q;
-      j.kout[pos] = k;
+      kout[pos] = k;
       j.vout[pos] = sval[q];
     }
     __syncthreads();
   }
 }
 
-void launch_sort(cudaStream_t s, const SortJobs* ab, const SortJobs* ba, int njobs, int G, int cap, int np, uint64_t* launches) {
+void launch_sort(cudaStream_t s, const SortJobs* ab, const SortJobs* ba, int njobs, int G, int cap, int np, int key_bytes, uint64_t* launches) {
   dim3 grid(grid_x((cap + RS_TILE - 1) / RS_TILE, G, njobs), njobs, G);
   for (int p = 0; p < np; p++) {
     const SortJobs* J = (p & 1) ? ba : ab;
-    rs_hist_kernel<<<grid, RS_T, 0, s>>>(J, p, np);
-    rs_scatter_kernel<<<grid, RS_T, 0, s>>>(J, p, np, p == 0 ? 1 : 0);
+    if (key_bytes == 4) {
+      rs_hist_kernel<u32><<<grid, RS_T, 0, s>>>(J, p, np);
+      rs_scatter_kernel<u32><<<grid, RS_T, 0, s>>>(J, p, np, p == 0 ? 1 : 0);
+    } else {
+      rs_hist_kernel<u64><<<grid, RS_T, 0, s>>>(J, p, np);
+      rs_scatter_kernel<u64><<<grid, RS_T, 0, s>>>(J, p, np, p == 0 ? 1 : 0);
+    }
     if (launches) *launches += 2;
   }
 }
@@ -163,10 +179,13 @@ void launch_sort(cudaStream_t s, const SortJobs* ab, const SortJobs* ba, int njo
 // ------------------------------------------------------------------------------------------
 // segment heads of a sorted key array (one segment per distinct key), order preserving
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool seg_is_head(const u64* keys, int i) { return i == 0 || keys[i] != keys[i - 1]; }
+template <typename KT>
+__device__ __forceinline__ bool seg_is_head(const KT* keys, int i) { return i == 0 || keys[i] != keys[i - 1]; }
 
+template <typename KT>
 __global__ void __launch_bounds__(RS_T) seg_count_kernel(const SegJobs* __restrict__ JB) {
   const SegJob& j = JB[blockIdx.z].j[blockIdx.y];
+  const KT* __restrict__ keys = (const KT*)j.keys;
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
   const int t = threadIdx.x;
@@ -179,7 +198,7 @@ __global__ void __launch_bounds__(RS_T) seg_count_kernel(const SegJobs* __restri
     const int base = tile * RS_TILE;
     int c = 0;
 #pragma unroll
-    for (int r = 0; r < RS_I; r++) { int i = base + r * RS_T + t; if (i < n && seg_is_head(j.keys, i)) c++; }
+    for (int r = 0; r < RS_I; r++) { int i = base + r * RS_T + t; if (i < n && seg_is_head(keys, i)) c++; }
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((t & 31) == 0) s_cnt[t >> 5] = c;
     __syncthreads();
@@ -212,8 +231,10 @@ __global__ void __launch_bounds__(RS_T) seg_count_kernel(const SegJobs* __restri
   }
 }
 
+template <typename KT>
 __global__ void __launch_bounds__(RS_T) seg_write_kernel(const SegJobs* __restrict__ JB) {
   const SegJob& j = JB[blockIdx.z].j[blockIdx.y];
+  const KT* __restrict__ keys = (const KT*)j.keys;
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -225,7 +246,7 @@ __global__ void __launch_bounds__(RS_T) seg_write_kernel(const SegJobs* __restri
     const int base = tile * RS_TILE;
     for (int r = 0; r < RS_I; r++) {
       int i = base + r * RS_T + t;
-      bool head = (i < n) && seg_is_head(j.keys, i);
+      bool head = (i < n) && seg_is_head(keys, i);
       unsigned b = __ballot_sync(0xffffffffu, head);
       if (lane == 0) s_w[warp] = __popc(b);
       __syncthreads();
@@ -239,10 +260,10 @@ __global__ void __launch_bounds__(RS_T) seg_write_kernel(const SegJobs* __restri
   }
 }
 
-void launch_segments(cudaStream_t s, const SegJobs* jobs, int njobs, int G, int cap, uint64_t* launches) {
+void launch_segments(cudaStream_t s, const SegJobs* jobs, int njobs, int G, int cap, int key_bytes, uint64_t* launches) {
   dim3 grid(grid_x((cap + RS_TILE - 1) / RS_TILE, G, njobs), njobs, G);
-  seg_count_kernel<<<grid, RS_T, 0, s>>>(jobs);
-  seg_write_kernel<<<grid, RS_T, 0, s>>>(jobs);
+  if (key_bytes == 4) { seg_count_kernel<u32><<<grid, RS_T, 0, s>>>(jobs); seg_write_kernel<u32><<<grid, RS_T, 0, s>>>(jobs); }
+  else { seg_count_kernel<u64><<<grid, RS_T, 0, s>>>(jobs); seg_write_kernel<u64><<<grid, RS_T, 0, s>>>(jobs); }
   if (launches) *launches += 2;
 }
 

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) vg_minmax_kernel(const VGArgs* __restrict
   st->nbits = nbits < 1 ? 1 : nbits;
 }
 
+template <typename KT>
 __global__ void __launch_bounds__(256) vg_keys_kernel(const VGArgs* __restrict__ AB) {
   const VGArgs& A = AB[blockIdx.z];
   const int c = blockIdx.y;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256) vg_keys_kernel(const VGArgs* __restrict__
       int i2 = (int)(floorf(z * inv) - mb2);
       key = (u64)((long long)i0 + (long long)i1 * d0 + (long long)i2 * d01);
     }
-    A.keys[c][i] = key;
+    ((KT*)A.keys[c])[i] = (KT)key;
   }
 }
 
@@ -129,6 +130,7 @@ struct VGOut {
 };
 
 // one thread per occupied cell: in-order float32 running sum (pcl::CentroidPoint<PointXYZ>)
+template <typename KT>
 __global__ void __launch_bounds__(128) vg_centroid_kernel(const VGOut* __restrict__ AB) {
   const VGOut& A = AB[blockIdx.z];
   const int c = blockIdx.y;
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(128) vg_centroid_kernel(const VGOut* __restric
     }
     float fn = (float)(e - b);
     A.out[c][3 * s] = sx / fn; A.out[c][3 * s + 1] = sy / fn; A.out[c][3 * s + 2] = sz / fn;
-    A.cell[c][s] = (long long)A.keys[c][b];
+    A.cell[c][s] = (long long)((const KT*)A.keys[c])[b];
     A.cnt[c][s] = e - b;
   }
 }
@@ -221,11 +223,19 @@ void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uin
   int nb_mm = (cap + 256 * 8 - 1) / (256 * 8);
   if (nb_mm > 592) nb_mm = 592;
   vg_minmax_kernel<<<dim3(grid_x(nb_mm, G, ncloud), ncloud, G), 256, 0, s>>>(dA);
-  vg_keys_kernel<<<dim3(grid_x((cap + 255) / 256, G, ncloud), ncloud, G), 256, 0, s>>>(dA);
+  // With pcl::VoxelGrid's int32 overflow bail-out emulated, every key (cell index, point index when bailing
+  // out, "non-finite" = number of cells) fits 32 bits: the sort moves 4-byte keys.  Without it cells may
+  // need the full 64 bits.
+  const int kb = b.p.emulate_pcl_overflow ? 4 : 8;
+  if (kb == 4) vg_keys_kernel<u32><<<dim3(grid_x((cap + 255) / 256, G, ncloud), ncloud, G), 256, 0, s>>>(dA);
+  else vg_keys_kernel<u64><<<dim3(grid_x((cap + 255) / 256, G, ncloud), ncloud, G), 256, 0, s>>>(dA);
   if (launches) *launches += 2;
-  launch_sort(s, dab, dba, ncloud, G, cap, 4, launches);   // result back in keyA / idxA
-  launch_segments(s, dsj, ncloud, G, cap, launches);
-  vg_centroid_kernel<<<dim3(grid_x((cap + 127) / 128, G, ncloud, 16384), ncloud, G), 128, 0, s>>>(dO);   // more CTAs per lane: fewer lanes in flight, their clouds stay in L2 while they are gathered from
+  launch_sort(s, dab, dba, ncloud, G, cap, kb == 4 ? 4 : 8, kb, launches);   // result back in keyA / idxA (even pass counts)
+  launch_segments(s, dsj, ncloud, G, cap, kb, launches);
+  // more CTAs of this kernel per lane: fewer lanes in flight at once, so that the clouds being gathered from stay in L2
+  const dim3 gc(grid_x((cap + 127) / 128, G, ncloud, 16384), ncloud, G);
+  if (kb == 4) vg_centroid_kernel<u32><<<gc, 128, 0, s>>>(dO);
+  else vg_centroid_kernel<u64><<<gc, 128, 0, s>>>(dO);
   if (launches) *launches += 1;
 }
 

@@ -578,3 +578,27 @@ def test_batch_of_outdoor_pairs(oracle_mod):
             assert np.array_equal(c.blob(name), o.blob(name)), (k, name)
         assert scenes.rotation_error_deg(Ts, To) <= 0.01 and scenes.translation_error(Ts, To) <= 1e-3, k
     c.close()
+
+
+def test_voxelgrid_without_pcl_overflow_emulation(oracle_mod):
+    """emulate_pcl_overflow = 0: cells are addressed with 64-bit keys (the sort's 8-byte key path), also on
+    grids of more than 2^31 cells where pcl itself would bail out; with the emulation on, the same cloud is
+    returned unfiltered (4-byte key path, key = point index)."""
+    import fccf_pcr_b200 as fccf
+
+    rng = np.random.default_rng(9)
+    pts = (rng.uniform(-1, 1, (200000, 3)) * [3000, 3000, 300]).astype(np.float32)     # 6 km x 6 km x 600 m at leaf 0.25: 2.8e11 cells
+    pts[17] = [np.nan, 0, 0]
+    src, tar, _ = scenes.make_pair("indoor", 20000, 7)
+    for emu in (0, 1):
+        c = fccf.Context(0, emulate_pcl_overflow=emu)
+        o = oracle_mod.Oracle(emulate_pcl_overflow=emu)
+        for cloud, leaf in ((pts, 0.25), (src, 0.1)):
+            a, b = c.voxelgrid(cloud, leaf), o.voxelgrid(cloud, leaf)
+            for x, y in zip(a, b):
+                assert x.shape == y.shape and np.array_equal(x, y, equal_nan=True), emu
+        if emu == 0:
+            assert int(c.voxelgrid(pts, 0.25)[1].max()) > 2**32        # cell indices beyond 32 bits
+        Tg, To = c.register(src, tar, 0.1), o.register(src, tar, 0.1)
+        assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
+        c.close()
