@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   const int n = st->n_hyp[ty], base = st->hyp_off[ty], tnum = st->hyp_off[3];
   const float* qt = A.hyp_qt + (size_t)base * 8;
   float* centre = A.centre + (size_t)ty * FCCF_MAXCENTRE * 8;
-  __shared__ int s_flag, s_K, s_E;
+  __shared__ int s_flag, s_K, s_E, s_special;
   __shared__ unsigned long long s_sort[40];
   __shared__ int s_emit[FCCF_MAXCENTRE];
   __shared__ int s_mem[32][CL_WSCR];
@@ -330,11 +330,12 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   // ---- adaptive cut-off walk (FCCF.cpp:1123-1229) ----
   if (t == 0) {
     int clusternum = key[0];
-    int emitted = 0;
+    int emitted = 0, special = 0;
     for (int ci = 0; ci < K; ci++) {
       if (key[ci] >= clusternum) {
         if (emitted >= FCCF_MAXCENTRE) { atomicOr(&st->status, ST_CENTRE_OVERFLOW); break; }
         s_emit[emitted++] = perm[ci];
+        special |= (key[ci] == 0 || key[ci] > CL_WSCR);     // clusters the warp path below does not finish (empty / above CL_WSCR members)
         if (cluster_num >= 0 && emitted > cluster_num) break;
       } else {
         if ((double)emitted < (cluster_num / 2.0)) { clusternum--; if (clusternum < 2) break; }
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
     }
     s_E = emitted;
     st->n_centre[ty] = emitted;
+    s_special = special;
   }
   __syncthreads();
   const int E = s_E;
@@ -351,12 +353,11 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   for (int e = warp; e < E; e += 32) {
     int k = s_emit[e]; int i = seeds[k]; int m = size[k];
     if (m > CL_WSCR || m == 0) continue;
-    int lo, hi; cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
+    int lo = 0, hi = 0;
     int cntw = 0;
     if (sm && !(deg[i] & 0x40000000)) {     // members from the neighbour list (m <= CL_NB <= 32), distances recomputed
       if (lane < m) { int j = nbl[(size_t)i * CL_NB + lane]; s_mem[warp][lane] = j; s_md[warp][lane] = cl_dist2(tr + (size_t)i * 3, tr + (size_t)j * 3); }
-      lo = hi;
-    }
+    } else cl_window(xs, n, tr[(size_t)i * ts], rr, lo, hi);
     for (int k0 = lo; k0 < hi; k0 += 32) {
       int kk = k0 + lane; bool ok = false; float d = 0.f; int j = -1;
       if (kk < hi) { j = order[kk] - obase; ok = CL_NEIGH(i, j, &d); }
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   int* gmem = A.members + base; float* gmd = A.mdist + base;
   int* gsorted = A.members + A.cap_hyp + base;   // second half of the member scratch
   __shared__ int s_cnt, s_w2[32];
-  for (int e = 0; e < E; e++) {
+  for (int e = 0; e < (s_special ? E : 0); e++) {
     int k = s_emit[e]; int i = seeds[k]; int m = size[k];
     if (m == 0) { if (t == 0) { float* o = centre + (size_t)e * 8; float nanv = CUDART_NAN_F; for (int u = 0; u < 8; u++) o[u] = nanv; } continue; }
     if (m <= CL_WSCR) continue;
