@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
     }
     __syncthreads();
   }
+  CL_MARK(9)
   // ---- greedy seeding as parallel rounds ----
   // A hypothesis is a seed iff none of its EARLIER neighbours is one (FCCF.cpp:1084-1121 in index order).
   while (true) {
