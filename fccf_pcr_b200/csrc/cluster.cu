@@ -122,9 +122,8 @@ __device__ void cl_emit_centre(const float* qt, const int* mem, int m, float* ou
 }
 
 #define CL_NB 24               // neighbours listed per hypothesis
-#define CL_CAND 64             // radius candidates collected per hypothesis before the angle test
-#define CL_SMEM_N 3072        // pools up to this many hypotheses are clustered out of shared memory
-#define CL_SMEM_BYTES (CL_SMEM_N * 52)
+#define CL_SMEM_N 2816        // pools up to this many hypotheses are clustered out of shared memory
+#define CL_SMEM_BYTES (CL_SMEM_N * 64)
 extern __shared__ __align__(16) unsigned char cl_dyn[];
 
 __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict__ AB) {
@@ -158,11 +157,12 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   // greedy rounds poll `state` of every earlier neighbour); larger pools work on the global arrays.
   const bool sm = n <= CL_SMEM_N;
   const double* an; const float* tr; const float* ax; const float* xs; const int* order; int ts, as, obase;
-  int* state; int* key; int* perm;
+  int* state; int* key; int* perm; float* d_trs = nullptr;
   if (sm) {
     double* d_an = (double*)cl_dyn;
     float* d_tr = (float*)(d_an + CL_SMEM_N); float* d_ax = d_tr + 3 * CL_SMEM_N; float* d_xs = d_ax + 3 * CL_SMEM_N;
     int* d_ord = (int*)(d_xs + CL_SMEM_N); state = d_ord + CL_SMEM_N; key = state + CL_SMEM_N; perm = key + CL_SMEM_N;
+    d_trs = (float*)(perm + CL_SMEM_N);     // translations once more, in x-sorted order: a window is contiguous (conflict-free sweeps)
     for (int i = t; i < n; i += 1024) {
       const float* q = qt + (size_t)i * 8; const float* a = A.hyp_ax + (size_t)(base + i) * 4;
       d_tr[3 * i] = q[4]; d_tr[3 * i + 1] = q[5]; d_tr[3 * i + 2] = q[6];
@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
       d_an[i] = A.hyp_an[base + i];
       d_xs[i] = A.xs[base + i];
       d_ord[i] = (int)A.order[base + i] - base;
+      const float* qs = qt + (size_t)d_ord[i] * 8;
+      d_trs[3 * i] = qs[4]; d_trs[3 * i + 1] = qs[5]; d_trs[3 * i + 2] = qs[6];
     }
     an = d_an; tr = d_tr; ax = d_ax; xs = d_xs; order = d_ord; ts = 3; as = 3; obase = 0;
   } else {
@@ -187,36 +189,73 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   CL_MARK(0)
   int rounds = 0;
   // ---- neighbour lists (shared-memory pools) ----
-  // Every thread finds ALL neighbours of its (<= 3) hypotheses once: a cheap float pass over the x-window
-  // collects the candidates inside the radius, then the FP64 angle test runs on the compacted candidates
-  // (so that the lanes of a warp do it together instead of diverging on ~5 % of the window).  Lists of up
-  // to CL_NB neighbours are kept (nbl), the count always (deg; bit 30: no list); the seeding rounds, the
-  // cluster sizes and the centre averaging below read them instead of re-scanning windows.
+  // ALL neighbours of every hypothesis, found once.  One warp per hypothesis: its lanes sweep the x-window
+  // with the cheap float radius test, ballots append the candidates (i, j) to a per-warp queue, and the
+  // expensive FP64 angle test runs on full batches of 32 queued candidates (of one or several hypotheses),
+  // so neither the window sweep nor the angle test wastes lanes.  Lists of up to CL_NB neighbours are kept
+  // (nbl), the count always (deg; bit 30: no list); the seeding rounds, the cluster sizes and the centre
+  // averaging below read them instead of re-scanning windows.
   int* nbl = A.nbl + (size_t)ty * CL_SMEM_N * CL_NB; int* deg = A.deg + (size_t)ty * CL_SMEM_N;
   if (sm) {
-#pragma unroll 1
-    for (int u = 0; u < 3; u++) {
-      const int i = t + u * 1024;
-      if (i >= n) continue;
-      int lo, hi; cl_window(xs, n, tr[(size_t)i * 3], rr, lo, hi);
-      const float ti[3] = {tr[(size_t)i * 3], tr[(size_t)i * 3 + 1], tr[(size_t)i * 3 + 2]};
-      int cand[CL_CAND]; int c = 0;
-      for (int k = lo; k < hi; k++) {
-        int j = order[k];
-        if (cl_dist2(ti, tr + (size_t)j * 3) < r2) { if (c < CL_CAND) cand[c] = j; c++; }
-      }
-      int m = 0; bool listed = c <= CL_CAND;
-      if (listed) {
-        for (int q = 0; q < c; q++) {
-          int j = cand[q];
-          if (cl_angle_ok(ax + (size_t)i * 3, an[i], ax + (size_t)j * 3, an[j], A.ang_cut)) { if (m < CL_NB) nbl[(size_t)i * CL_NB + m] = j; m++; }
+    for (int i = t; i < n; i += 1024) deg[i] = 0;
+    __syncthreads();
+    int* qi = s_mem[warp]; int* qj = (int*)s_md[warp];       // queue of candidates inside the radius (CL_WSCR = 128 entries)
+    int qn = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    // angle test of queue entries [0, nf): every passing lane appends j to the list of its i
+    auto flush = [&](int nf) {
+      for (int b0 = 0; b0 < nf; b0 += 32) {
+        const int e = b0 + lane;
+        bool ok = false; int i = -1, j = -1;
+        if (e < nf) { i = qi[e]; j = qj[e]; ok = cl_angle_ok(ax + (size_t)i * 3, an[i], ax + (size_t)j * 3, an[j], A.ang_cut); }
+        const unsigned pm = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const unsigned peers = __match_any_sync(pm, i);       // passing lanes of the same hypothesis
+          const int leader = __ffs(peers) - 1;
+          int old = 0;
+          if (lane == leader) { old = deg[i]; deg[i] = old + __popc(peers); }
+          old = __shfl_sync(peers, old, leader);
+          const int p = old + __popc(peers & lt);
+          if (p < CL_NB) nbl[(size_t)i * CL_NB + p] = j;
         }
-        listed = m <= CL_NB;
-      } else {
-        for (int k = lo; k < hi; k++) { int j = order[k]; if (CL_NEIGH(i, j, nullptr)) m++; }
+        __syncwarp();
       }
-      deg[i] = listed ? m : (m | 0x40000000);
+    };
+    for (int g0 = warp; g0 < n; g0 += 32 * 32) {                // 32 hypotheses of this warp at a time
+      const int il = g0 + 32 * lane;                            // lane l looks up the window of hypothesis il
+      int lo_l = 0, hi_l = 0;
+      if (il < n) cl_window(xs, n, tr[(size_t)il * 3], rr, lo_l, hi_l);
+      for (int l2 = 0; l2 < 32; l2++) {
+        const int i = g0 + 32 * l2;
+        if (i >= n) break;
+        const int lo = __shfl_sync(0xffffffffu, lo_l, l2), hi = __shfl_sync(0xffffffffu, hi_l, l2);
+        const float ti[3] = {tr[(size_t)i * 3], tr[(size_t)i * 3 + 1], tr[(size_t)i * 3 + 2]};
+        for (int k0 = lo; k0 < hi; k0 += 32) {
+          const int k = k0 + lane;
+          int j = -1;
+          bool cand = false;
+          if (k < hi) cand = cl_dist2(ti, d_trs + (size_t)k * 3) < r2;
+          const unsigned bal = __ballot_sync(0xffffffffu, cand);
+          if (cand) { j = order[k]; const int p = qn + __popc(bal & lt); qi[p] = i; qj[p] = j; }
+          qn += __popc(bal);
+          if (qn >= CL_WSCR - 32) {                             // the next sweep step may add 32 more
+            __syncwarp();
+            const int nf = qn & ~31, rem = qn - nf;
+            flush(nf);
+            int ri = 0, rj = 0;
+            if (lane < rem) { ri = qi[nf + lane]; rj = qj[nf + lane]; }
+            __syncwarp();
+            if (lane < rem) { qi[lane] = ri; qj[lane] = rj; }
+            qn = rem;
+            __syncwarp();
+          }
+        }
+      }
     }
+    __syncwarp();
+    flush(qn);
+    __syncthreads();
+    for (int i = t; i < n; i += 1024) if (deg[i] > CL_NB) deg[i] |= 0x40000000;
     __syncthreads();
   }
   CL_MARK(9)
