@@ -325,14 +325,40 @@ __device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long
   __syncthreads();
   int P = (int)s_u[32];
   __syncthreads();
+  // A rare minimum (a handful of empty clusters among hundreds of singletons) would keep P near n although
+  // almost every late pass is a no-op.  Then the pipelined passes stop at thr = the second smallest value
+  // (P = #{key > thr}): afterwards key[P..n) holds only values <= thr, a pass whose key[i] == thr moves
+  // nothing, and the few passes that start from a smaller key are run by one thread below, each ending as
+  // soon as its running maximum reaches thr.
+  unsigned thr = mn;
+  if (P > 0 && (n - P) * 8 <= n) {
+    unsigned m2 = 0xffffffffu;
+    for (int j = t; j < n; j += nt) { unsigned o = ord_key(key[j]); if (o > mn) m2 = min(m2, o); }
+    for (int o = 16; o; o >>= 1) m2 = min(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    if (lane == 0) s_u[warp] = m2;
+    __syncthreads();
+    if (warp == 0) { unsigned v = lane < nw ? s_u[lane] : 0xffffffffu; for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o)); if (lane == 0) s_u[32] = v; }
+    __syncthreads();
+    thr = s_u[32];
+    __syncthreads();
+    int c2 = 0;
+    for (int j = t; j < n; j += nt) c2 += (ord_key(key[j]) > thr) ? 1 : 0;
+    for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    if (lane == 0) s_u[warp] = (unsigned)c2;
+    __syncthreads();
+    if (warp == 0) { unsigned v = lane < nw ? s_u[lane] : 0u; for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); if (lane == 0) s_u[32] = v; }
+    __syncthreads();
+    P = (int)s_u[32];
+    __syncthreads();
+  }
   if (P > n - 1) P = n - 1;
-  if (P <= 0) return;
   if (P > 3 * nt) { block_exchange_sort_passes(key, perm, n, s_scratch); return; }
+  if (P <= 0 && thr == mn) return;
   // passes owned by this thread: t, t + nt, t + 2 nt.  Only the warps that own a pass take part in the
   // step loop (named barrier 1 over nact threads); the rest wait at the closing block barrier.
   const int nact = P >= nt ? nt : ((P + 31) & ~31);
   const int nslot = (P + nt - 1) / nt;
-  if (t < nact) {
+  if (P > 0 && t < nact) {
     K cur[3]; int curp[3];
 #pragma unroll
     for (int u = 0; u < 3; u++) { cur[u] = K(); curp[u] = 0; }
@@ -347,14 +373,21 @@ __device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long
           if (q >= q0 && q <= qmax) {
             if (q == q0) { cur[u] = key[i]; curp[u] = perm[i]; }
             const int jb = q * XS_B;
-            K v[XS_B];
+            // the whole tile (keys and payloads) is fetched first, the compare/swap chain then runs on
+            // registers, and only the positions it changed are written back
+            K v[XS_B]; int vp[XS_B]; unsigned changed = 0u;
 #pragma unroll
-            for (int e = 0; e < XS_B; e++) { const int j = jb + e; if (j > i && j < n) v[e] = key[j]; }
+            for (int e = 0; e < XS_B; e++) { const int j = jb + e; if (j > i && j < n) { v[e] = key[j]; vp[e] = perm[j]; } }
 #pragma unroll
             for (int e = 0; e < XS_B; e++) {
               const int j = jb + e;
-              if (j > i && j < n && cur[u] < v[e]) { const int vp = perm[j]; key[j] = cur[u]; perm[j] = curp[u]; cur[u] = v[e]; curp[u] = vp; }
+              if (j > i && j < n && cur[u] < v[e]) {
+                const K tk = v[e]; const int tp = vp[e];
+                v[e] = cur[u]; vp[e] = curp[u]; cur[u] = tk; curp[u] = tp; changed |= 1u << e;
+              }
             }
+#pragma unroll
+            for (int e = 0; e < XS_B; e++) if (changed & (1u << e)) { key[jb + e] = v[e]; perm[jb + e] = vp[e]; }
             if (q == qmax) { key[i] = cur[u]; perm[i] = curp[u]; }
           }
         }
@@ -363,6 +396,22 @@ __device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long
     }
   }
   __syncthreads();
+  // passes P..n-2 that start below thr (see above), in order, by one thread
+  if (thr != mn) {
+    if (t == 0) {
+      for (int i = P; i + 1 < n; i++) {
+        K cur = key[i];
+        if (ord_key(cur) >= thr) continue;
+        int curp = perm[i];
+        for (int j = i + 1; j < n; j++) {
+          const K v = key[j];
+          if (cur < v) { const int vp = perm[j]; key[j] = cur; perm[j] = curp; cur = v; curp = vp; if (ord_key(cur) >= thr) break; }
+        }
+        key[i] = cur; perm[i] = curp;
+      }
+    }
+    __syncthreads();
+  }
 }
 
 }  // namespace fccf

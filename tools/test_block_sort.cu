@@ -8,12 +8,12 @@ template <typename K> __global__ void k(K* key, int* perm, int n) { __shared__ u
 template <typename K> void ref(std::vector<K>& k, std::vector<int>& p) { int n = k.size(); for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (k[i] < k[j]) { std::swap(k[i], k[j]); std::swap(p[i], p[j]); } }
 int main() {
   int bad = 0;
-  for (int trial = 0; trial < 60; trial++) {
+  for (int trial = 0; trial < 100; trial++) {
     int n = trial < 5 ? trial : (rand() % 3000 + 1);
     int nt = (trial % 3 == 0) ? 1024 : ((trial % 3 == 1) ? 256 : 96);
     std::vector<int> key(n), perm(n);
-    int mode = trial % 4;
-    for (int i = 0; i < n; i++) { key[i] = mode == 0 ? 1 + (rand() % 100 == 0) * (rand() % 50) : (mode == 1 ? rand() % 5 : (mode == 2 ? rand() : i)); perm[i] = i; }
+    int mode = trial % 5;
+    for (int i = 0; i < n; i++) { key[i] = mode == 0 ? 1 + (rand() % 100 == 0) * (rand() % 50) : (mode == 1 ? rand() % 5 : (mode == 2 ? rand() : (mode == 3 ? i : (rand() % 40 == 0 ? 0 : 1 + (rand() % 6 == 0) * (rand() % 20))))); perm[i] = i; }
     std::vector<int> rk = key, rp = perm; ref(rk, rp);
     int *dk, *dp; cudaMalloc(&dk, 4 * (n + 1)); cudaMalloc(&dp, 4 * (n + 1));
     cudaMemcpy(dk, key.data(), 4 * n, cudaMemcpyHostToDevice); cudaMemcpy(dp, perm.data(), 4 * n, cudaMemcpyHostToDevice);
