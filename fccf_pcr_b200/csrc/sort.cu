@@ -91,49 +91,58 @@ __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __r
   const int nact = (n + RS_TILE - 1) / RS_TILE;
   if (pass >= rs_active(*j.nbits, np)) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  // cnt: per (round, warp) row digit counters during the ranking; afterwards the same memory stages the
-  // tile in digit order (2048 keys + 2048 values = 24 KB) so that the global writes are coalesced runs
-  __shared__ __align__(16) unsigned char s_raw[RS_I * 8 * 256 * 2];
-  unsigned short (*cnt)[256] = (unsigned short (*)[256])s_raw;
-  KT* skey = (KT*)s_raw; u32* sval = (u32*)(s_raw + RS_TILE * sizeof(KT));
+  // Warp w owns the 256 consecutive keys [w * 256, (w + 1) * 256) of the tile, in 8 rounds of 32: the stable
+  // order of the tile is (warp, round, lane), so ONE private counter row per warp, bumped round after round
+  // by the warp itself, gives every key its rank inside (warp, digit) without block barriers; the block
+  // then only scans 8 rows per digit.  The tile is staged in digit order in shared memory so that the
+  // global writes are coalesced runs.
+  __shared__ u32 cntw[RS_T / 32][256];
+  __shared__ __align__(16) unsigned char s_stage[RS_TILE * (sizeof(KT) + 4)];
+  KT* skey = (KT*)s_stage; u32* sval = (u32*)(s_stage + RS_TILE * sizeof(KT));
   __shared__ u32 gbase[256];      // global offset of the digit, minus the digit's start inside the tile
   __shared__ u32 dstart[256];     // start of the digit inside the tile
   __shared__ u32 s_ws[RS_T / 32];
   const int bpp = rs_bpp(*j.nbits, np), shift = pass * bpp;
   const u32 mask = (1u << bpp) - 1u;
+  const unsigned lt = (1u << lane) - 1u;
   for (int tile = blockIdx.x; tile < nact; tile += gridDim.x) {
-    for (int k = t; k < RS_I * 8 * 256 / 2; k += RS_T) ((u32*)s_raw)[k] = 0u;
-    const int base = tile * RS_TILE;
+#pragma unroll
+    for (int w = 0; w < RS_T / 32; w++) cntw[w][t] = 0u;
+    const int base = tile * RS_TILE + warp * (RS_I * 32);
     const u32 gb = j.hist[(size_t)tile * 256 + t] + j.hist[(size_t)nact * 256 + t];
     __syncthreads();
-    KT key[RS_I]; u32 val[RS_I]; int dig[RS_I]; int rk[RS_I];
-    // all loads of the tile first (eight keys and values in flight per thread), then the ranking
+    KT key[RS_I]; u32 val[RS_I]; int dig[RS_I]; int off[RS_I];
+    // all loads of the warp's 256 keys first (eight keys and values in flight per thread), then the ranking
 #pragma unroll
     for (int r = 0; r < RS_I; r++) {
-      int i = base + r * RS_T + t;
+      const int i = base + r * 32 + lane;
       key[r] = (i < n) ? kin[i] : (KT)0;
       val[r] = (i < n) ? (identity ? (u32)i : j.vin[i]) : 0u;
     }
 #pragma unroll
     for (int r = 0; r < RS_I; r++) {
-      int i = base + r * RS_T + t;
-      bool valid = i < n;
-      unsigned am = __ballot_sync(0xffffffffu, valid);
-      dig[r] = -1; rk[r] = 0;
+      const int i = base + r * 32 + lane;
+      const bool valid = i < n;
+      const unsigned am = __ballot_sync(0xffffffffu, valid);
+      dig[r] = -1; off[r] = 0;
       if (valid) {
         dig[r] = (int)((u32)(key[r] >> shift) & mask);
-        // lanes of this warp row with the same digit: one ballot per digit bit
+        // lanes of this round with the same digit: one ballot per digit bit
         unsigned peers = am;
-        for (int bb = 0; bb < bpp; bb++) { unsigned bal = __ballot_sync(am, (dig[r] >> bb) & 1); peers &= ((dig[r] >> bb) & 1) ? bal : ~bal; }
-        rk[r] = __popc(peers & ((1u << lane) - 1u));
-        if (lane == __ffs(peers) - 1) cnt[r * 8 + warp][dig[r]] = (unsigned short)__popc(peers);
+        for (int bb = 0; bb < bpp; bb++) { const unsigned bal = __ballot_sync(am, (dig[r] >> bb) & 1); peers &= ((dig[r] >> bb) & 1) ? bal : ~bal; }
+        const int leader = __ffs(peers) - 1;
+        u32 old = 0;
+        if (lane == leader) { old = cntw[warp][dig[r]]; cntw[warp][dig[r]] = old + (u32)__popc(peers); }
+        old = __shfl_sync(peers, old, leader);
+        off[r] = (int)old + __popc(peers & lt);
       }
+      __syncwarp();
     }
     __syncthreads();
-    // digit t: exclusive prefix over the (round, warp) rows, then over the digits of the tile
+    // digit t: exclusive prefix over the warps' rows, then over the digits of the tile
     u32 run = 0;
-#pragma unroll 8
-    for (int e = 0; e < RS_I * 8; e++) { u32 c = cnt[e][t]; cnt[e][t] = (unsigned short)run; run += c; }
+#pragma unroll
+    for (int w = 0; w < RS_T / 32; w++) { const u32 c = cntw[w][t]; cntw[w][t] = run; run += c; }
     u32 inc = run;
     for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
     if (lane == 31) s_ws[warp] = inc;
@@ -143,14 +152,10 @@ __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __r
     const u32 ds = woff + inc - run;
     dstart[t] = ds; gbase[t] = gb - ds;
     __syncthreads();
-    int lp[RS_I];
 #pragma unroll
-    for (int r = 0; r < RS_I; r++) lp[r] = (dig[r] >= 0) ? (int)(dstart[dig[r]] + cnt[r * 8 + warp][dig[r]] + rk[r]) : -1;
-    __syncthreads();                 // every read of cnt is done: the memory becomes the staging area
-#pragma unroll
-    for (int r = 0; r < RS_I; r++) if (lp[r] >= 0) { skey[lp[r]] = key[r]; sval[lp[r]] = val[r]; }
+    for (int r = 0; r < RS_I; r++) if (dig[r] >= 0) { const int lp = (int)(dstart[dig[r]] + cntw[warp][dig[r]]) + off[r]; skey[lp] = key[r]; sval[lp] = val[r]; }
     __syncthreads();
-    const int ntile = min(RS_TILE, n - base);
+    const int ntile = min(RS_TILE, n - tile * RS_TILE);
     for (int q = t; q < ntile; q += RS_T) {
       const KT k = skey[q];
       const u32 pos = gbase[(u32)(k >> shift) & mask] + (u32)q;
