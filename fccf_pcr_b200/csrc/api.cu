@@ -56,6 +56,8 @@ struct GraphRec { int G = 0; cudaGraphExec_t exec = nullptr; int launches = 0; }
 // while some groups compute, the next one receives its clouds (FCCF_GROUPS overrides the count).
 struct Group {
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // second capture stream: the graph branch of the fine-verify table build
+  cudaEvent_t fork = nullptr, join = nullptr;
   std::vector<Lane> lanes;
   PipeState* d_st_all = nullptr; PipeState* h_st_all = nullptr;
   CallArgs* d_calls = nullptr; CallArgs* h_calls = nullptr;
@@ -140,6 +142,8 @@ static int group_create(fccf_ctx* ctx, Group** out) {
   Group* g = new Group();
   const int nl = ctx->max_lanes;
   bool ok = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&g->fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&g->join, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaMalloc(&g->d_st_all, sizeof(PipeState) * nl) == cudaSuccess && cudaMallocHost(&g->h_st_all, sizeof(PipeState) * nl) == cudaSuccess;
   ok = ok && cudaMalloc(&g->d_calls, sizeof(CallArgs) * nl) == cudaSuccess && cudaMallocHost(&g->h_calls, sizeof(CallArgs) * nl) == cudaSuccess;
   if (!ok) { delete g; ctx->err = "state allocation failed"; cudaGetLastError(); return FCCF_ERR_CUDA; }
@@ -169,6 +173,9 @@ static void group_destroy(Group* g) {
   table_destroy(g->tab);
   for (int i = 0; i < 6; i++) cudaEventDestroy(g->ev[i]);
   for (int i = 0; i < 8; i++) cudaEventDestroy(g->sev[i]);
+  if (g->fork) cudaEventDestroy(g->fork);
+  if (g->join) cudaEventDestroy(g->join);
+  if (g->stream2) cudaStreamDestroy(g->stream2);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -376,12 +383,23 @@ static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_
   CK(rec(g->sev[0]));
   launch_planes(s, b, 2, 1, launches);               // FCCF.cpp:1400-1401
   CK(rec(g->sev[1]));
+  // The fine-verify voxel table needs only the leftover cloud of the plane stage: in a captured graph it is
+  // a branch of its own (second capture stream forked / joined by events), next to the mostly single-CTA
+  // hypothesis, clustering and quick-verify kernels.
+  if (capturing) {
+    CK(cudaEventRecord(g->fork, s));
+    CK(cudaStreamWaitEvent(g->stream2, g->fork, 0));
+    launch_fine_verify_build(g->stream2, b, launches);
+    CK(cudaEventRecord(g->join, g->stream2));
+  }
   launch_hypotheses(s, b, launches);                 // FCCF.cpp:1406-1427, 1439-1462
   CK(rec(g->sev[2]));
   launch_cluster(s, b, launches);                    // FCCF.cpp:1464-1466
   CK(rec(g->sev[3]));
   launch_quick_verify(s, b, launches);               // FCCF.cpp:1468-1494
   CK(rec(g->sev[4]));
+  if (capturing) CK(cudaStreamWaitEvent(s, g->join, 0));
+  else launch_fine_verify_build(s, b, launches);
   launch_fine_verify_fuse(s, b, launches);           // FCCF.cpp:1499-1606
   CK(rec(g->ev[3]));
   CK(cudaMemcpyAsync(g->h_st_all, g->d_st_all, sizeof(PipeState) * (size_t)G, cudaMemcpyDeviceToHost, s));

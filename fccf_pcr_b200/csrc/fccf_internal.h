@@ -231,7 +231,8 @@ void launch_planes(cudaStream_t s, const Batch& b, int ncloud, int src_stage, ui
 void launch_hypotheses(cudaStream_t s, const Batch& b, uint64_t* launches);
 void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches);
 void launch_quick_verify(cudaStream_t s, const Batch& b, uint64_t* launches);
-void launch_fine_verify_fuse(cudaStream_t s, const Batch& b, uint64_t* launches);
+void launch_fine_verify_build(cudaStream_t s, const Batch& b, uint64_t* launches);   // static voxel table (needs only the plane stage)
+void launch_fine_verify_fuse(cudaStream_t s, const Batch& b, uint64_t* launches);    // scoring of the selected centres + fusion
 
 // stand-alone stage entry points (C-ABI helpers)
 void launch_quick_verify_list(cudaStream_t s, const fccf_params& p, float* d_T16, int n, const float* d_planes1, int f1,

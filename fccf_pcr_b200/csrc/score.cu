@@ -620,19 +620,31 @@ __global__ void fuse_kernel(const FuseArgs* __restrict__ AB) {
   T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
 }
 
+// fine verify in two parts: the static voxel table of cloud 1's leftover points (depends only on the plane
+// stage, so a captured graph runs it on a branch beside hypotheses / clustering / quick verify), then the
+// scoring of the selected centres and the fusion.
+static ScoreWS fv_ws(const Work& w) { ScoreWS ws = w.h.fv; ws.ss = &w.st->fv; ws.status = &w.st->status; return ws; }
+
+void launch_fine_verify_build(cudaStream_t s, const Batch& b, uint64_t* launches) {
+  const int G = b.G;
+  std::vector<ScoreBuildJob> jobs(G);
+  for (int g = 0; g < G; g++) {
+    const Work& w = b.w[g]; PipeState* st = w.st;
+    jobs[g].s1 = w.c[0].sub; jobs[g].n1 = &st->oct[0].S; jobs[g].n2 = &st->oct[1].S; jobs[g].ws = fv_ws(w);
+  }
+  launch_score_build(s, b.p, jobs.data(), G, *b.tab, launches);
+}
+
 void launch_fine_verify_fuse(cudaStream_t s, const Batch& b, uint64_t* launches) {
   const int G = b.G;
-  std::vector<ScoreBuildJob> jobs(G); std::vector<ScArgs> As(G); std::vector<FuseArgs> Fs(G);
+  std::vector<ScArgs> As(G); std::vector<FuseArgs> Fs(G);
   for (int g = 0; g < G; g++) {
     const Work& w = b.w[g]; const HypWS& h = w.h;
     PipeState* st = w.st;
-    ScoreWS ws = h.fv; ws.ss = &st->fv; ws.status = &st->status;
-    jobs[g].s1 = w.c[0].sub; jobs[g].n1 = &st->oct[0].S; jobs[g].n2 = &st->oct[1].S; jobs[g].ws = ws;
-    ScArgs& A = As[g]; fill_common(A, b.p, ws);
+    ScArgs& A = As[g]; fill_common(A, b.p, fv_ws(w));
     A.T = h.top_T; A.n_hyp = 3 * fccf_topk(b.p); A.n_top = st->n_top; A.topk = fccf_topk(b.p); A.s2 = w.c[1].sub; A.scores = h.top_s2;
     FuseArgs& F = Fs[g]; F.st = st; F.top_T = h.top_T; F.top_s1 = h.top_s1; F.top_s2 = h.top_s2; F.fine_number = b.p.fine_verify_number; F.topk = fccf_topk(b.p);
   }
-  launch_score_build(s, b.p, jobs.data(), G, *b.tab, launches);
   score_launch(s, As, *b.tab, launches);
   fuse_kernel<<<G, 1, 0, s>>>(b.tab->put(Fs.data(), G));
   if (launches) *launches += 1;
