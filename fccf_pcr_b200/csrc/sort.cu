@@ -63,12 +63,12 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restric
     __threadfence();
     // last tile: hist[b][d] -> exclusive prefix over tiles; row nact = exclusive prefix over digits
     u32 run = 0;
-    for (int b0 = 0; b0 < nact; b0 += 8) {      // eight independent loads in flight per thread
-      u32 v[8];
+    for (int b0 = 0; b0 < nact; b0 += 16) {     // sixteen independent loads in flight per thread (10M-point clouds: ~5000 tiles)
+      u32 v[16];
 #pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = (b0 + u < nact) ? __ldcg(&j.hist[(size_t)(b0 + u) * 256 + t]) : 0u;
+      for (int u = 0; u < 16; u++) v[u] = (b0 + u < nact) ? __ldcg(&j.hist[(size_t)(b0 + u) * 256 + t]) : 0u;
 #pragma unroll
-      for (int u = 0; u < 8; u++) if (b0 + u < nact) { j.hist[(size_t)(b0 + u) * 256 + t] = run; run += v[u]; }
+      for (int u = 0; u < 16; u++) if (b0 + u < nact) { j.hist[(size_t)(b0 + u) * 256 + t] = run; run += v[u]; }
     }
     h[t] = run;
     __syncthreads();
