@@ -46,7 +46,7 @@ struct Lane {
   int pair = -1;
 };
 
-struct GraphRec { int G = 0; cudaGraphExec_t exec = nullptr; int launches = 0; };
+struct GraphRec { int G = 0; bool fast = false; cudaGraphExec_t exec = nullptr; int launches = 0; };
 
 // A group = the lanes that run as ONE batched launch sequence on one stream: every kernel of the
 // pipeline is launched once with grid.z = G and serves G independent registrations (most stages of one
@@ -68,6 +68,9 @@ struct Group {
   cudaEvent_t sev[8];
   bool busy = false, had_h2d = false;
   int G = 0;                     // lanes of the sequence in flight
+  bool fast = false;             // the sequence in flight uses the cluster VoxelGrid (voxelgrid_fast.cu)
+  float leaf = 0.f;
+  VgFastScratch vf;              // its per-cluster scratch (L2-resident)
   size_t last_h2d = 0;
   uint64_t launches = 0, l0 = 0;
 };
@@ -81,6 +84,11 @@ struct fccf_ctx {
   std::vector<Group*> groups;
   int max_lanes = 64;
   bool use_graph = true;
+  // Cluster VoxelGrid: tried first; a cloud it cannot hold (ST_VG_FAST_MISS) makes the host re-run the sequence
+  // through the generic kernels, and calls with a leaf <= the one that missed go generic directly for a while.
+  bool vg_fast = false;
+  float fast_miss_leaf = 0.f; int fast_miss_ttl = 0;
+  uint64_t fast_runs = 0, fast_misses = 0;
   uint64_t params_epoch = 1;
   int cap_hyp = 1 << 18;
   bool have_run = false;
@@ -166,6 +174,8 @@ static void group_destroy(Group* g) {
     for (int c = 0; c < 2; c++) { if (L.cloud_arena[c].base) cudaFree(L.cloud_arena[c].base); if (L.d_raw[c]) cudaFree(L.d_raw[c]); }
     if (L.hyp_arena.base) cudaFree(L.hyp_arena.base);
   }
+  if (g->vf.pre) cudaFree(g->vf.pre);
+  if (g->vf.queue) cudaFree(g->vf.queue);
   if (g->d_st_all) cudaFree(g->d_st_all);
   if (g->h_st_all) cudaFreeHost(g->h_st_all);
   if (g->d_calls) cudaFree(g->d_calls);
@@ -180,7 +190,21 @@ static void group_destroy(Group* g) {
   delete g;
 }
 
-// workspaces of lane `li` of group `g` for clouds of up to max(n0, n1) points
+static void lane_release(Lane* L) {
+  for (int c = 0; c < 2; c++) {
+    if (L->cloud_arena[c].base) cudaFree(L->cloud_arena[c].base);
+    if (L->d_raw[c]) cudaFree(L->d_raw[c]);
+    L->cloud_arena[c] = Arena(); L->d_raw[c] = nullptr;
+    memset(&L->c[c], 0, sizeof L->c[c]);
+  }
+  if (L->hyp_arena.base) cudaFree(L->hyp_arena.base);
+  L->hyp_arena = Arena();
+  memset(&L->h, 0, sizeof L->h);
+  L->cap_pts = 0;
+}
+
+// workspaces of lane `li` of group `g` for clouds of up to max(n0, n1) points.  On failure the lane owns
+// nothing and reports capacity 0 (no pointer to freed memory survives), and the group's graphs are dropped.
 static int ensure_capacity(fccf_ctx* ctx, Group* g, int li, size_t n0, size_t n1) {
   Lane* L = &g->lanes[li];
   size_t need = std::max(n0, n1);
@@ -190,21 +214,17 @@ static int ensure_capacity(fccf_ctx* ctx, Group* g, int li, size_t n0, size_t n1
   int cap = (int)((need + 4095) & ~(size_t)4095);
   CK(cudaStreamSynchronize(g->stream));
   group_drop_graphs(g);            // captured graphs hold the old pointers
+  lane_release(L);
   for (int c = 0; c < 2; c++) {
-    if (L->cloud_arena[c].base) CK(cudaFree(L->cloud_arena[c].base));
-    if (L->d_raw[c]) CK(cudaFree(L->d_raw[c]));
-    L->cloud_arena[c] = Arena();
-    L->d_raw[c] = nullptr;
     size_t bytes = cloud_bytes(cap);
-    CK(cudaMalloc(&L->cloud_arena[c].base, bytes));
+    if (cudaMalloc(&L->cloud_arena[c].base, bytes) != cudaSuccess || cudaMalloc(&L->d_raw[c], (size_t)cap * 12) != cudaSuccess) {
+      cudaGetLastError(); lane_release(L); ctx->err = "out of device memory (cloud workspace)"; return FCCF_ERR_CUDA;
+    }
     L->cloud_arena[c].size = bytes;
-    CK(cudaMalloc(&L->d_raw[c], (size_t)cap * 12));
     cloud_carve(L->cloud_arena[c], L->c[c], cap);
     L->c[c].raw = L->d_raw[c];
   }
   // fine-verify hash sized for the leftover cloud (<= cap points)
-  if (L->hyp_arena.base) CK(cudaFree(L->hyp_arena.base));
-  L->hyp_arena = Arena();
   HypWS& h = L->h;
   size_t ch = (size_t)ctx->cap_hyp, nbh = ch / RS_TILE + 2;
   size_t bytes = 0;
@@ -220,7 +240,7 @@ static int ensure_capacity(fccf_ctx* ctx, Group* g, int li, size_t n0, size_t n1
   size_t fv_bytes = score_ws_layout(nullptr, nullptr, cap, 48);   // 48 counter rows: hypotheses in flight of the global-table kernel
   add(fv_bytes);
   bytes += 8192;
-  CK(cudaMalloc(&L->hyp_arena.base, bytes));
+  if (cudaMalloc(&L->hyp_arena.base, bytes) != cudaSuccess) { cudaGetLastError(); lane_release(L); ctx->err = "out of device memory (hypothesis workspace)"; return FCCF_ERR_CUDA; }
   L->hyp_arena.size = bytes;
   Arena& a = L->hyp_arena;
   h.cap_hyp = ctx->cap_hyp;
@@ -235,6 +255,29 @@ static int ensure_capacity(fccf_ctx* ctx, Group* g, int li, size_t n0, size_t n1
   h.top_T = a.take<float>(ntop * 16); h.top_s1 = a.take<float>(ntop); h.top_s2 = a.take<float>(ntop); h.top_centre = a.take<int>(ntop);
   score_ws_layout(&h.fv, a.take<char>(fv_bytes), cap, 48);
   L->cap_pts = cap;
+  return FCCF_OK;
+}
+
+// per-cluster scratch of the cluster VoxelGrid for clouds of up to n points (shared by the lanes of the group)
+static int ensure_fast_scratch(fccf_ctx* ctx, Group* g, size_t n) {
+  if (!ctx->vg_fast) return FCCF_OK;
+  size_t want = std::min<size_t>((n + 4095) & ~(size_t)4095, (size_t)((vg_fast_nmax() + 4095) & ~4095));
+  if (want < 4096) want = 4096;
+  if ((size_t)g->vf.stride >= want) return FCCF_OK;
+  CK(cudaStreamSynchronize(g->stream));
+  group_drop_graphs(g);
+  if (g->vf.pre) cudaFree(g->vf.pre);
+  if (g->vf.queue) cudaFree(g->vf.queue);
+  g->vf = VgFastScratch();
+  int ncl = std::min(vg_fast_max_clusters(), 2 * ctx->max_lanes);
+  if (ncl < 1) return FCCF_OK;
+  if (cudaMalloc(&g->vf.pre, (size_t)ncl * want * 16) != cudaSuccess || cudaMalloc(&g->vf.queue, (size_t)ncl * want * 16) != cudaSuccess) {
+    cudaGetLastError();
+    if (g->vf.pre) cudaFree(g->vf.pre);
+    g->vf = VgFastScratch();
+    ctx->err = "out of device memory (cluster VoxelGrid scratch)"; return FCCF_ERR_CUDA;
+  }
+  g->vf.stride = (int)want; g->vf.ncl = ncl;
   return FCCF_OK;
 }
 
@@ -254,17 +297,37 @@ void fccf_default_params(fccf_params* p) {
   p->emulate_pcl_overflow = 1;
 }
 
+// Values the kernels cannot run with (fixed-size tables, divisions): rejected up front with FCCF_ERR_ARG.
+static const char* params_problem(const fccf_params& p) {
+  if (!(p.face_voxel_size > 0.f) || !(p.fine_verify_voxel_size > 0.f)) return "face_voxel_size and fine_verify_voxel_size must be > 0";
+  if (!(p.cluster_number_threshold >= 0.f) || p.cluster_number_threshold > (float)FCCF_MAXCENTRE) return "cluster_number_threshold must be in [0, 256] (cluster centre capacity per roughness type)";
+  if (!(p.select_plane_number >= 0.f) || p.select_plane_number > (float)(FCCF_MAXF - 1)) return "select_plane_number must be in [0, 15] (the reference keeps select_plane_number + 1 <= 16 planes)";
+  if (!(p.fine_verify_number >= 0.f)) return "fine_verify_number must be >= 0";
+  if (!(p.seclct_cluster_number >= 0.f)) return "seclct_cluster_number must be >= 0";
+  if (!(p.cluster_distance_threshold >= 0.f)) return "cluster_distance_threshold must be >= 0";
+  if (p.batch_lanes < 0) return "batch_lanes must be >= 0";
+  if (p.emulate_pcl_overflow != 0 && p.emulate_pcl_overflow != 1) return "emulate_pcl_overflow must be 0 or 1";
+  return nullptr;
+}
+static thread_local std::string g_create_error;
+
 fccf_ctx* fccf_create(int device, const fccf_params* params) {
+  g_create_error.clear();
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return nullptr;
-  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { g_create_error = "no usable CUDA device (libfccf has no CPU path)"; return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return nullptr; }
+  fccf_params p0;
+  if (params) p0 = *params; else fccf_default_params(&p0);
+  if (const char* why = params_problem(p0)) { g_create_error = std::string("bad parameter: ") + why; return nullptr; }
   fccf_ctx* ctx = new fccf_ctx();
   ctx->device = device;
-  if (params) ctx->p = *params; else fccf_default_params(&ctx->p);
+  ctx->p = p0;
   if (ctx->p.batch_lanes > 0) ctx->max_lanes = ctx->p.batch_lanes > 1024 ? 1024 : ctx->p.batch_lanes;
   if (const char* e = getenv("FCCF_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
   score_init_attributes();
   cluster_init_attributes();
+  ctx->vg_fast = vg_fast_init() > 0;
+  if (const char* e = getenv("FCCF_NO_VG_FAST")) if (e[0] == '1') ctx->vg_fast = false;
   Group* g = nullptr;
   if (group_create(ctx, &g) != FCCF_OK) { delete ctx; return nullptr; }
   ctx->groups.push_back(g);
@@ -289,14 +352,21 @@ void fccf_destroy(fccf_ctx* ctx) {
   delete ctx;
 }
 
-const char* fccf_last_error(const fccf_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no usable CUDA device)"; }
+const char* fccf_last_error(const fccf_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  return g_create_error.empty() ? "no context (no usable CUDA device)" : g_create_error.c_str();   // why the last fccf_create of this thread failed
+}
 int fccf_set_params(fccf_ctx* ctx, const fccf_params* params) {
   if (!ctx || !params) return FCCF_ERR_ARG;
+  if (const char* why = params_problem(*params)) { ctx->err = std::string("bad parameter: ") + why; return FCCF_ERR_ARG; }
+  ctx->fast_miss_leaf = 0.f; ctx->fast_miss_ttl = 0;
   int lanes = ctx->p.batch_lanes;
   ctx->p = *params; ctx->p.batch_lanes = lanes;   // the lane count is fixed at creation
   ctx->params_epoch++;                            // captured graphs hold the old values: re-capture lazily
   return FCCF_OK;
 }
+// library-level integers for tools (not part of include/fccf.h)
+int fccf_debug_int(const char* name) { if (name && !strcmp(name, "vg_fast_max_clusters")) return vg_fast_max_clusters(); return -1; }
 uint64_t fccf_launch_count(const fccf_ctx* ctx) {
   if (!ctx) return 0;
   uint64_t n = ctx->launches;
@@ -357,6 +427,7 @@ static int set_single_call(fccf_ctx* ctx, int n0, int n1, float leaf) {
 }
 
 static int check_status(fccf_ctx* ctx, int st) {
+  st &= ~ST_VG_FAST_MISS;          // not an error (handled by the caller: generic re-run)
   if (st == 0) return FCCF_OK;
   char b[256];
   snprintf(b, sizeof b, "device status 0x%x:%s%s%s%s%s", st, (st & ST_OCT_DEPTH) ? " octree deeper than the 32-bit Morton key" : "",
@@ -370,16 +441,18 @@ static int check_status(fccf_ctx* ctx, int st) {
 // blocks, in stream order on the group's stream.  All sizes are device-side and the per-call values
 // (point counts, leaf, raw-cloud pointers) are read from the group's call array, so the sequence is
 // identical for every call with the same G: it is captured into a CUDA graph once and replayed.
-static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_t* launches, bool capturing) {
+static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_t* launches, bool capturing, bool fast) {
   cudaStream_t s = g->stream;
   // inside a capture a plain cudaEventRecord is only a dependency; the External flag makes a timing node
   auto rec = [&](cudaEvent_t e) { return capturing ? cudaEventRecordWithFlags(e, s, cudaEventRecordExternal) : cudaEventRecord(e, s); };
   std::vector<Work> ws;
   Batch b = make_batch(ctx, g, G, ws, tab);
   launch_init_state(s, b, g->d_calls, launches);
-  launch_voxelgrid(s, b, 0, 2, launches);            // main(): FCCF.cpp:1668-1678
+  if (fast) CK(launch_voxelgrid_fast(s, b, 0, 2, g->vf, launches));   // main(): FCCF.cpp:1668-1678, one cluster per cloud
+  else launch_voxelgrid(s, b, 0, 2, launches);
   CK(rec(g->ev[2]));
-  launch_voxelgrid(s, b, 1, 2, launches);            // FCCF.cpp:1377-1387
+  if (fast) CK(launch_voxelgrid_fast(s, b, 1, 2, g->vf, launches));   // FCCF.cpp:1377-1387
+  else launch_voxelgrid(s, b, 1, 2, launches);
   CK(rec(g->sev[0]));
   launch_planes(s, b, 2, 1, launches);               // FCCF.cpp:1400-1401
   CK(rec(g->sev[1]));
@@ -407,19 +480,19 @@ static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_
   return FCCF_OK;
 }
 
-static int group_graph(fccf_ctx* ctx, Group* g, int G, GraphRec** out) {
+static int group_graph(fccf_ctx* ctx, Group* g, int G, bool fast, GraphRec** out) {
   if (g->params_epoch != ctx->params_epoch) { CK(cudaStreamSynchronize(g->stream)); group_drop_graphs(g); g->params_epoch = ctx->params_epoch; }
-  for (GraphRec& r : g->graphs) if (r.G == G) { *out = &r; return FCCF_OK; }
+  for (GraphRec& r : g->graphs) if (r.G == G && r.fast == fast) { *out = &r; return FCCF_OK; }
   // room for one more capture?  (about 10 KB of argument blocks per lane)
-  if (g->graphs.size() >= 6 || g->tab.off + (size_t)G * 12288 + 65536 > g->tab.cap) { CK(cudaStreamSynchronize(g->stream)); group_drop_graphs(g); }
+  if (g->graphs.size() >= 8 || g->tab.off + (size_t)G * 12288 + 65536 > g->tab.cap) { CK(cudaStreamSynchronize(g->stream)); group_drop_graphs(g); }
   cudaStream_t s = g->stream;
-  GraphRec r; r.G = G;
+  GraphRec r; r.G = G; r.fast = fast;
   size_t off0 = g->tab.off;
   g->tab.immediate = false;
   cudaGraph_t graph = nullptr;
   uint64_t cnt = 0;
   CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-  int rc = group_pipeline(ctx, g, G, &g->tab, &cnt, true);
+  int rc = group_pipeline(ctx, g, G, &g->tab, &cnt, true, fast);
   cudaError_t e = cudaStreamEndCapture(s, &graph);
   if (rc != FCCF_OK || e != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
@@ -436,6 +509,24 @@ static int group_graph(fccf_ctx* ctx, Group* g, int G, GraphRec** out) {
   r.launches = (int)cnt;
   g->graphs.push_back(r);
   *out = &g->graphs.back();
+  return FCCF_OK;
+}
+
+// The batched pipeline of the G lanes whose call blocks are in g->d_calls (graph replay, or plain launches).
+static int group_launch(fccf_ctx* ctx, Group* g, int G, bool fast) {
+  cudaStream_t s = g->stream;
+  if (ctx->use_graph) {
+    GraphRec* r = nullptr;
+    int rc = group_graph(ctx, g, G, fast, &r);
+    if (rc) return rc;
+    CK(cudaGraphLaunch(r->exec, s));
+    g->launches += (uint64_t)r->launches;
+  } else {
+    g->tab.immediate = true; g->tab.off = 0; g->tab.overflow = false;
+    int rc = group_pipeline(ctx, g, G, &g->tab, &g->launches, false, fast);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(g->ev[4], s));
   return FCCF_OK;
 }
 
@@ -461,18 +552,14 @@ static int group_enqueue(fccf_ctx* ctx, Group* g, int G, int pair0, const float*
   }
   CK(cudaMemcpyAsync(g->d_calls, g->h_calls, sizeof(CallArgs) * (size_t)G, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(g->ev[1], s));
-  if (ctx->use_graph) {
-    GraphRec* r = nullptr;
-    int rc = group_graph(ctx, g, G, &r);
-    if (rc) return rc;
-    CK(cudaGraphLaunch(r->exec, s));
-    g->launches += (uint64_t)r->launches;
-  } else {
-    g->tab.immediate = true; g->tab.off = 0; g->tab.overflow = false;
-    int rc = group_pipeline(ctx, g, G, &g->tab, &g->launches, false);
-    if (rc) return rc;
-  }
-  CK(cudaEventRecord(g->ev[4], s));
+  // cluster VoxelGrid first, unless a cloud cannot fit its scratch or this leaf missed recently
+  size_t nmax = 0;
+  for (int l = 0; l < G; l++) nmax = std::max(nmax, std::max(n_src[l], n_tar[l]));
+  bool fast = ctx->vg_fast && g->vf.ncl > 0 && nmax <= (size_t)g->vf.stride && nmax <= (size_t)vg_fast_nmax();
+  if (fast && ctx->fast_miss_ttl > 0 && leaf <= ctx->fast_miss_leaf) { fast = false; ctx->fast_miss_ttl--; }
+  g->fast = fast; g->leaf = leaf;
+  int rc = group_launch(ctx, g, G, fast);
+  if (rc) return rc;
   g->busy = true;
   return FCCF_OK;
 }
@@ -480,9 +567,25 @@ static int group_enqueue(fccf_ctx* ctx, Group* g, int G, int pair0, const float*
 // Waits for the group's registrations, returns their matrices (T_out indexed by pair) and adds the
 // group's device timings to *tm.  Returns the worst status of its lanes.
 static int group_finish(fccf_ctx* ctx, Group* g, float* T_out, fccf_timing* tm) {
+  g->busy = false;                 // whatever happens below, the group is drained or abandoned
   CK(cudaStreamSynchronize(g->stream));
   CK(cudaGetLastError());
-  g->busy = false;
+  if (g->fast) {
+    ctx->fast_runs++;
+    bool miss = false;
+    for (int l = 0; l < g->G; l++) miss = miss || (g->lanes[l].h_st->status & ST_VG_FAST_MISS);
+    if (miss) {
+      // a cloud the cluster VoxelGrid could not hold: the same call blocks and raw clouds are still on the
+      // device, so the sequence is simply replayed through the generic kernels
+      ctx->fast_misses++;
+      ctx->fast_miss_leaf = std::max(ctx->fast_miss_leaf, g->leaf); ctx->fast_miss_ttl = 64;
+      g->fast = false;
+      int rc = group_launch(ctx, g, g->G, false);
+      if (rc) return rc;
+      CK(cudaStreamSynchronize(g->stream));
+      CK(cudaGetLastError());
+    }
+  }
   int worst = FCCF_OK;
   for (int l = 0; l < g->G; l++) {
     Lane& L = g->lanes[l];
@@ -507,15 +610,29 @@ static int group_finish(fccf_ctx* ctx, Group* g, float* T_out, fccf_timing* tm) 
   return worst;
 }
 
+// Waits for every group that still has work in flight (an earlier call that returned on an error) and marks
+// it idle, without touching any result buffer: after this no copy from a caller's host buffer is pending and
+// no lane refers to an old batch.
+static void drain_groups(fccf_ctx* ctx) {
+  for (Group* g : ctx->groups) {
+    cudaStreamSynchronize(g->stream);
+    g->busy = false; g->G = 0;
+    for (Lane& L : g->lanes) L.pair = -1;
+  }
+  cudaGetLastError();
+}
+
 static int register_one(fccf_ctx* ctx, const float* src, size_t n_src, const float* tar, size_t n_tar, float leaf, float T_out[16], fccf_timing* timing, bool host_in) {
   if (!ctx) return FCCF_ERR_NO_DEVICE;
   if (!T_out || (!src && n_src) || (!tar && n_tar) || !(leaf > 0.f)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   Group* g = ctx->groups[0];
+  drain_groups(ctx);
   int rc = ensure_capacity(ctx, g, 0, n_tar, n_src);
   if (rc) return rc;
+  if ((rc = ensure_fast_scratch(ctx, g, std::max(n_tar, n_src)))) return rc;
   rc = group_enqueue(ctx, g, 1, 0, &src, &n_src, &tar, &n_tar, leaf, host_in);
-  if (rc) return rc;
+  if (rc) { drain_groups(ctx); return rc; }
   fccf_timing tm; memset(&tm, 0, sizeof tm);
   rc = group_finish(ctx, g, T_out, &tm);
   if (timing) *timing = tm;
@@ -551,9 +668,23 @@ static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, co
   const int ngroups = std::min(nchunks, max_groups);
   size_t nmax = 0;
   for (int b = 0; b < n_pairs; b++) { if ((!src[b] && n_src[b]) || (!tar[b] && n_tar[b])) { ctx->err = "bad argument"; return FCCF_ERR_ARG; } nmax = std::max(nmax, std::max(n_src[b], n_tar[b])); }
+  drain_groups(ctx);               // nothing of an earlier (failed) call may still be in flight
   while ((int)ctx->groups.size() < ngroups) { Group* g = nullptr; int rc = group_create(ctx, &g); if (rc) return rc; ctx->groups.push_back(g); }
-  for (int k = 0; k < nchunks; k++)
-    for (int l = 0; l < chunk[k]; l++) { int rc = ensure_capacity(ctx, ctx->groups[k % ngroups], l, nmax, nmax); if (rc) return rc; }
+  // a lane is sized for the largest cloud of the pairs it will actually receive (pair p0 + l of every chunk of its group)
+  {
+    int p0c = 0;
+    std::vector<std::vector<size_t>> need(ngroups);
+    for (int k = 0; k < nchunks; k++) {
+      std::vector<size_t>& nd = need[k % ngroups];
+      if ((int)nd.size() < chunk[k]) nd.resize(chunk[k], 0);
+      for (int l = 0; l < chunk[k]; l++) nd[l] = std::max(nd[l], std::max(n_src[p0c + l], n_tar[p0c + l]));
+      p0c += chunk[k];
+    }
+    for (int gi = 0; gi < ngroups; gi++) {
+      for (size_t l = 0; l < need[gi].size(); l++) { int rc = ensure_capacity(ctx, ctx->groups[gi], (int)l, need[gi][l], need[gi][l]); if (rc) return rc; }
+      int rc = ensure_fast_scratch(ctx, ctx->groups[gi], nmax); if (rc) return rc;
+    }
+  }
   // device time of the whole batch: an event on group 0's stream before the first enqueue, and one
   // after it has waited for the last sequence of the other groups
   Group* Z = ctx->groups[0];
@@ -564,12 +695,12 @@ static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, co
   int p0 = 0;
   for (int k = 0; k < nchunks; k++) {
     Group* g = ctx->groups[k % ngroups];
-    if (g->busy) { int rc = group_finish(ctx, g, T_out, &acc); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc; if (rc) worst = rc; }
+    if (g->busy) { int rc = group_finish(ctx, g, T_out, &acc); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) { drain_groups(ctx); return rc; } if (rc) worst = rc; }
     const int G = chunk[k];
     auto te0 = std::chrono::steady_clock::now();
     int rc = group_enqueue(ctx, g, G, p0, src + p0, n_src + p0, tar + p0, n_tar + p0, leaf, host_in);
     enq_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - te0).count();
-    if (rc) return rc;
+    if (rc) { drain_groups(ctx); return rc; }
     p0 += G;
   }
   if (getenv("FCCF_DEBUG_TIMING")) fprintf(stderr, "[fccf] batch of %d in %d chunk(s): host enqueue %.3f ms total\n", n_pairs, nchunks, enq_ms);
@@ -577,7 +708,7 @@ static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, co
   CK(cudaEventRecord(Z->sev[7], Z->stream));
   for (int gi = 0; gi < ngroups; gi++) {
     Group* g = ctx->groups[gi];
-    if (g->busy) { int rc = group_finish(ctx, g, T_out, &acc); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) return rc; if (rc) worst = rc; }
+    if (g->busy) { int rc = group_finish(ctx, g, T_out, &acc); if (rc == FCCF_ERR_CUDA || rc == FCCF_ERR_ARG) { drain_groups(ctx); return rc; } if (rc) worst = rc; }
   }
   CK(cudaEventSynchronize(Z->sev[7]));
   cudaEventElapsedTime(&acc.total_ms, Z->sev[6], Z->sev[7]);
@@ -611,17 +742,30 @@ int fccf_voxelgrid(fccf_ctx* ctx, const float* xyz, size_t n, float leaf, float*
   if (!ctx) return FCCF_ERR_NO_DEVICE;
   if (!n_out || (!xyz && n) || !(leaf > 0.f)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
+  drain_groups(ctx);
   int rc = ensure_capacity(ctx, ctx->groups[0], 0, n, 0);
   if (rc) return rc;
+  if ((rc = ensure_fast_scratch(ctx, ctx->groups[0], n))) return rc;
   cudaStream_t s = ctx->stream;
   CK(cudaStreamSynchronize(s));
   if (n) CK(cudaMemcpyAsync(ctx->L0().d_raw[0], xyz, n * 12, cudaMemcpyHostToDevice, s));
-  std::vector<Work> ws; Batch w = single_batch(ctx, ws);
-  if ((rc = set_single_call(ctx, (int)n, 0, leaf))) return rc;
-  launch_init_state(s, w, ctx->G0().d_calls, &ctx->launches);
-  launch_voxelgrid(s, w, 0, 1, &ctx->launches);
-  CK(cudaMemcpyAsync(ctx->L0().h_st, ctx->L0().d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  Group& g = ctx->G0();
+  // the cluster kernel first; a cloud it cannot hold raises ST_VG_FAST_MISS and the generic kernels run
+  bool fast = ctx->vg_fast && g.vf.ncl > 0 && n <= (size_t)g.vf.stride && n <= (size_t)vg_fast_nmax() && !getenv("FCCF_VG_GENERIC");
+  for (int attempt = 0; attempt < 2; attempt++) {
+    std::vector<Work> ws; Batch w = single_batch(ctx, ws);
+    if ((rc = set_single_call(ctx, (int)n, 0, leaf))) return rc;
+    launch_init_state(s, w, g.d_calls, &ctx->launches);
+    if (fast) CK(launch_voxelgrid_fast(s, w, 0, 1, g.vf, &ctx->launches));
+    else launch_voxelgrid(s, w, 0, 1, &ctx->launches);
+    CK(cudaMemcpyAsync(ctx->L0().h_st, ctx->L0().d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (fast) ctx->fast_runs++;
+    if (!fast || !(ctx->L0().h_st->status & ST_VG_FAST_MISS)) break;
+    ctx->fast_misses++;
+    fast = false;
+  }
   size_t m = (size_t)ctx->L0().h_st->vg[0][0].n_out;
   *n_out = m;
   if (m && out_xyz) CK(cudaMemcpy(out_xyz, ctx->L0().c[0].vg_xyz[0], m * 12, cudaMemcpyDeviceToHost));
@@ -802,6 +946,13 @@ int fccf_quick_verify(fccf_ctx* ctx, float* T, size_t n_hyp, const float* planes
 // ---------------------------------------------------------------------------------------------
 int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_bytes, size_t* bytes, int* dtype) {
   if (!ctx) return FCCF_ERR_NO_DEVICE;
+  if (name_c && !strcmp(name_c, "vg_fast")) {      // [sequences run through the cluster VoxelGrid, of which re-run through the generic kernels]
+    long long v[2] = {(long long)ctx->fast_runs, (long long)ctx->fast_misses};
+    if (bytes) *bytes = sizeof v;
+    if (dtype) *dtype = FCCF_I64;
+    if (dst) { if (cap_bytes < sizeof v) { ctx->err = "blob buffer too small"; return FCCF_ERR_ARG; } memcpy(dst, v, sizeof v); }
+    return FCCF_OK;
+  }
   if (!name_c || !ctx->have_run) { ctx->err = "no run to inspect"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -25,7 +25,8 @@ inline int fccf_topk(const fccf_params& p) { int k = (int)p.fine_verify_number; 
 #define RS_TILE (RS_T * RS_I)
 
 // status bits written by kernels (checked by the host after the final synchronise)
-enum { ST_OCT_DEPTH = 1, ST_HYP_OVERFLOW = 2, ST_KEYBITS = 4, ST_CENTRE_OVERFLOW = 8, ST_HASH_FULL = 16, ST_CLUSTER_MEMBERS = 32 };
+enum { ST_OCT_DEPTH = 1, ST_HYP_OVERFLOW = 2, ST_KEYBITS = 4, ST_CENTRE_OVERFLOW = 8, ST_HASH_FULL = 16, ST_CLUSTER_MEMBERS = 32,
+       ST_VG_FAST_MISS = 64 };   // not an error: the cluster VoxelGrid (voxelgrid_fast.cu) could not hold a cloud, the host re-runs the generic kernels
 
 struct VGState {
   int n_in, n_finite;
@@ -226,6 +227,13 @@ int cluster_deg_ints();
 void score_init_attributes();   // one-time function attributes (not allowed inside a stream capture)
 // VoxelGrid stage `stage` (0: on raw clouds, 1: on the stage-0 output) for both clouds
 void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uint64_t* launches);
+// The same stage by one thread-block cluster per cloud (voxelgrid_fast.cu).  scratch: per resident cluster
+// 2 x `stride` float4 (never leaves L2).  Clouds it cannot hold raise ST_VG_FAST_MISS.
+struct VgFastScratch { float4* pre = nullptr; float4* queue = nullptr; int stride = 0; int ncl = 0; };
+int vg_fast_init();             // one-time attributes; returns the number of co-resident clusters (0: unavailable)
+int vg_fast_max_clusters();
+int vg_fast_nmax();             // largest cloud (points) the cluster path takes
+cudaError_t launch_voxelgrid_fast(cudaStream_t s, const Batch& b, int stage, int ncloud, const VgFastScratch& sc, uint64_t* launches);
 // face_extrate for both clouds (input: vg_xyz[1] with st->vg[1][c].n_out points)
 void launch_planes(cudaStream_t s, const Batch& b, int ncloud, int src_stage, uint64_t* launches);
 void launch_hypotheses(cudaStream_t s, const Batch& b, uint64_t* launches);
