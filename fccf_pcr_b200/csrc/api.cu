@@ -174,7 +174,7 @@ static void group_destroy(Group* g) {
     for (int c = 0; c < 2; c++) { if (L.cloud_arena[c].base) cudaFree(L.cloud_arena[c].base); if (L.d_raw[c]) cudaFree(L.d_raw[c]); }
     if (L.hyp_arena.base) cudaFree(L.hyp_arena.base);
   }
-  if (g->vf.pre) cudaFree(g->vf.pre);
+  if (g->vf.info) cudaFree(g->vf.info);
   if (g->vf.queue) cudaFree(g->vf.queue);
   if (g->d_st_all) cudaFree(g->d_st_all);
   if (g->h_st_all) cudaFreeHost(g->h_st_all);
@@ -266,14 +266,14 @@ static int ensure_fast_scratch(fccf_ctx* ctx, Group* g, size_t n) {
   if ((size_t)g->vf.stride >= want) return FCCF_OK;
   CK(cudaStreamSynchronize(g->stream));
   group_drop_graphs(g);
-  if (g->vf.pre) cudaFree(g->vf.pre);
+  if (g->vf.info) cudaFree(g->vf.info);
   if (g->vf.queue) cudaFree(g->vf.queue);
   g->vf = VgFastScratch();
   int ncl = std::min(vg_fast_max_clusters(), 2 * ctx->max_lanes);
   if (ncl < 1) return FCCF_OK;
-  if (cudaMalloc(&g->vf.pre, (size_t)ncl * want * 16) != cudaSuccess || cudaMalloc(&g->vf.queue, (size_t)ncl * want * 16) != cudaSuccess) {
+  if (cudaMalloc(&g->vf.info, (size_t)ncl * want * 4) != cudaSuccess || cudaMalloc(&g->vf.queue, (size_t)ncl * want * 16) != cudaSuccess) {
     cudaGetLastError();
-    if (g->vf.pre) cudaFree(g->vf.pre);
+    if (g->vf.info) cudaFree(g->vf.info);
     g->vf = VgFastScratch();
     ctx->err = "out of device memory (cluster VoxelGrid scratch)"; return FCCF_ERR_CUDA;
   }
@@ -401,6 +401,13 @@ AngleCuts make_angle_cuts(const fccf_params& p) {
   return c;
 }
 }  // namespace fccf
+
+// device buffers of a stand-alone entry point, released on every return path
+struct DevTmp {
+  std::vector<void*> ptrs;
+  ~DevTmp() { for (void* p : ptrs) if (p) cudaFree(p); }
+  template <class T> cudaError_t get(T** p, size_t bytes) { *p = nullptr; cudaError_t e = cudaMalloc((void**)p, bytes ? bytes : 4); if (e == cudaSuccess) ptrs.push_back(*p); return e; }
+};
 
 static Work lane_work(const Lane& L) {
   Work w; w.c[0] = L.c[0]; w.c[1] = L.c[1]; w.h = L.h; w.st = L.d_st;
@@ -865,12 +872,16 @@ int fccf_score_hypotheses_bench(fccf_ctx* ctx, const float* T, size_t n_hyp, con
   int rc = score_prepare(ctx, T, n_hyp, s1_xyz, n1, s2_xyz, n2);
   if (rc) return rc;
   cudaStream_t s = ctx->stream;
-  for (int w = 0; w < 3; w++) launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, ctx->itab, &ctx->launches);
+  // every launch takes one argument block of the immediate table: rewind it to the mark each time (the block
+  // is stream-ordered before its kernel and identical from launch to launch), so no repeat count overflows it
+  const size_t mark = ctx->itab.off;
+  for (int w = 0; w < 3; w++) { ctx->itab.off = mark; launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, ctx->itab, &ctx->launches); }
   CK(cudaStreamSynchronize(s));
   CK(cudaEventRecord(ctx->G0().ev[0], s));
-  for (int r = 0; r < repeat; r++) launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, ctx->itab, &ctx->launches);
+  for (int r = 0; r < repeat; r++) { ctx->itab.off = mark; launch_score_list(s, ctx->p, ctx->d_sc_T, (int)n_hyp, ctx->d_sc_s2, ctx->sc_ws, ctx->d_sc_scores, ctx->itab, &ctx->launches); }
   CK(cudaEventRecord(ctx->G0().ev[1], s));
   CK(cudaStreamSynchronize(s));
+  if (ctx->itab.overflow) { ctx->err = "argument table overflow"; return FCCF_ERR_CAPACITY; }
   float ms = 0; cudaEventElapsedTime(&ms, ctx->G0().ev[0], ctx->G0().ev[1]);
   if (kernel_ms) *kernel_ms = ms / repeat;
   if (scores && n_hyp) CK(cudaMemcpy(scores, ctx->d_sc_scores, n_hyp * 4, cudaMemcpyDeviceToHost));
@@ -896,11 +907,14 @@ int fccf_score_best(fccf_ctx* ctx, size_t index_base, int64_t* packed_host, int6
 int fccf_score_counts(fccf_ctx* ctx, size_t hyp, int32_t* rows, size_t cap_rows, size_t* n_rows) {
   if (!ctx) return FCCF_ERR_NO_DEVICE;
   if (!rows || !n_rows || !ctx->d_sc_ss) { ctx->err = "bad argument / no previous fccf_score_hypotheses call"; return FCCF_ERR_ARG; }
+  if (hyp >= ctx->sc_nhyp) { ctx->err = "hypothesis index beyond the last scored list"; return FCCF_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
+  DevTmp tmp;
   int* d_rows = nullptr; int* d_n = nullptr;
-  CK(cudaMalloc(&d_rows, std::max<size_t>(cap_rows, 1) * 20));
-  CK(cudaMalloc(&d_n, 4));
+  CK(tmp.get(&d_rows, std::max<size_t>(cap_rows, 1) * 20));
+  CK(tmp.get(&d_n, 4));
   CK(cudaMemsetAsync(d_n, 0, 4, ctx->stream));
+  ctx->itab.off = 0; ctx->itab.overflow = false; ctx->itab.immediate = true; ctx->itab.stream = ctx->stream;
   launch_score_dump(ctx->stream, ctx->p, ctx->d_sc_T + 16 * hyp, ctx->d_sc_s2, ctx->sc_ws, d_rows, (int)cap_rows, d_n, ctx->itab, &ctx->launches);
   int n = 0;
   CK(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -908,7 +922,6 @@ int fccf_score_counts(fccf_ctx* ctx, size_t hyp, int32_t* rows, size_t cap_rows,
   *n_rows = (size_t)n;
   size_t m = std::min<size_t>((size_t)n, cap_rows);
   if (m) CK(cudaMemcpy(rows, d_rows, m * 20, cudaMemcpyDeviceToHost));
-  cudaFree(d_rows); cudaFree(d_n);
   CK(cudaGetLastError());
   return FCCF_OK;
 }
@@ -923,8 +936,9 @@ int fccf_quick_verify(fccf_ctx* ctx, float* T, size_t n_hyp, const float* planes
   std::vector<float> p1(8 * FCCF_MAXF, 0.f), p2(8 * FCCF_MAXF, 0.f);
   for (int i = 0; i < f1; i++) for (int k = 0; k < 7; k++) p1[8 * i + k] = planes1[7 * i + k];
   for (int i = 0; i < f2; i++) for (int k = 0; k < 7; k++) p2[8 * i + k] = planes2[7 * i + k];
-  CK(cudaMalloc(&dT, n_hyp * 64)); CK(cudaMalloc(&dp1, p1.size() * 4)); CK(cudaMalloc(&dp2, p2.size() * 4)); CK(cudaMalloc(&dsc, n_hyp * 4));
-  CK(cudaMalloc(&dnp, n_hyp * 4)); CK(cudaMalloc(&dpr, n_hyp * 128)); CK(cudaMalloc(&dit, n_hyp * 4));
+  DevTmp tmp;
+  CK(tmp.get(&dT, n_hyp * 64)); CK(tmp.get(&dp1, p1.size() * 4)); CK(tmp.get(&dp2, p2.size() * 4)); CK(tmp.get(&dsc, n_hyp * 4));
+  CK(tmp.get(&dnp, n_hyp * 4)); CK(tmp.get(&dpr, n_hyp * 128)); CK(tmp.get(&dit, n_hyp * 4));
   CK(cudaMemcpy(dT, T, n_hyp * 64, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dp1, p1.data(), p1.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dp2, p2.data(), p2.size() * 4, cudaMemcpyHostToDevice));
@@ -936,7 +950,6 @@ int fccf_quick_verify(fccf_ctx* ctx, float* T, size_t n_hyp, const float* planes
   if (pair_count) CK(cudaMemcpy(pair_count, dnp, n_hyp * 4, cudaMemcpyDeviceToHost));
   if (pairs) CK(cudaMemcpy(pairs, dpr, n_hyp * 128, cudaMemcpyDeviceToHost));
   if (iters) CK(cudaMemcpy(iters, dit, n_hyp * 4, cudaMemcpyDeviceToHost));
-  cudaFree(dT); cudaFree(dp1); cudaFree(dp2); cudaFree(dsc); cudaFree(dnp); cudaFree(dpr); cudaFree(dit);
   CK(cudaGetLastError());
   return FCCF_OK;
 }
@@ -960,9 +973,10 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
   std::string name(name_c);
   const PipeState& st = *ctx->L0().h_st;
   std::vector<char> out; int dt = FCCF_F32;
+  cudaError_t fetch_err = cudaSuccess;
   auto fetch = [&](const void* dptr, size_t nbytes) -> std::vector<char> {
     std::vector<char> v(nbytes);
-    if (nbytes) cudaMemcpy(v.data(), dptr, nbytes, cudaMemcpyDeviceToHost);
+    if (nbytes) { cudaError_t e = cudaMemcpy(v.data(), dptr, nbytes, cudaMemcpyDeviceToHost); if (e != cudaSuccess) fetch_err = e; }
     return v;
   };
   auto put = [&](const void* p, size_t nbytes, int d) { out.assign((const char*)p, (const char*)p + nbytes); dt = d; };
@@ -1055,7 +1069,8 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
     ScoreWS ws = ctx->L0().h.fv; ws.ss = &ctx->L0().d_st->fv; ws.status = &ctx->L0().d_st->status;
     int cap_rows = std::max(st.fv.n_occ, 1);
     int* d_rows = nullptr; int* d_n = nullptr;
-    CK(cudaMalloc(&d_rows, (size_t)cap_rows * 20)); CK(cudaMalloc(&d_n, 4));
+    DevTmp tmp;
+    CK(tmp.get(&d_rows, (size_t)cap_rows * 20)); CK(tmp.get(&d_n, 4));
     std::vector<int> all, off;
     for (int k = 0; k < st.n_top[ti]; k++) {
       CK(cudaMemsetAsync(d_n, 0, 4, ctx->stream));
@@ -1069,7 +1084,6 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
       for (int i = 0; i < n; i++) for (int a = 0; a < 5; a++) all.push_back(rows[5 * order[i] + a]);
     }
     off.push_back((int)all.size() / 5);
-    cudaFree(d_rows); cudaFree(d_n);
     if (stem == "fv_counts") put(all.data(), all.size() * 4, FCCF_I32); else put(off.data(), off.size() * 4, FCCF_I32);
   }
   else if (name == "type_best") put(st.type_best, sizeof st.type_best, FCCF_F32);
@@ -1077,6 +1091,7 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
   else if (name == "final_T") put(st.T_final, 64, FCCF_F32);
   else ok = false;
   if (!ok) { ctx->err = "unknown blob: " + name; return FCCF_ERR_ARG; }
+  if (fetch_err != cudaSuccess) { ctx->err = std::string("blob read-back failed: ") + cudaGetErrorString(fetch_err); cudaGetLastError(); return FCCF_ERR_CUDA; }
   if (bytes) *bytes = out.size();
   if (dtype) *dtype = dt;
   if (dst) { if (out.size() > cap_bytes) { ctx->err = "blob buffer too small"; return FCCF_ERR_ARG; } if (!out.empty()) memcpy(dst, out.data(), out.size()); }

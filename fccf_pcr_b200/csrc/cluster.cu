@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
     if (n == 0) {
       if (t == 0) { centre[0] = 1.f; for (int k = 1; k < 8; k++) centre[k] = 0.f; st->n_centre[ty] = 1; st->n_seeds[ty] = 0; }
     } else {
-      for (int k = t; k < n * 8; k += 1024) centre[k] = qt[k];
-      if (t == 0) { st->n_centre[ty] = n; st->n_seeds[ty] = 0; }
+      // cluster_number_threshold <= FCCF_MAXCENTRE is checked on the host; clamp anyway and report it
+      const int m = n < FCCF_MAXCENTRE ? n : FCCF_MAXCENTRE;
+      for (int k = t; k < m * 8; k += 1024) centre[k] = qt[k];
+      if (t == 0) { st->n_centre[ty] = m; st->n_seeds[ty] = 0; if (m < n) atomicOr(&st->status, ST_CENTRE_OVERFLOW); }
     }
     return;
   }

@@ -228,8 +228,8 @@ void score_init_attributes();   // one-time function attributes (not allowed ins
 // VoxelGrid stage `stage` (0: on raw clouds, 1: on the stage-0 output) for both clouds
 void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uint64_t* launches);
 // The same stage by one thread-block cluster per cloud (voxelgrid_fast.cu).  scratch: per resident cluster
-// 2 x `stride` float4 (never leaves L2).  Clouds it cannot hold raise ST_VG_FAST_MISS.
-struct VgFastScratch { float4* pre = nullptr; float4* queue = nullptr; int stride = 0; int ncl = 0; };
+// `stride` u32 + `stride` float4 (sized to stay in L2).  Clouds it cannot hold raise ST_VG_FAST_MISS.
+struct VgFastScratch { u32* info = nullptr; float4* queue = nullptr; int stride = 0; int ncl = 0; };
 int vg_fast_init();             // one-time attributes; returns the number of co-resident clusters (0: unavailable)
 int vg_fast_max_clusters();
 int vg_fast_nmax();             // largest cloud (points) the cluster path takes

@@ -7,7 +7,7 @@
 //   match_compact one CTA: ordered list of the matched (pair,pair) indices
 //   hyp_count     one WARP per match: the (third plane of cloud 1) x (third plane of cloud 2) combinations
 //                 are split over the lanes in the reference's loop order, ballots count them
-//   match_scan    ordered scan of the counts per roughness type (three 21-bit fields of a u64)
+//   match_scan    ordered scan of the counts per roughness type (three saturating 32-bit counters)
 //   emit_hyp      one warp per match: every lane with a passing combination solves its translation and
 //                 writes the hypothesis (3x4 + quaternion/translation) at pool offset + ballot rank
 #include "fccf_dev.cuh"
@@ -231,41 +231,49 @@ __global__ void __launch_bounds__(128) hyp_count_kernel(const HypArgs* __restric
 }
 
 // ---- ordered scan of the counts per type: pool offsets in the reference's push_back order ----
+// Three 32-bit counters side by side (one per roughness type), each saturating at cap_hyp + 1: a pool that
+// outgrows the arena is reported (ST_HYP_OVERFLOW) instead of wrapping into its neighbour.
+struct u3 { u32 a[3]; };
+__device__ __forceinline__ u32 sat_add(u32 x, u32 y, u32 lim) { const u32 s = x + y; return (s < x || s > lim) ? lim : s; }
 __global__ void __launch_bounds__(1024) match_scan_kernel(const HypArgs* __restrict__ AB) {
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  __shared__ u64 s_w64[32];
-  __shared__ u64 s_carry;
+  __shared__ u32 s_w[3][32];
+  __shared__ u32 s_carry[3];
   const int B1 = st->base[0].B, B2 = st->base[1].B;
   const int NM = B1 * B2;
-  if (t == 0) s_carry = 0;
+  const u32 lim = (u32)A.cap_hyp + 1u;
+  if (t < 3) s_carry[t] = 0;
   __syncthreads();
   for (int i0 = 0; i0 < NM; i0 += 1024) {
     int idx = i0 + t;
-    u64 x = 0;
-    if (idx < NM) { int cnt = A.match_cnt[idx]; if (cnt > 0) { int ty = st->base[0].type[idx / B2]; x = (u64)cnt << (21 * ty); } }
-    u64 inc = x;
-    for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
-    if (lane == 31) s_w64[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      u64 w = s_w64[lane], wi = w;
-      for (int d = 1; d < 32; d <<= 1) { u64 y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += y; }
-      s_w64[lane] = wi - w;
+    u32 x[3] = {0u, 0u, 0u}; int ty = -1;
+    if (idx < NM) { int cnt = A.match_cnt[idx]; if (cnt > 0) { ty = st->base[0].type[idx / B2]; x[ty] = (u32)cnt; } }
+    u32 inc[3] = {x[0], x[1], x[2]};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, inc[k], d); if (lane >= d) inc[k] = sat_add(inc[k], y, lim); }
+      if (lane == 31) s_w[k][warp] = inc[k];
     }
     __syncthreads();
-    u64 excl = s_carry + s_w64[warp] + inc - x;
-    if (idx < NM && x) { int ty = st->base[0].type[idx / B2]; A.match_off[idx] = (int)((excl >> (21 * ty)) & 0x1fffffull); }
+    if (warp < 3) {
+      u32 wv = s_w[warp][lane], wi = wv;
+      for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi = sat_add(wi, y, lim); }
+      u32 ex = __shfl_up_sync(0xffffffffu, wi, 1);
+      s_w[warp][lane] = lane ? ex : 0u;
+    }
     __syncthreads();
-    if (t == 1023) s_carry = excl + x;
+    if (ty >= 0) A.match_off[idx] = (int)sat_add(sat_add(s_carry[ty], s_w[ty][warp], lim), inc[ty] - x[ty], lim);
+    __syncthreads();
+    if (t == 1023) { for (int k = 0; k < 3; k++) s_carry[k] = sat_add(sat_add(s_carry[k], s_w[k][warp], lim), inc[k], lim); }
     __syncthreads();
   }
   if (t == 0) {
-    int n0 = (int)(s_carry & 0x1fffffull), n1 = (int)((s_carry >> 21) & 0x1fffffull), n2 = (int)((s_carry >> 42) & 0x1fffffull);
-    if (n0 + n1 + n2 > A.cap_hyp) { atomicOr(&st->status, ST_HYP_OVERFLOW); n0 = n1 = n2 = 0; }
-    st->n_hyp[0] = n0; st->n_hyp[1] = n1; st->n_hyp[2] = n2;
-    st->hyp_off[0] = 0; st->hyp_off[1] = n0; st->hyp_off[2] = n0 + n1; st->hyp_off[3] = n0 + n1 + n2;
+    u32 n0 = s_carry[0], n1 = s_carry[1], n2 = s_carry[2];
+    if ((unsigned long long)n0 + n1 + n2 > (unsigned long long)A.cap_hyp) { atomicOr(&st->status, ST_HYP_OVERFLOW); n0 = n1 = n2 = 0; }
+    st->n_hyp[0] = (int)n0; st->n_hyp[1] = (int)n1; st->n_hyp[2] = (int)n2;
+    st->hyp_off[0] = 0; st->hyp_off[1] = (int)n0; st->hyp_off[2] = (int)(n0 + n1); st->hyp_off[3] = (int)(n0 + n1 + n2);
     st->n_match = NM;
   }
 }

@@ -14,8 +14,8 @@
 //      the point among the points of its digit in index order = running count of (warp, d), bumped with
 //      per-bit ballots, + prefix over the warps of the CTA (shared memory) + prefix over the CTAs (the
 //      owner warp of d reads / writes the CTA tables through DSMEM) + prefix over the digits.  The
-//      point and its rank word go to the scratch as one 16-byte record.
-//   B2 every record is written as (x, y, z, slot) at its rank into the queue of its digit: the queue
+//      rank word (slot, digit, rank inside the warp's run) goes to the scratch, 4 bytes per point.
+//   B2 every point is written as (x, y, z, slot) at its rank into the queue of its digit: the queue
 //      of a digit lists its points in ascending index
 //   C  owner warp (digit d = w*CS + rank) walks its queue 32 entries at a time: lanes of one round
 //      that hit the same cell are found with ballots over the slot bits and applied in lane order,
@@ -135,7 +135,7 @@ __device__ __forceinline__ unsigned vf_group(bool in, int v, int nbits) {
 }
 
 template <int CS>
-__global__ void __launch_bounds__(VF_T, 1) vg_fast_kernel(const VFArgs* __restrict__ AB, int ncloud, int nitems, float4* __restrict__ pre_all,
+__global__ void __launch_bounds__(VF_T, 1) vg_fast_kernel(const VFArgs* __restrict__ AB, int ncloud, int nitems, u32* __restrict__ info_all,
                                                           float4* __restrict__ queue_all, int stride) {
   typedef VfGeo<CS> G;
   constexpr int DIG = G::DIG, DB = G::DB, MAXSLOT = G::MAXSLOT, TABSTRIDE = G::TABSTRIDE;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(VF_T, 1) vg_fast_kernel(const VFArgs* __restri
   int* s_cta = (int*)(vf_smem + G::OFF_CTA);
   int* s_glob = (int*)(vf_smem + G::OFF_GLOB);
   int* s_fail = (int*)(vf_smem + G::OFF_FAIL);
-  float4* pre = pre_all + (size_t)cid * stride;     // (x, y, z, rank word) of every point, in index order
+  u32* info = info_all + (size_t)cid * stride;      // rank word of every point, in index order
   float4* queue = queue_all + (size_t)cid * stride;
   const int gw = r * VF_NW + w;
   u32* cw = cntw + w * DIG;                          // this warp's counter row
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(VF_T, 1) vg_fast_kernel(const VFArgs* __restri
     {
       const float mb0 = (float)minb[0], mb1 = (float)minb[1], mb2 = (float)minb[2];
       const int d0 = (int)div[0], d01 = (int)(div[0] * div[1]);
-      float4* prew = pre + first + lane;
+      u32* infow = info + first + lane;
       L.init(p, first, n, nr, lane, stgw);
       for (int k = 0; k < nr; k++) {
         float x, y, z;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(VF_T, 1) vg_fast_kernel(const VFArgs* __restri
           if ((peers & lt) == 0u) cw[d] = old + (u32)__popc(peers);
           word = ((u32)slot << 22) | ((u32)d << 14) | (old + (u32)__popc(peers & lt));
         }
-        if (valid) prew[k * 32] = make_float4(x, y, z, __uint_as_float(word));
+        if (valid) infow[k * 32] = word;
         __syncwarp();
       }
     }
@@ -351,22 +351,23 @@ __global__ void __launch_bounds__(VF_T, 1) vg_fast_kernel(const VFArgs* __restri
     __syncwarp();
 
     VF_MARK(4)
-    // ---- B2: points into the queues of their digits -------------------------------------------
+    // ---- B2: points into the queues of their digits (the cloud is read a third time, out of L2) ----
     {
-      const float4* prew = pre + first + lane;
+      const u32* infow = info + first + lane;
+      L.init(p, first, n, nr, lane, stgw);
+      u32 w0 = 0xffffffffu, w1 = 0xffffffffu;
       const int lim = n - first - lane;                  // rounds k with k*32 < lim hold a point of this lane
-      float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0, e2 = e0;
-      if (0 < lim) e0 = __ldcg(prew);
-      if (32 < lim) e1 = __ldcg(prew + 32);
-      if (64 < lim) e2 = __ldcg(prew + 64);
+      if (0 < lim) w0 = __ldcg(infow);
+      if (32 < lim) w1 = __ldcg(infow + 32);
       for (int k = 0; k < nr; k++) {
-        const float4 e = e0;
-        e0 = e1; e1 = e2;
-        if ((k + 3) * 32 < lim) e2 = __ldcg(prew + (k + 3) * 32);
-        const u32 word = __float_as_uint(e.w);
-        if (k * 32 < lim && word != 0xffffffffu) {
+        float x, y, z;
+        L.get(k, x, y, z);
+        const u32 word = w0;
+        w0 = w1; w1 = 0xffffffffu;
+        if ((k + 2) * 32 < lim) w1 = __ldcg(infow + (k + 2) * 32);
+        if (word != 0xffffffffu) {
           const u32 pos = cw[(word >> 14) & 255u] + (word & 0x3fffu);
-          queue[pos] = make_float4(e.x, e.y, e.z, __int_as_float((int)(word >> 22)));
+          queue[pos] = make_float4(x, y, z, __int_as_float((int)(word >> 22)));
         }
       }
     }
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(VF_T, 1) vg_fast_kernel(const VFArgs* __restri
 // 33 clusters of 4 = 132 SMs).  A launch with few clouds takes clusters of 8 (a cloud finishes sooner: 195k
 // against 342k cycles for 200k points), a launch with more clouds than 8-CTA clusters fit takes clusters of 4.
 static int g_vf_max8 = -1, g_vf_max4 = -1, g_vf_force = 0;
+static size_t g_vf_l2_budget = (size_t)80 << 20;
 
 template <int CS> static int vf_query() {
   if (cudaFuncSetAttribute(vg_fast_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, VfGeo<CS>::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -512,6 +514,8 @@ int vg_fast_init() {
   g_vf_force = 0;
   if (const char* e = getenv("FCCF_VF_CS")) g_vf_force = atoi(e);
   g_vf_max8 = vf_query<8>(); g_vf_max4 = vf_query<4>();
+  { int dev = 0, l2 = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess && l2 > 0) g_vf_l2_budget = (size_t)l2 / 10 * 8; }
+  if (const char* e = getenv("FCCF_VF_L2_MB")) g_vf_l2_budget = (size_t)atoi(e) << 20;
   if (g_vf_max8 < 1 || g_vf_max4 < 1) { g_vf_max8 = g_vf_max4 = 0; }
   return vg_fast_max_clusters();
 }
@@ -539,9 +543,18 @@ cudaError_t launch_voxelgrid_fast(cudaStream_t s, const Batch& b, int stage, int
   }
   const VFArgs* dA = b.tab->put(As.data(), G);
   const int nitems = G * ncloud;
-  int cs = nitems > g_vf_max8 ? 4 : 8;
+  // Clusters in flight are capped so that what they keep between their phases (per point 12 B of the cloud, the
+  // 4-byte rank word and the 16-byte queue entry) stays inside L2: a scratch that spills turns every 16-byte
+  // queue store into DRAM read-modify-write traffic (measured: 94 B of DRAM traffic per point with 33 clusters
+  // of 200k-point clouds in flight, 3x slower scatter).  Stage 1 works on the stage-0 output (a fraction of
+  // the raw cloud; the count is device-side, so the capacity / 4 stands in for it).
+  const size_t per_cloud = (size_t)32 * (size_t)(stage == 0 ? sc.stride : (sc.stride + 3) / 4);
+  int allowed = (int)(g_vf_l2_budget / (per_cloud ? per_cloud : 1));
+  if (allowed < 2) allowed = 2;
+  int cs = (nitems > g_vf_max8 && allowed > g_vf_max8 + g_vf_max8 / 2) ? 4 : 8;
   if (g_vf_force == 4 || g_vf_force == 8) cs = g_vf_force;
   int ncl = cs == 8 ? g_vf_max8 : g_vf_max4;
+  if (ncl > allowed) ncl = allowed;
   if (ncl > sc.ncl) ncl = sc.ncl;
   if (ncl > nitems) ncl = nitems;
   if (ncl < 1) ncl = 1;
@@ -549,8 +562,8 @@ cudaError_t launch_voxelgrid_fast(cudaStream_t s, const Batch& b, int stage, int
   cfg.gridDim = dim3(cs * ncl); cfg.blockDim = dim3(VF_T); cfg.dynamicSmemBytes = cs == 8 ? VfGeo<8>::SMEM_BYTES : VfGeo<4>::SMEM_BYTES; cfg.stream = s;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cs == 8 ? cudaLaunchKernelEx(&cfg, vg_fast_kernel<8>, dA, ncloud, nitems, sc.pre, sc.queue, sc.stride)
-                          : cudaLaunchKernelEx(&cfg, vg_fast_kernel<4>, dA, ncloud, nitems, sc.pre, sc.queue, sc.stride);
+  cudaError_t e = cs == 8 ? cudaLaunchKernelEx(&cfg, vg_fast_kernel<8>, dA, ncloud, nitems, sc.info, sc.queue, sc.stride)
+                          : cudaLaunchKernelEx(&cfg, vg_fast_kernel<4>, dA, ncloud, nitems, sc.info, sc.queue, sc.stride);
   if (launches) *launches += 1;
   return e;
 }
