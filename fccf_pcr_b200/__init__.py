@@ -43,7 +43,8 @@ EXPORTS = [
     "fccf_default_params", "fccf_create", "fccf_destroy", "fccf_last_error", "fccf_set_params", "fccf_register",
     "fccf_register_device", "fccf_register_batch", "fccf_voxelgrid", "fccf_extract_planes", "fccf_score_hypotheses",
     "fccf_score_hypotheses_bench", "fccf_score_counts", "fccf_quick_verify", "fccf_debug_blob", "fccf_launch_count",
-    "fccf_stream_handle", "fccf_score_best", "fccf_register_batch_device",
+    "fccf_stream_handle", "fccf_score_best", "fccf_register_batch_device", "fccf_register_batch_multi", "fccf_score_sharded",
+    "fccf_device_count",
 ]
 
 
@@ -90,6 +91,9 @@ def lib():
         L.fccf_launch_count.restype = C.c_uint64
         L.fccf_stream_handle.argtypes = [vp]
         L.fccf_stream_handle.restype = vp
+        L.fccf_register_batch_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(fp), C.POINTER(C.c_size_t), C.POINTER(fp), C.POINTER(C.c_size_t), C.c_float, fp, C.POINTER(Timing)]
+        L.fccf_score_sharded.argtypes = [C.POINTER(vp), C.c_int, fp, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t, fp, fp, C.POINTER(C.c_int64), ip]
+        L.fccf_device_count.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -127,6 +131,40 @@ class HostBatch:
         self.ns = (C.c_size_t * n)(*[len(a) for a in self.srcs])
         self.nt = (C.c_size_t * n)(*[len(a) for a in self.tars])
         self.T = np.zeros((n, 16), np.float32)
+
+
+def device_count():
+    return int(lib().fccf_device_count())
+
+
+def register_batch_multi(ctxs, hb, leaf):
+    """fccf_register_batch_multi: a prepared host batch (HostBatch) over several contexts, one host thread per GPU."""
+    L = lib()
+    n = len(ctxs)
+    hs = (C.c_void_p * n)(*[c.h for c in ctxs])
+    tms = (Timing * n)()
+    rc = L.fccf_register_batch_multi(hs, n, hb.n, hb.sp, hb.ns, hb.tp, hb.nt, C.c_float(leaf), _f(hb.T), tms)
+    if rc not in (0, 3):
+        raise FccfError("libfccf error %d: %s" % (rc, L.fccf_last_error(ctxs[0].h).decode()))
+    return hb.T.reshape(hb.n, 4, 4), list(tms)
+
+
+def score_sharded(ctxs, Ts, s1, s2):
+    """fccf_score_sharded: (scores, best score, best global index, used_nccl)."""
+    L = lib()
+    n = len(ctxs)
+    hs = (C.c_void_p * n)(*[c.h for c in ctxs])
+    Ts = np.ascontiguousarray(Ts, np.float32).reshape(-1, 16)
+    s1 = np.ascontiguousarray(s1, np.float32)
+    s2 = np.ascontiguousarray(s2, np.float32)
+    sc = np.zeros(max(len(Ts), 1), np.float32)
+    best = C.c_float(0)
+    idx = C.c_int64(0)
+    used = C.c_int(0)
+    rc = L.fccf_score_sharded(hs, n, _f(Ts), len(Ts), _f(s1), len(s1), _f(s2), len(s2), _f(sc), C.byref(best), C.byref(idx), C.byref(used))
+    if rc not in (0, 3):
+        raise FccfError("libfccf error %d: %s" % (rc, L.fccf_last_error(ctxs[0].h).decode()))
+    return sc[:len(Ts)], float(best.value), int(idx.value), bool(used.value)
 
 
 class Context:

@@ -11,9 +11,17 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <climits>
+#include <memory>
+#include <thread>
 #include "fccf_internal.h"
+#include "hostcopy.h"
 
 using namespace fccf;
+
+namespace fccf {
+bool nccl_allreduce_max_i64(const std::vector<int>& devs, const std::vector<cudaStream_t>& streams, const std::vector<const long long*>& words_dev, long long* out);
+}
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -100,6 +108,8 @@ struct fccf_ctx {
   Arena sc_arena; ScoreWS sc_ws; int sc_cap_hash = 0; ScoreState* d_sc_ss = nullptr; int* d_sc_n = nullptr;
   size_t sc_n2 = 0, sc_nhyp = 0;
   long long* d_sc_best = nullptr;
+  std::unique_ptr<CopyPool> pool;   // pageable host inputs: pinned staging chunks filled by worker threads (hostcopy.h), created on first use
+  uint64_t staged_bytes = 0;
   Group& G0() { return *groups[0]; }
   Lane& L0() { return groups[0]->lanes[0]; }
 };
@@ -313,6 +323,10 @@ static thread_local std::string g_create_error;
 
 fccf_ctx* fccf_create(int device, const fccf_params* params) {
   g_create_error.clear();
+  // One hardware work queue per in-flight launch sequence: the driver default of 8 connections serialises the
+  // rotating groups of fccf_register_batch.  Read when the process creates its CUDA context, so it only takes
+  // effect if no CUDA call came first; an explicit setting of the caller is kept.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { g_create_error = "no usable CUDA device (libfccf has no CPU path)"; return nullptr; }
   if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return nullptr; }
@@ -339,6 +353,8 @@ fccf_ctx* fccf_create(int device, const fccf_params* params) {
 void fccf_destroy(fccf_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (Group* g : ctx->groups) if (g && g->stream) cudaStreamSynchronize(g->stream);
+  ctx->pool.reset();
   for (Group* g : ctx->groups) group_destroy(g);
   table_destroy(ctx->itab);
   if (ctx->sc_arena.base) cudaFree(ctx->sc_arena.base);
@@ -544,19 +560,38 @@ static int group_enqueue(fccf_ctx* ctx, Group* g, int G, int pair0, const float*
                          float leaf, bool host_in) {
   cudaStream_t s = g->stream;
   g->l0 = g->launches; g->had_h2d = host_in; g->G = G; g->last_h2d = 0;
+  bool staged = false;
+  static const bool stage_pageable = !(getenv("FCCF_NO_STAGING") && getenv("FCCF_NO_STAGING")[0] == '1');
   CK(cudaEventRecord(g->ev[0], s));
   for (int l = 0; l < G; l++) {
     Lane& L = g->lanes[l];
     L.pair = pair0 + l;
     if (host_in) {
-      if (n_tar[l]) CK(cudaMemcpyAsync(L.d_raw[0], tar[l], n_tar[l] * 12, cudaMemcpyHostToDevice, s));
-      if (n_src[l]) CK(cudaMemcpyAsync(L.d_raw[1], src[l], n_src[l] * 12, cudaMemcpyHostToDevice, s));
+      const float* hp[2] = {tar[l], src[l]}; const size_t hn[2] = {n_tar[l], n_src[l]};
+      for (int c = 0; c < 2; c++) {
+        if (!hn[c]) continue;
+        // pinned (or registered) memory: one DMA straight from the caller's buffer; pageable memory (the
+        // reference's std::vector / pcl storage): through the context's pinned staging chunks
+        if (!stage_pageable || host_pointer_is_pinned(hp[c])) CK(cudaMemcpyAsync(L.d_raw[c], hp[c], hn[c] * 12, cudaMemcpyHostToDevice, s));
+        else {
+          if (!ctx->pool) {
+            int nw = 0;
+            if (const char* e = getenv("FCCF_COPY_THREADS")) nw = atoi(e);
+            if (nw <= 0) { int hw = (int)std::thread::hardware_concurrency(), nd = 1; cudaGetDeviceCount(&nd); nw = std::max(2, std::min(8, hw / std::max(1, nd))); }
+            ctx->pool.reset(new CopyPool(ctx->device, nw, (size_t)8 << 20));   // 8 MiB chunks: per-chunk driver overhead dominates below ~4 MiB (17 GB/s at 2 MiB, 31 GB/s at 8 MiB)
+            if (!ctx->pool->ok()) { ctx->pool.reset(); ctx->err = "pinned staging allocation failed"; cudaGetLastError(); return FCCF_ERR_CUDA; }
+          }
+          ctx->pool->add(L.d_raw[c], hp[c], hn[c] * 12);
+          staged = true; ctx->staged_bytes += hn[c] * 12;
+        }
+      }
       g->last_h2d += (n_tar[l] + n_src[l]) * 12;
     }
     CallArgs& c = g->h_calls[l];
     c.n0 = (int)n_tar[l]; c.n1 = (int)n_src[l]; c.leaf = leaf; c.pad = 0;
     c.raw[0] = host_in ? L.d_raw[0] : tar[l]; c.raw[1] = host_in ? L.d_raw[1] : src[l];
   }
+  if (staged) CK(ctx->pool->flush_into(s));      // every staged chunk issued; the group's stream waits for the workers' DMAs
   CK(cudaMemcpyAsync(g->d_calls, g->h_calls, sizeof(CallArgs) * (size_t)G, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(g->ev[1], s));
   // cluster VoxelGrid first, unless a cloud cannot fit its scratch or this leaf missed recently
@@ -1096,6 +1131,97 @@ int fccf_debug_blob(fccf_ctx* ctx, const char* name_c, void* dst, size_t cap_byt
   if (dtype) *dtype = dt;
   if (dst) { if (out.size() > cap_bytes) { ctx->err = "blob buffer too small"; return FCCF_ERR_ARG; } if (!out.empty()) memcpy(dst, out.data(), out.size()); }
   CK(cudaGetLastError());
+  return FCCF_OK;
+}
+
+int fccf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// contiguous [lo, hi) of n ordered items for part i of k (the first n % k parts get one more)
+static void part_range(size_t n, int i, int k, size_t* lo, size_t* hi) {
+  size_t q = n / (size_t)k, r = n % (size_t)k;
+  *lo = (size_t)i * q + std::min<size_t>((size_t)i, r);
+  *hi = *lo + q + ((size_t)i < r ? 1 : 0);
+}
+
+int fccf_register_batch_multi(fccf_ctx* const* ctxs, int n_ctx, int n_pairs, const float* const* src_xyz, const size_t* n_src,
+                              const float* const* tar_xyz, const size_t* n_tar, float leaf, float* T_out, fccf_timing* timing) {
+  if (!ctxs || n_ctx < 1) return FCCF_ERR_ARG;
+  for (int i = 0; i < n_ctx; i++) if (!ctxs[i]) return FCCF_ERR_NO_DEVICE;
+  if (n_ctx == 1) return register_many(ctxs[0], n_pairs, src_xyz, n_src, tar_xyz, n_tar, leaf, T_out, timing, true);
+  if (n_pairs < 0 || (n_pairs && (!src_xyz || !tar_xyz || !n_src || !n_tar || !T_out))) { ctxs[0]->err = "bad argument"; return FCCF_ERR_ARG; }
+  std::vector<int> rc(n_ctx, FCCF_OK);
+  std::vector<std::thread> th;
+  for (int i = 0; i < n_ctx; i++) {
+    th.emplace_back([&, i]() {
+      size_t lo, hi; part_range((size_t)n_pairs, i, n_ctx, &lo, &hi);
+      fccf_timing tm; memset(&tm, 0, sizeof tm);
+      rc[i] = register_many(ctxs[i], (int)(hi - lo), src_xyz + lo, n_src + lo, tar_xyz + lo, n_tar + lo, leaf, T_out + 16 * lo, &tm, true);
+      if (timing) timing[i] = tm;
+    });
+  }
+  for (std::thread& t : th) t.join();
+  int worst = FCCF_OK;
+  for (int i = 0; i < n_ctx; i++) if (rc[i] != FCCF_OK && (worst == FCCF_OK || rc[i] != FCCF_ERR_CAPACITY)) worst = rc[i];
+  return worst;
+}
+
+int fccf_score_sharded(fccf_ctx* const* ctxs, int n_ctx, const float* T, size_t n_hyp, const float* s1_xyz, size_t n1, const float* s2_xyz, size_t n2,
+                       float* scores, float* best_score, int64_t* best_index, int* used_nccl) {
+  if (!ctxs || n_ctx < 1) return FCCF_ERR_ARG;
+  for (int i = 0; i < n_ctx; i++) if (!ctxs[i]) return FCCF_ERR_NO_DEVICE;
+  if (!T && n_hyp) { ctxs[0]->err = "bad argument"; return FCCF_ERR_ARG; }
+  std::vector<float> tmp;
+  if (!scores) { tmp.resize(std::max<size_t>(n_hyp, 1)); scores = tmp.data(); }
+  std::vector<int> rc(n_ctx, FCCF_OK);
+  auto work = [&](int i) {
+    fccf_ctx* ctx = ctxs[i];
+    size_t lo, hi; part_range(n_hyp, i, n_ctx, &lo, &hi);
+    rc[i] = fccf_score_hypotheses(ctx, T + 16 * lo, hi - lo, s1_xyz, n1, s2_xyz, n2, scores + lo);
+    if (rc[i] != FCCF_OK && rc[i] != FCCF_ERR_CAPACITY) return;
+    cudaSetDevice(ctx->device);
+    if (!ctx->d_sc_best && cudaMalloc(&ctx->d_sc_best, 8) != cudaSuccess) { cudaGetLastError(); rc[i] = FCCF_ERR_CUDA; return; }
+    // block-reduced argmax of this shard: packed (score, global index) word, left on the device for the all-reduce
+    launch_score_best(ctx->stream, ctx->d_sc_scores, (int)(hi - lo), (long long)lo, ctx->d_sc_best, &ctx->launches);
+  };
+  if (n_ctx == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_ctx; i++) th.emplace_back(work, i);
+    for (std::thread& t : th) t.join();
+  }
+  for (int i = 0; i < n_ctx; i++) if (rc[i] != FCCF_OK && rc[i] != FCCF_ERR_CAPACITY) { if (i) ctxs[0]->err = ctxs[i]->err; return rc[i]; }
+  std::vector<long long> words(n_ctx, LLONG_MIN);
+  bool nccl = false;
+  if (n_ctx > 1) {
+    std::vector<int> devs; std::vector<cudaStream_t> streams; std::vector<const long long*> wd;
+    bool distinct = true;
+    for (int i = 0; i < n_ctx; i++) { for (int d : devs) distinct = distinct && d != ctxs[i]->device; devs.push_back(ctxs[i]->device); streams.push_back(ctxs[i]->stream); wd.push_back(ctxs[i]->d_sc_best); }
+    if (distinct) nccl = nccl_allreduce_max_i64(devs, streams, wd, words.data());     // one 8-byte all-reduce(max) over NVLink
+  }
+  if (!nccl) {
+    for (int i = 0; i < n_ctx; i++) {
+      fccf_ctx* ctx = ctxs[i];
+      CK(cudaSetDevice(ctx->device));
+      CK(cudaMemcpyAsync(&words[i], ctx->d_sc_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    long long m = *std::max_element(words.begin(), words.end());
+    for (long long& w : words) w = m;
+  }
+  const long long best = words[0];
+  if (used_nccl) *used_nccl = nccl ? 1 : 0;
+  const int key = (int)(best >> 32);
+  if (best_index) *best_index = n_hyp ? (int64_t)(0xffffffffll - (best & 0xffffffffll)) : -1;
+  if (best_score) {
+    float sc;
+    if (key == INT_MIN || !n_hyp) sc = std::nanf("");
+    else { int b = key >= 0 ? key : (key ^ 0x7fffffff); memcpy(&sc, &b, 4); }
+    *best_score = sc;
+  }
   return FCCF_OK;
 }
 

@@ -157,50 +157,127 @@ static void print_eigen_matrix4f(std::ostream& s, const float T[16]) {
   }
 }
 
+// name=value overrides after the positional arguments: every tunable of the reference
+// (FCCF.cpp:126-176) by its own name, plus the library's switches.  Unknown names are an error.
+struct ParamName { const char* name; float fccf_params::*field; };
+static const ParamName kParamNames[] = {
+  {"parameter_l1", &fccf_params::parameter_l1}, {"parameter_l2", &fccf_params::parameter_l2}, {"parameter_k1", &fccf_params::parameter_k1},
+  {"parameter_k2", &fccf_params::parameter_k2}, {"normal_vector_threshold1", &fccf_params::normal_vector_threshold1},
+  {"normal_vector_threshold2", &fccf_params::normal_vector_threshold2}, {"face_voxel_size", &fccf_params::face_voxel_size},
+  {"voxel_point_threshold", &fccf_params::voxel_point_threshold}, {"curvature_threshold", &fccf_params::curvature_threshold},
+  {"select_plane_number", &fccf_params::select_plane_number}, {"quick_verify_angel_threshold", &fccf_params::quick_verify_angel_threshold},
+  {"quick_verify_distance_threshold", &fccf_params::quick_verify_distance_threshold}, {"required_optimize_plane", &fccf_params::required_optimize_plane},
+  {"fine_verify_voxel_size", &fccf_params::fine_verify_voxel_size}, {"fine_verify_number", &fccf_params::fine_verify_number},
+  {"included_angle_same_threshold", &fccf_params::included_angle_same_threshold}, {"included_angle_min_threshold", &fccf_params::included_angle_min_threshold},
+  {"included_angle_max_threshold", &fccf_params::included_angle_max_threshold}, {"third_plane_threshold", &fccf_params::third_plane_threshold},
+  {"third_plane_normal_threshold", &fccf_params::third_plane_normal_threshold}, {"cluster_number_threshold", &fccf_params::cluster_number_threshold},
+  {"cluster_angel_threshold", &fccf_params::cluster_angel_threshold}, {"cluster_distance_threshold", &fccf_params::cluster_distance_threshold},
+  {"seclct_cluster_number", &fccf_params::seclct_cluster_number}, {"rough_threshold_gl", &fccf_params::rough_threshold_gl},
+};
+struct Options { fccf_params prm; int gpus = 1; int device = 0; bool warm = false; };
+static bool parse_options(int argc, char** argv, int first, Options& o) {
+  for (int a = first; a < argc; a++) {
+    std::string kv = argv[a]; size_t eq = kv.find('=');
+    if (eq == std::string::npos) { std::cerr << "FCCF: expected name=value, got '" << kv << "'" << std::endl; return false; }
+    std::string k = kv.substr(0, eq); float v = (float)std::atof(kv.c_str() + eq + 1);
+    bool known = false;
+    for (const ParamName& pn : kParamNames) if (k == pn.name) { o.prm.*(pn.field) = v; known = true; }
+    if (k == "emulate_pcl_overflow") { o.prm.emulate_pcl_overflow = (int)v; known = true; }
+    else if (k == "exhaustive") { if (v != 0.f) o.prm.fine_verify_number = 256; known = true; }   // fine-verify every cluster centre
+    else if (k == "gpus") { o.gpus = (int)v; known = true; }
+    else if (k == "device") { o.device = (int)v; known = true; }
+    else if (k == "warm") { o.warm = v != 0.f; known = true; }
+    else if (k == "batch_lanes") { o.prm.batch_lanes = (int)v; known = true; }
+    if (!known) { std::cerr << "FCCF: unknown parameter '" << k << "' (the reference's tunables FCCF.cpp:126-176 by name, emulate_pcl_overflow, exhaustive, gpus, device, warm, batch_lanes)" << std::endl; return false; }
+  }
+  return true;
+}
+
+static void print_result(const float T[16]) {
+  std::cout << "Transformation: \n";
+  print_eigen_matrix4f(std::cout, T);
+  std::cout << std::endl;
+}
+
+// FCCF --batch LIST.txt {voxel} [name=value ...]: every line of LIST names one pair "SRC.ply TAR.ply"; the pairs are
+// registered as ONE batch (fccf_register_batch_multi: gpus=N contexts, one host thread per GPU; BASELINE config 4)
+// and printed in order, each in the reference's format.
+static int run_batch(int argc, char** argv) {
+  if (argc < 4) { std::cerr << "usage: FCCF --batch LIST.txt {voxel} [name=value ...]" << std::endl; return 2; }
+  float LeafSize = (float)std::atof(argv[3]);
+  Options o; fccf_default_params(&o.prm);
+  if (!parse_options(argc, argv, 4, o)) return 2;
+  std::ifstream in(argv[2]);
+  if (!in) { fprintf(stderr, "Couldn't read file \n"); return 0; }
+  std::vector<std::string> names; std::string a, b;
+  while (in >> a >> b) { names.push_back(a); names.push_back(b); }
+  const int np = (int)names.size() / 2;
+  std::vector<Cloud> clouds(names.size());
+  auto tl0 = std::chrono::steady_clock::now();
+  for (size_t i = 0; i < names.size(); i++) if (!load_ply_xyz(names[i], clouds[i])) { fprintf(stderr, "Couldn't read file \n"); return 0; }
+  double load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl0).count();
+  std::cout << "Leaf size : " << LeafSize << std::endl;
+  int ndev = fccf_device_count();
+  int ng = o.gpus < 1 ? 1 : o.gpus; if (ng > ndev) ng = ndev; if (ng > np && np > 0) ng = np;
+  if (ng < 1) { std::cerr << "FCCF: no usable CUDA device (this build has no CPU path)" << std::endl; return 3; }
+  std::vector<fccf_ctx*> ctxs;
+  for (int g = 0; g < ng; g++) { fccf_ctx* c = fccf_create(o.device + g, &o.prm); if (!c) { std::cerr << "FCCF: " << fccf_last_error(nullptr) << std::endl; for (fccf_ctx* x : ctxs) fccf_destroy(x); return 3; } ctxs.push_back(c); }
+  std::vector<const float*> sp(np), tp(np); std::vector<size_t> ns(np), nt(np);
+  for (int i = 0; i < np; i++) { sp[i] = clouds[2 * i].xyz; ns[i] = clouds[2 * i].n; tp[i] = clouds[2 * i + 1].xyz; nt[i] = clouds[2 * i + 1].n; }
+  std::vector<float> T((size_t)16 * (np ? np : 1));
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = fccf_register_batch_multi(ctxs.data(), ng, np, sp.data(), ns.data(), tp.data(), nt.data(), LeafSize, T.data(), nullptr);
+  double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (rc != FCCF_OK && rc != FCCF_ERR_CAPACITY) { std::cerr << "FCCF: " << fccf_last_error(ctxs[0]) << std::endl; for (fccf_ctx* x : ctxs) fccf_destroy(x); return 4; }
+  for (int i = 0; i < np; i++) print_result(&T[16 * (size_t)i]);
+  std::cout << "Time batch: " << np << " registrations on " << ng << " GPU(s) in " << ms << " ms (" << (np ? ms / np : 0.0) << " ms/registration, host clouds in -> matrices out, first call: includes allocation and graph capture)" << std::endl;
+  std::cout << "Time PLY load: " << load_ms << " ms" << std::endl;
+  for (fccf_ctx* x : ctxs) fccf_destroy(x);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && std::string(argv[1]) == "--batch") return run_batch(argc, argv);
   if (argc < 4) {   // the reference dereferences argv unchecked (FCCF.cpp:1648-1650); a usage line is strictly safer
-    std::cerr << "usage: " << (argc ? argv[0] : "FCCF") << " {SRC.ply} {TAR.ply} {voxel}" << std::endl;
+    std::cerr << "usage: " << (argc ? argv[0] : "FCCF") << " {SRC.ply} {TAR.ply} {voxel} [name=value ...]   |   FCCF --batch LIST.txt {voxel} [gpus=N name=value ...]" << std::endl;
     return 2;
   }
   std::string fnameS = argv[1], fnameT = argv[2];
   float LeafSize = (float)std::atof(argv[3]);
+  Options o; fccf_default_params(&o.prm);
+  if (!parse_options(argc, argv, 4, o)) return 2;
   Cloud source, target;
   auto tl0 = std::chrono::steady_clock::now();
   if (!load_ply_xyz(fnameS, source)) { fprintf(stderr, "Couldn't read file \n"); return 0; }
   if (!load_ply_xyz(fnameT, target)) { fprintf(stderr, "Couldn't read file \n"); return 0; }
   double load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl0).count();
   std::cout << "Leaf size : " << LeafSize << std::endl;
-  fccf_params prm; fccf_default_params(&prm);
-  // optional overrides after the three positional arguments: name=value
-  for (int a = 4; a < argc; a++) {
-    std::string kv = argv[a]; size_t eq = kv.find('=');
-    if (eq == std::string::npos) continue;
-    std::string k = kv.substr(0, eq); float v = (float)std::atof(kv.c_str() + eq + 1);
-    if (k == "face_voxel_size") prm.face_voxel_size = v;
-    else if (k == "fine_verify_voxel_size") prm.fine_verify_voxel_size = v;
-    else if (k == "select_plane_number") prm.select_plane_number = v;
-    else if (k == "fine_verify_number") prm.fine_verify_number = v;
-    else if (k == "seclct_cluster_number") prm.seclct_cluster_number = v;
-    else if (k == "emulate_pcl_overflow") prm.emulate_pcl_overflow = (int)v;
-    else if (k == "exhaustive" && v != 0.f) prm.fine_verify_number = 256;   // fine-verify every cluster centre
-  }
-  int dev = 0;
+  int dev = o.device;
   if (const char* e = std::getenv("FCCF_DEVICE")) dev = std::atoi(e);
-  fccf_ctx* ctx = fccf_create(dev, &prm);
-  if (!ctx) { std::cerr << "FCCF: no usable CUDA device (this build has no CPU path)" << std::endl; return 3; }
+  fccf_ctx* ctx = fccf_create(dev, &o.prm);
+  if (!ctx) { std::cerr << "FCCF: " << fccf_last_error(nullptr) << std::endl; return 3; }
   float T[16]; fccf_timing tm;
+  auto tr0 = std::chrono::steady_clock::now();
   int rc = fccf_register(ctx, source.xyz, source.n, target.xyz, target.n, LeafSize, T, &tm);
+  double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count();
   if (rc != FCCF_OK && rc != FCCF_ERR_CAPACITY) { std::cerr << "FCCF: " << fccf_last_error(ctx) << std::endl; fccf_destroy(ctx); return 4; }
   if (rc == FCCF_ERR_CAPACITY) std::cerr << "FCCF: warning: " << fccf_last_error(ctx) << std::endl;
-  std::cout << "Transformation: \n";
-  print_eigen_matrix4f(std::cout, T);
-  std::cout << std::endl;
-  // a second, warm run gives the steady-state timing (the first includes allocation and module load)
-  fccf_timing tw; float T2[16];
-  if (std::getenv("FCCF_NO_WARM_TIMING") == nullptr && fccf_register(ctx, source.xyz, source.n, target.xyz, target.n, LeafSize, T2, &tw) == FCCF_OK) tm = tw;
+  print_result(T);
+  // Timing of THE run that produced the matrix (device events; "wall" = host clock around the call, which on a first
+  // call also pays workspace allocation, module load and graph capture).  warm=1 repeats the registration once and
+  // prints the steady-state figures as well.
   std::cout << "Time pipeline (computer_transform_guess, the reference's clock() region): " << tm.pipeline_ms << " ms" << std::endl;
   std::cout << "Time end-to-end (H2D " << tm.h2d_ms << " + downsample " << tm.downsample_ms << " + pipeline + D2H " << tm.d2h_ms << "): " << tm.total_ms << " ms, "
-            << tm.n_launches << " kernel launches" << std::endl;
+            << tm.n_launches << " kernel launches; wall " << wall_ms << " ms" << std::endl;
+  if (o.warm) {
+    fccf_timing tw; float T2[16];
+    auto tw0 = std::chrono::steady_clock::now();
+    if (fccf_register(ctx, source.xyz, source.n, target.xyz, target.n, LeafSize, T2, &tw) == FCCF_OK) {
+      double w2 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
+      std::cout << "Time warm repeat: pipeline " << tw.pipeline_ms << " ms, end-to-end (H2D " << tw.h2d_ms << " + downsample " << tw.downsample_ms << " + pipeline + D2H " << tw.d2h_ms
+                << ") " << tw.total_ms << " ms; wall " << w2 << " ms" << std::endl;
+    }
+  }
   std::cout << "Time PLY load: " << load_ms << " ms (" << (source.in_place && target.in_place ? "memory-mapped, used in place" : "parsed") << ")" << std::endl;
   // machine-readable record (the reference's dead writefile / dropped costTime, FCCF.cpp:1610-1644, 1685)
   if (const char* lp = std::getenv("FCCF_LOG")) {

@@ -118,6 +118,29 @@ def gather_transforms(T_local, n_pairs, device=None):
     return allT.reshape(-1, 4, 4)
 
 
+def gather_blocks(T_local, n_total, device=None):
+    """Results of a batch cut into CONTIGUOUS blocks (shard_range): rank r holds the 4x4 of pairs [lo_r, hi_r); every
+    rank gets all of them in order."""
+    import torch
+
+    dist = _dist()
+    T_local = np.ascontiguousarray(T_local, np.float32).reshape(-1, 16)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return T_local.reshape(-1, 4, 4)
+    world = dist.get_world_size()
+    per = (int(n_total) + world - 1) // world
+    buf = np.zeros((per, 16), np.float32)
+    buf[:len(T_local)] = T_local
+    t = torch.from_numpy(buf).to(device if device is not None else "cpu")
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    allT = np.zeros((int(n_total), 16), np.float32)
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        allT[lo:hi] = out[r].cpu().numpy()[:hi - lo]
+    return allT.reshape(-1, 4, 4)
+
+
 def register_pairs_sharded(ctx, srcs, tars, leaf, device=None):
     """BASELINE config 4: a batch of independent pairs over the ranks of the job.  `srcs`/`tars` list ALL
     pairs on every rank (or None for pairs this rank does not own)."""

@@ -96,6 +96,17 @@ int fccf_register_batch(fccf_ctx* ctx, int n_pairs, const float* const* src_xyz,
 int fccf_register_batch_device(fccf_ctx* ctx, int n_pairs, const float* const* d_src_xyz, const size_t* n_src,
                                const float* const* d_tar_xyz, const size_t* n_tar, float leaf, float* T_out, fccf_timing* timing);
 
+/* Batch of independent pairs over SEVERAL contexts, one per GPU (BASELINE config 4 inside the library): the pairs
+ * are cut into n_ctx contiguous blocks, block i is registered by ctxs[i] on its own host thread; no data-path
+ * collective (the unit of work is one independent main() run, FCCF.cpp:1646-1690).  Host pointers may be pinned
+ * or pageable (std::vector / pcl storage): pageable clouds go through the context's pinned staging chunks.
+ * timing: NULL or an array of n_ctx records (one per context, as fccf_register_batch fills it). */
+int fccf_register_batch_multi(fccf_ctx* const* ctxs, int n_ctx, int n_pairs, const float* const* src_xyz, const size_t* n_src,
+                              const float* const* tar_xyz, const size_t* n_tar, float leaf, float* T_out, fccf_timing* timing);
+
+/* Number of CUDA devices this process can use (0: none). */
+int fccf_device_count(void);
+
 /* replaces: pcl::VoxelGrid<PointXYZ>::filter as called at FCCF.cpp:1668-1678 / 1377-1387.
  * out_xyz: capacity n points; out_cell (int64 linear cell index) / out_cnt may be NULL. */
 int fccf_voxelgrid(fccf_ctx* ctx, const float* xyz, size_t n, float leaf, float* out_xyz, int64_t* out_cell,
@@ -121,6 +132,15 @@ int fccf_score_hypotheses_bench(fccf_ctx* ctx, const float* T, size_t n_hyp, con
  * its signed maximum over several GPUs (one 8-byte all-reduce) is the global best, smallest index
  * among ties.  packed_host and/or packed_device (a device pointer, e.g. an NCCL buffer) receive it. */
 int fccf_score_best(fccf_ctx* ctx, size_t index_base, int64_t* packed_host, int64_t* packed_device);
+
+/* Hypothesis scoring sharded over several contexts / GPUs (BASELINE config 3; fine_verify FCCF.cpp:785-839 and the
+ * first-maximum scan 1559): the ordered list T is cut into n_ctx contiguous ranges, every context builds the same
+ * static voxel table (s1) and holds the same moving cloud (s2), scores its range, reduces it to one packed
+ * (score, global index) word on the device, and ONE 8-byte ncclAllReduce(max, int64) over NVLink gives every GPU the
+ * global best (smallest index among ties).  libnccl.so.2 is loaded at run time; when it is missing (or two contexts
+ * share a device) the n_ctx words are compared on the host and *used_nccl is 0.  scores: NULL or n_hyp floats. */
+int fccf_score_sharded(fccf_ctx* const* ctxs, int n_ctx, const float* T, size_t n_hyp, const float* s1_xyz, size_t n1,
+                       const float* s2_xyz, size_t n2, float* scores, float* best_score, int64_t* best_index, int* used_nccl);
 
 /* Per-voxel overlap counts of hypothesis `hyp` of the last fccf_score_hypotheses call: rows of
  * (Lx, Ly, Lz, s, t) for voxels holding both static and moving points; returns rows in *n_rows. */
