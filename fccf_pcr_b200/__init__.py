@@ -44,7 +44,7 @@ EXPORTS = [
     "fccf_register_device", "fccf_register_batch", "fccf_voxelgrid", "fccf_extract_planes", "fccf_score_hypotheses",
     "fccf_score_hypotheses_bench", "fccf_score_counts", "fccf_quick_verify", "fccf_debug_blob", "fccf_launch_count",
     "fccf_stream_handle", "fccf_score_best", "fccf_register_batch_device", "fccf_register_batch_multi", "fccf_score_sharded",
-    "fccf_device_count",
+    "fccf_device_count", "fccf_base_pairs", "fccf_hypotheses", "fccf_cluster", "fccf_fuse",
 ]
 
 
@@ -94,6 +94,11 @@ def lib():
         L.fccf_register_batch_multi.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(fp), C.POINTER(C.c_size_t), C.POINTER(fp), C.POINTER(C.c_size_t), C.c_float, fp, C.POINTER(Timing)]
         L.fccf_score_sharded.argtypes = [C.POINTER(vp), C.c_int, fp, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t, fp, fp, C.POINTER(C.c_int64), ip]
         L.fccf_device_count.restype = C.c_int
+        dp = C.POINTER(C.c_double)
+        L.fccf_base_pairs.argtypes = [vp, fp, dp, C.c_int, ip, fp, ip]
+        L.fccf_hypotheses.argtypes = [vp, fp, dp, C.c_int, fp, dp, C.c_int, ip]
+        L.fccf_cluster.argtypes = [vp, fp, ip, ip]
+        L.fccf_fuse.argtypes = [vp, fp, fp, fp, ip, C.c_int, fp]
         _LIB = L
     return _LIB
 
@@ -306,6 +311,46 @@ class Context:
         iters = np.zeros(n, np.int32)
         self._check(self.L.fccf_quick_verify(self.h, _f(Ts), n, _f(p1), len(p1), _f(p2), len(p2), _f(sc), _i(npair), _i(pairs), _i(iters)))
         return sc, Ts.reshape(-1, 4, 4), npair, pairs, iters
+
+    def base_pairs(self, planes, theta):
+        """select_base on one plane table: (pairs [B,3] = i, j, type; angles [B])."""
+        p = np.ascontiguousarray(planes, np.float32).reshape(-1, 7)
+        th = np.ascontiguousarray(theta, np.float64)
+        pairs = np.zeros((120, 3), np.int32)
+        ang = np.zeros(120, np.float32)
+        n = C.c_int(0)
+        self._check(self.L.fccf_base_pairs(self.h, _f(p), th.ctypes.data_as(C.POINTER(C.c_double)), len(p), _i(pairs), _f(ang), C.byref(n)))
+        return pairs[:n.value].copy(), ang[:n.value].copy()
+
+    def hypotheses(self, planes1, theta1, planes2, theta2):
+        """select_base x 2 + match loop + computer_transform: n_hyp[3]; pools via blob('hyp0') ..."""
+        p1 = np.ascontiguousarray(planes1, np.float32).reshape(-1, 7)
+        p2 = np.ascontiguousarray(planes2, np.float32).reshape(-1, 7)
+        t1 = np.ascontiguousarray(theta1, np.float64)
+        t2 = np.ascontiguousarray(theta2, np.float64)
+        nh = np.zeros(3, np.int32)
+        dp = C.POINTER(C.c_double)
+        self._check(self.L.fccf_hypotheses(self.h, _f(p1), t1.ctypes.data_as(dp), len(p1), _f(p2), t2.ctypes.data_as(dp), len(p2), _i(nh)), soft=True)
+        return nh
+
+    def cluster(self, qt7, n_hyp):
+        """cluster_num + transform_cluster of three concatenated pools of (qw qx qy qz tx ty tz) rows: n_centres[3]."""
+        q = np.ascontiguousarray(qt7, np.float32).reshape(-1, 7)
+        nh = np.ascontiguousarray(n_hyp, np.int32)
+        nc = np.zeros(3, np.int32)
+        self._check(self.L.fccf_cluster(self.h, _f(q), _i(nh), _i(nc)), soft=True)
+        return nc
+
+    def fuse(self, top_T, s1, s2, n_top):
+        """per-type best + 0.8 gate + fuse_answer: top_T [3,k,4,4], s1 / s2 [3,k], n_top[3] -> 4x4."""
+        T = np.ascontiguousarray(top_T, np.float32)
+        k = T.shape[1]
+        a = np.ascontiguousarray(s1, np.float32).reshape(3, k)
+        b = np.ascontiguousarray(s2, np.float32).reshape(3, k)
+        nt = np.ascontiguousarray(n_top, np.int32)
+        out = np.zeros(16, np.float32)
+        self._check(self.L.fccf_fuse(self.h, _f(T), _f(a), _f(b), _i(nt), k, _f(out)))
+        return out.reshape(4, 4)
 
     def blob(self, name):
         nb = C.c_size_t(0)

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include <climits>
+#include <cstddef>
 #include <memory>
 #include <thread>
 #include "fccf_internal.h"
@@ -1223,6 +1224,112 @@ int fccf_score_sharded(fccf_ctx* const* ctxs, int n_ctx, const float* T, size_t 
     *best_score = sc;
   }
   return FCCF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone entry points of the small stages: inputs go straight into lane 0's state block, the
+// stage's own kernels run, results are read through fccf_debug_blob
+// ---------------------------------------------------------------------------------------------
+static int stage_begin(fccf_ctx* ctx) {
+  CK(cudaSetDevice(ctx->device));
+  drain_groups(ctx);
+  int rc = ensure_capacity(ctx, ctx->groups[0], 0, 1024, 1024);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  CK(cudaStreamSynchronize(s));
+  if ((rc = set_single_call(ctx, 0, 0, 1.0f))) return rc;
+  return FCCF_OK;
+}
+static int stage_end(fccf_ctx* ctx) {
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->L0().h_st, ctx->L0().d_st, sizeof(PipeState), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  ctx->have_run = true;
+  return check_status(ctx, ctx->L0().h_st->status);
+}
+static void fill_face_table(FaceTable& ft, const float* planes, const double* theta, int f) {
+  memset(&ft, 0, sizeof ft);
+  ft.F = f;
+  for (int i = 0; i < f; i++) {
+    for (int k = 0; k < 7; k++) ft.plane[i][k] = planes[7 * i + k];
+    ft.plane[i][7] = 1.f; ft.theta[i] = theta ? theta[i] : 0.0; ft.id[i] = i;
+  }
+}
+
+int fccf_hypotheses(fccf_ctx* ctx, const float* planes1, const double* theta1, int f1, const float* planes2, const double* theta2, int f2, int32_t n_hyp[3]) {
+  if (!ctx) return FCCF_ERR_NO_DEVICE;
+  if (f1 < 0 || f2 < 0 || f1 > FCCF_MAXF || f2 > FCCF_MAXF || (f1 && !planes1) || (f2 && !planes2)) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
+  int rc = stage_begin(ctx);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  std::vector<Work> ws; Batch w = single_batch(ctx, ws);
+  launch_init_state(s, w, ctx->G0().d_calls, &ctx->launches);
+  FaceTable ft[2];
+  fill_face_table(ft[0], planes1, theta1, f1); fill_face_table(ft[1], planes2, theta2, f2);
+  CK(cudaMemcpyAsync(&ctx->L0().d_st->ft[0], ft, sizeof ft, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));        // ft lives on this stack frame
+  launch_hypotheses(s, w, &ctx->launches);
+  rc = stage_end(ctx);
+  if (n_hyp) for (int i = 0; i < 3; i++) n_hyp[i] = ctx->L0().h_st->n_hyp[i];
+  return rc;
+}
+
+int fccf_base_pairs(fccf_ctx* ctx, const float* planes, const double* theta, int f, int32_t* pairs, float* angles, int32_t* n_pairs) {
+  if (!ctx) return FCCF_ERR_NO_DEVICE;
+  if (!n_pairs) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
+  int rc = fccf_hypotheses(ctx, planes, theta, f, nullptr, nullptr, 0, nullptr);      // an empty second table: no match, no hypothesis
+  if (rc) return rc;
+  const BaseTable& b = ctx->L0().h_st->base[0];
+  *n_pairs = b.B;
+  for (int i = 0; i < b.B; i++) {
+    if (pairs) { pairs[3 * i] = b.i[i]; pairs[3 * i + 1] = b.j[i]; pairs[3 * i + 2] = b.type[i]; }
+    if (angles) angles[i] = b.angle[i];
+  }
+  return FCCF_OK;
+}
+
+int fccf_cluster(fccf_ctx* ctx, const float* qt7, const int32_t n_hyp[3], int32_t n_centres[3]) {
+  if (!ctx) return FCCF_ERR_NO_DEVICE;
+  if (!n_hyp || n_hyp[0] < 0 || n_hyp[1] < 0 || n_hyp[2] < 0) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
+  const long long tot = (long long)n_hyp[0] + n_hyp[1] + n_hyp[2];
+  if (tot > ctx->cap_hyp || (tot && !qt7)) { ctx->err = "bad argument / more hypotheses than the arena holds"; return FCCF_ERR_ARG; }
+  int rc = stage_begin(ctx);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  std::vector<Work> ws; Batch w = single_batch(ctx, ws);
+  launch_init_state(s, w, ctx->G0().d_calls, &ctx->launches);
+  std::vector<float> q8((size_t)8 * (size_t)std::max<long long>(tot, 1), 0.f);
+  for (long long i = 0; i < tot; i++) for (int k = 0; k < 7; k++) q8[8 * i + k] = qt7[7 * i + k];
+  int hdr[7] = {n_hyp[0], n_hyp[1], n_hyp[2], 0, n_hyp[0], n_hyp[0] + n_hyp[1], (int)tot};      // n_hyp[3], hyp_off[4]
+  static_assert(offsetof(PipeState, hyp_off) == offsetof(PipeState, n_hyp) + 12, "n_hyp and hyp_off are adjacent");
+  if (tot) CK(cudaMemcpyAsync(ctx->L0().h.hyp_qt, q8.data(), (size_t)tot * 32, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(&ctx->L0().d_st->n_hyp[0], hdr, sizeof hdr, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  launch_cluster(s, w, &ctx->launches);
+  rc = stage_end(ctx);
+  if (n_centres) for (int i = 0; i < 3; i++) n_centres[i] = ctx->L0().h_st->n_centre[i];
+  return rc;
+}
+
+int fccf_fuse(fccf_ctx* ctx, const float* top_T, const float* s1, const float* s2, const int32_t n_top[3], int k, float T_out[16]) {
+  if (!ctx) return FCCF_ERR_NO_DEVICE;
+  if (!top_T || !s1 || !s2 || !n_top || !T_out || k < 1 || k > FCCF_TOPK || n_top[0] < 0 || n_top[1] < 0 || n_top[2] < 0 || n_top[0] > k || n_top[1] > k || n_top[2] > k) { ctx->err = "bad argument"; return FCCF_ERR_ARG; }
+  int rc = stage_begin(ctx);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  std::vector<Work> ws; Batch w = single_batch(ctx, ws);
+  launch_init_state(s, w, ctx->G0().d_calls, &ctx->launches);
+  HypWS& h = ctx->L0().h;
+  CK(cudaMemcpyAsync(h.top_T, top_T, (size_t)3 * k * 64, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h.top_s1, s1, (size_t)3 * k * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(h.top_s2, s2, (size_t)3 * k * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(&ctx->L0().d_st->n_top[0], n_top, 12, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  launch_fuse(s, ctx->L0().d_st, h.top_T, h.top_s1, h.top_s2, ctx->p.fine_verify_number, k, ctx->itab, &ctx->launches);
+  rc = stage_end(ctx);
+  for (int i = 0; i < 16; i++) T_out[i] = ctx->L0().h_st->T_final[i];
+  return rc;
 }
 
 }  // extern "C"

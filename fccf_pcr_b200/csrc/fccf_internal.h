@@ -252,6 +252,7 @@ void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJo
 void launch_score_list(cudaStream_t s, const fccf_params& p, const float* d_T16, int n_hyp, const float* d_s2, const ScoreWS& ws, float* d_scores, ArgTable& tab, uint64_t* launches);
 // packed (score, index) maximum of a device score list -> *d_out (8 bytes)
 void launch_score_best(cudaStream_t s, const float* d_scores, int n, long long index_base, long long* d_out, uint64_t* launches);
+void launch_fuse(cudaStream_t s, PipeState* st, const float* top_T, const float* top_s1, const float* top_s2, float fine_number, int topk, ArgTable& tab, uint64_t* launches);
 // per-voxel (s,t) rows of one hypothesis: rows of 5 ints, *d_nrows rows
 void launch_score_dump(cudaStream_t s, const fccf_params& p, const float* d_T16, const float* d_s2, const ScoreWS& ws, int* d_rows, int cap_rows, int* d_nrows, ArgTable& tab, uint64_t* launches);
 

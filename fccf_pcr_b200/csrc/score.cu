@@ -620,6 +620,13 @@ __global__ void fuse_kernel(const FuseArgs* __restrict__ AB) {
   T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
 }
 
+// per-type best + gate + fusion alone (stand-alone stage entry point fccf_fuse)
+void launch_fuse(cudaStream_t s, PipeState* st, const float* top_T, const float* top_s1, const float* top_s2, float fine_number, int topk, ArgTable& tab, uint64_t* launches) {
+  FuseArgs F; F.st = st; F.top_T = top_T; F.top_s1 = top_s1; F.top_s2 = top_s2; F.fine_number = fine_number; F.topk = topk;
+  fuse_kernel<<<1, 1, 0, s>>>(tab.put(&F, 1));
+  if (launches) *launches += 1;
+}
+
 // fine verify in two parts: the static voxel table of cloud 1's leftover points (depends only on the plane
 // stage, so a captured graph runs it on a branch beside hypotheses / clustering / quick verify), then the
 // scoring of the selected centres and the fusion.

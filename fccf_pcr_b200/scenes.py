@@ -43,6 +43,7 @@ class _Scene:
         self.rects = []      # (origin, u, v) parallelogram, or (origin, u, v, True) triangle
         self.spheres = []    # (centre, radius)
         self.cyls = []       # (centre, radius, height)
+        self.rough = {}      # rect index -> (amplitude, wavelength) of a long-wave undulation along u ("rough" planes)
 
     def add_box(self, centre, size, yaw, bottom=False):
         R = _rot_z(yaw)
@@ -82,6 +83,12 @@ class _Scene:
                 a = np.where(flip, 1.0 - a, a)
                 b = np.where(flip, 1.0 - b, b)
             p = o[None, :] + a[:, None] * u[None, :] + b[:, None] * v[None, :]
+            if k in self.rough:
+                # neighbouring 1 m voxels see normals a few degrees apart: a plane whose roughness (mean angle
+                # between the face normal and its voxels' normals, FCCF.cpp:660-667) exceeds rough_threshold_gl
+                amp, lam = self.rough[k]
+                nrm = np.cross(u, v); nrm = nrm / np.linalg.norm(nrm)
+                p = p + (amp * np.sin(2.0 * math.pi * a * np.linalg.norm(u) / lam))[:, None] * nrm[None, :]
             if undulation is not None and k == 0:
                 p[:, 2] += undulation(p[:, 0], p[:, 1])
             out.append(p)
@@ -152,11 +159,14 @@ def make_pair(kind="indoor", n_points=50_000, seed=1, overlap=0.7, sigma=0.005, 
     cropped by a half space so that roughly `overlap` of it is seen by the other.
     """
     rng_scene = np.random.Generator(np.random.PCG64(seed))
-    sc = _indoor_scene(rng_scene) if kind == "indoor" else _outdoor_scene(rng_scene)
+    sc = _indoor_scene(rng_scene) if kind in ("indoor", "indoor_rough") else _outdoor_scene(rng_scene)
+    if kind == "indoor_rough":      # every second surface undulates: roughness types 1 (rough-rough) and 2 (mixed) appear
+        for k in range(1, len(sc.rects), 2):
+            sc.rough[k] = (0.045, 4.0)
     und = None
-    if kind != "indoor":
+    if kind not in ("indoor", "indoor_rough"):
         und = lambda x, y: 0.4 * np.sin(x / 17.0) * np.cos(y / 23.0)  # noqa: E731
-    ext = 5.0 if kind == "indoor" else 100.0
+    ext = 5.0 if kind in ("indoor", "indoor_rough") else 100.0
     clouds = []
     for which in (0, 1):
         rng = np.random.Generator(np.random.PCG64([seed, 1000 + which]))

@@ -155,6 +155,26 @@ int fccf_score_counts(fccf_ctx* ctx, size_t hyp, int32_t* rows, size_t cap_rows,
 int fccf_quick_verify(fccf_ctx* ctx, float* T, size_t n_hyp, const float* planes1, int f1, const float* planes2, int f2,
                       float* scores, int32_t* pair_count, int32_t* pairs, int32_t* iters);
 
+/* replaces: select_base (FCCF.cpp:429-468) on one plane table (F x 7 floats: centroid, normal, point size) with its
+ * roughness values theta (F doubles, FCCF.cpp:660-667): pairs = rows of (i, j, type), angles = included angles. */
+int fccf_base_pairs(fccf_ctx* ctx, const float* planes, const double* theta, int f, int32_t* pairs, float* angles, int32_t* n_pairs);
+
+/* replaces: select_base x 2, the pair-descriptor match loop (FCCF.cpp:1412-1427), computer_transform (841-1018) and
+ * the matrix -> quaternion conversion (1439-1462) on two plane tables.  n_hyp: hypotheses per roughness type; the
+ * pools themselves are read with fccf_debug_blob: base1/2, base_angle1/2, matches, hyp0..2 (3x4), hyp_qt0..2. */
+int fccf_hypotheses(fccf_ctx* ctx, const float* planes1, const double* theta1, int f1, const float* planes2, const double* theta2, int f2,
+                    int32_t n_hyp[3]);
+
+/* replaces: cluster_num (FCCF.cpp:1465) + transform_cluster (1040-1231) for the three pools given as rows of
+ * (qw qx qy qz tx ty tz), pools concatenated in type order.  Centres etc. through fccf_debug_blob: centre0..2,
+ * n_centres, cluster_num, cluster_seed_sorted<t>, cluster_size_sorted<t>. */
+int fccf_cluster(fccf_ctx* ctx, const float* qt7, const int32_t n_hyp[3], int32_t n_centres[3]);
+
+/* replaces: the per-type best by s1/sum(s1) + s2/sum(s2), the 0.8 gate and fuse_answer (FCCF.cpp:1546-1606,
+ * 1291-1368) on up to 3 x k fine-verified candidates: top_T [3][k] row-major 4x4, s1 / s2 [3][k] (quick / fine
+ * score), n_top[t] candidates of type t in rank order.  Blob type_best: per type (score, 3x4). */
+int fccf_fuse(fccf_ctx* ctx, const float* top_T, const float* s1, const float* s2, const int32_t n_top[3], int k, float T_out[16]);
+
 /* Stage intermediates of the last fccf_register / fccf_extract_planes call, copied to host memory.
  * Returns FCCF_ERR_ARG for an unknown name; *bytes = size needed (also when dst is NULL). */
 int fccf_debug_blob(fccf_ctx* ctx, const char* name, void* dst, size_t cap_bytes, size_t* bytes, int* dtype);

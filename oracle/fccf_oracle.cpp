@@ -858,7 +858,11 @@ static void rot_with_jac(const double q[4], const double a[3], double f[3], doub
 // sum over rows is the xor-butterfly order  v[l] += v[l^16], v[l^8], ... v[l^1]  — Ceres/Eigen's
 // own blocked summation order is unknowable here, so the oracle fixes this one (it is the order a
 // 32-lane warp reduction produces, which lets the CUDA path agree to the last bit of the sums).
+// g_lm_sequential = 1 (test switch "lm_sequential"): plain row-order sums v[0] + v[1] + ... instead, to MEASURE how
+// much that choice matters (tests/test_oracle_kat.py::test_oracle_switches_do_not_move_the_result).
+static int g_lm_sequential = 0;
 static double bfly32(const double* v) {
+  if (g_lm_sequential) { double s = 0.0; for (int l = 0; l < 32; l++) s += v[l]; return s; }
   double a[16];   // lane 0 of the butterfly only needs the halving tree
   for (int l = 0; l < 16; l++) a[l] = v[l] + v[l + 16];
   for (int o = 8; o; o >>= 1) for (int l = 0; l < o; l++) a[l] = a[l] + a[l + o];
@@ -1149,6 +1153,89 @@ static void put_points(Ctx& C, const std::string& name, const std::vector<P3>& v
 }
 
 // FCCF.cpp:1370-1608.  `source`/`target` are the function's parameters: cloud 1 / cloud 2.
+// select_base x 2 (FCCF.cpp:1406,1409), the pair-descriptor match loop (1412-1427) and computer_transform (841-1018):
+// the three hypothesis pools in push_back order.  Blobs: base1/2, base_angle1/2, matches.
+static void stage_hypotheses(Ctx& C, const std::vector<FaceNode>& f1, const std::vector<double>& th1, const std::vector<FaceNode>& f2,
+                             const std::vector<double>& th2, std::vector<std::vector<M4f>>& tv) {
+  const Params& P = C.p;
+  std::vector<FaceBase> b1, b2; std::vector<int> ty1, ty2;
+  select_base(P, b1, f1, ty1, th1);
+  select_base(P, b2, f2, ty2, th2);
+  if (C.keep_blobs) {
+    for (int c = 0; c < 2; c++) {
+      auto& b = c ? b2 : b1; auto& ty = c ? ty2 : ty1;
+      std::vector<int> bi; std::vector<float> ba;
+      for (size_t i = 0; i < b.size(); i++) { bi.push_back(b[i].i1); bi.push_back(b[i].i2); bi.push_back(ty[i]); ba.push_back(b[i].angel); }
+      C.put_i32(c ? "base2" : "base1", bi); C.put_f32(c ? "base_angle2" : "base_angle1", ba);
+    }
+  }
+  float angthr = P.included_angle_same_threshold;
+  std::vector<int> matches;
+  for (size_t i1 = 0; i1 < b1.size(); i1++)
+    for (size_t i2 = 0; i2 < b2.size(); i2++)
+      if ((std::fabs(b1[i1].angel - b2[i2].angel)) < angthr && ty1[i1] == ty2[i2] && ty1[i1] < 3) {
+        size_t before = tv[ty1[i1]].size();
+        computer_transform(P, tv, b1[i1].i1, b1[i1].i2, b2[i2].i1, b2[i2].i2, f1, f2, ty1[i1]);
+        matches.push_back((int)i1); matches.push_back((int)i2); matches.push_back((int)(tv[ty1[i1]].size() - before));
+      }
+  C.put_i32("matches", matches);
+}
+
+// matrix -> quaternion of one pool (FCCF.cpp:1439-1462).  Blobs: hyp<t>, hyp_qt<t>.
+static void pool_to_qt(Ctx& C, const char* tg, const std::vector<M4f>& pool, std::vector<QT>& qv) {
+  for (auto& M : pool) {
+    M3f R; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) R.m[a][b] = M.m[a][b];
+    Quatf q = quat_from_matrix(R);
+    qv.push_back(QT{q.w, q.x, q.y, q.z, M.m[0][3], M.m[1][3], M.m[2][3], false});
+  }
+  if (C.keep_blobs) {
+    std::vector<float> h; for (auto& M : pool) for (int a = 0; a < 3; a++) for (int b = 0; b < 4; b++) h.push_back(M.m[a][b]);
+    C.put_f32(std::string("hyp") + tg, h);
+    std::vector<float> hq; for (auto& q : qv) { hq.push_back(q.qw); hq.push_back(q.qx); hq.push_back(q.qy); hq.push_back(q.qz); hq.push_back(q.tx); hq.push_back(q.ty); hq.push_back(q.tz); }
+    C.put_f32(std::string("hyp_qt") + tg, hq);
+  }
+}
+
+// cluster_num (FCCF.cpp:1465) + transform_cluster (1466) of one pool.  Blob: centre<t> (+ the seed / size lists).
+static int pool_cluster(Ctx& C, const char* tg, std::vector<QT>& qv, int tnum, std::vector<QT>& fine) {
+  const Params& P = C.p;
+  float cnf = P.seclct_cluster_number * qv.size() / tnum;
+  int cluster_num = (cnf == cnf) ? (int)cnf : INT32_MIN;  // NaN cast: cvttss2si gives INT_MIN
+  transform_cluster(C, tg, qv, fine, cluster_num);
+  if (C.keep_blobs) {
+    std::vector<float> ce; for (auto& q : fine) { ce.push_back(q.qw); ce.push_back(q.qx); ce.push_back(q.qy); ce.push_back(q.qz); ce.push_back(q.tx); ce.push_back(q.ty); ce.push_back(q.tz); }
+    C.put_f32(std::string("centre") + tg, ce);
+  }
+  return cluster_num;
+}
+
+// Per-type best of the fine-verified hypotheses by s1 / sum(s1) + s2 / sum(s2) with the sums over ALL types (Q19),
+// the 0.8 gate and fuse_answer (FCCF.cpp:1546-1606).  cand[t]: the fine-verified hypotheses of type t in rank order.
+// Blob: type_best.
+static void stage_fuse(Ctx& C, const std::vector<std::vector<TScore>>& cand, M4f& best) {
+  float score_sum = 0, score1_sum = 0, score2_sum = 0;
+  for (int i = 0; i < 3; i++) for (auto& ts : cand[i]) { score2_sum += ts.score2; score1_sum += ts.score; }
+  std::vector<HighScore> tmp3; float best_best = 0;
+  std::vector<float> type_best;
+  for (int i = 0; i < 3; i++) {
+    float best_score = 0; M4f tb = identity4();
+    for (auto& ts : cand[i]) {
+      float score = ts.score / score1_sum + ts.score2 / score2_sum;
+      if (score > best_score) { best_score = score; tb = ts.T; }
+    }
+    if (best_best < best_score) best_best = best_score;
+    M3f R; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) R.m[a][b] = tb.m[a][b];
+    Quatf q = quat_from_matrix(R);
+    HighScore h; h.qt = QT{q.w, q.x, q.y, q.z, tb.m[0][3], tb.m[1][3], tb.m[2][3], false}; h.score = best_score;
+    tmp3.push_back(h);
+    type_best.push_back(best_score); for (int a = 0; a < 3; a++) for (int b = 0; b < 4; b++) type_best.push_back(tb.m[a][b]);
+  }
+  C.put_f32("type_best", type_best);
+  std::vector<HighScore> hs;
+  for (auto& h : tmp3) if (h.score > best_best * 0.8) { hs.push_back(h); score_sum += h.score; }
+  fuse_answer(best, hs, score_sum);
+}
+
 static void computer_transform_guess(Ctx& C, const std::vector<P3>& source, const std::vector<P3>& target, float leaf, M4f& best) {
   const Params& P = C.p;
   std::vector<P3> c1, c2;
@@ -1161,56 +1248,19 @@ static void computer_transform_guess(Ctx& C, const std::vector<P3>& source, cons
   C.sub1.clear(); C.sub2.clear();
   face_extrate(C, "1", c1, f1, C.sub1, th1);
   face_extrate(C, "2", c2, f2, C.sub2, th2);
-  std::vector<FaceBase> b1, b2; std::vector<int> ty1, ty2;
-  select_base(P, b1, f1, ty1, th1);
-  select_base(P, b2, f2, ty2, th2);
-  if (C.keep_blobs) {
-    for (int c = 0; c < 2; c++) {
-      auto& b = c ? b2 : b1; auto& ty = c ? ty2 : ty1;
-      std::vector<int> bi; std::vector<float> ba;
-      for (size_t i = 0; i < b.size(); i++) { bi.push_back(b[i].i1); bi.push_back(b[i].i2); bi.push_back(ty[i]); ba.push_back(b[i].angel); }
-      C.put_i32(c ? "base2" : "base1", bi); C.put_f32(c ? "base_angle2" : "base_angle1", ba);
-    }
-  }
   std::vector<std::vector<M4f>> tv(3);
-  float angthr = P.included_angle_same_threshold;
-  std::vector<int> matches;
-  for (size_t i1 = 0; i1 < b1.size(); i1++)
-    for (size_t i2 = 0; i2 < b2.size(); i2++)
-      if ((std::fabs(b1[i1].angel - b2[i2].angel)) < angthr && ty1[i1] == ty2[i2] && ty1[i1] < 3) {
-        size_t before = tv[ty1[i1]].size();
-        computer_transform(P, tv, b1[i1].i1, b1[i1].i2, b2[i2].i1, b2[i2].i2, f1, f2, ty1[i1]);
-        matches.push_back((int)i1); matches.push_back((int)i2); matches.push_back((int)(tv[ty1[i1]].size() - before));
-      }
-  C.put_i32("matches", matches);
+  stage_hypotheses(C, f1, th1, f2, th2, tv);
   int tnum = (int)(tv[0].size() + tv[1].size() + tv[2].size());
-  float score_sum = 0, score1_sum = 0, score2_sum = 0;
   std::vector<std::vector<TScore>> ctv(3);
   int analyse_max = (int)P.fine_verify_number;
   std::vector<int> n_hyp, n_centres, cluster_nums;
   for (int i = 0; i < 3; i++) {
-    std::vector<QT> qv;
-    for (auto& M : tv[i]) {
-      M3f R; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) R.m[a][b] = M.m[a][b];
-      Quatf q = quat_from_matrix(R);
-      qv.push_back(QT{q.w, q.x, q.y, q.z, M.m[0][3], M.m[1][3], M.m[2][3], false});
-    }
     char tg[8]; snprintf(tg, sizeof tg, "%d", i);
-    if (C.keep_blobs) {
-      std::vector<float> h; for (auto& M : tv[i]) for (int a = 0; a < 3; a++) for (int b = 0; b < 4; b++) h.push_back(M.m[a][b]);
-      C.put_f32(std::string("hyp") + tg, h);
-      std::vector<float> hq; for (auto& q : qv) { hq.push_back(q.qw); hq.push_back(q.qx); hq.push_back(q.qy); hq.push_back(q.qz); hq.push_back(q.tx); hq.push_back(q.ty); hq.push_back(q.tz); }
-      C.put_f32(std::string("hyp_qt") + tg, hq);
-    }
+    std::vector<QT> qv;
+    pool_to_qt(C, tg, tv[i], qv);
     std::vector<QT> fine;
-    float cnf = P.seclct_cluster_number * tv[i].size() / tnum;
-    int cluster_num = (cnf == cnf) ? (int)cnf : INT32_MIN;  // NaN cast: cvttss2si gives INT_MIN
-    transform_cluster(C, tg, qv, fine, cluster_num);
+    int cluster_num = pool_cluster(C, tg, qv, tnum, fine);
     n_hyp.push_back((int)tv[i].size()); n_centres.push_back((int)fine.size()); cluster_nums.push_back(cluster_num);
-    if (C.keep_blobs) {
-      std::vector<float> ce; for (auto& q : fine) { ce.push_back(q.qw); ce.push_back(q.qx); ce.push_back(q.qy); ce.push_back(q.qz); ce.push_back(q.tx); ce.push_back(q.ty); ce.push_back(q.tz); }
-      C.put_f32(std::string("centre") + tg, ce);
-    }
     std::vector<float> qs, qT; std::vector<int> qpairs, qpoff, qiters;
     int ci = 0;
     for (auto& q : fine) {
@@ -1232,35 +1282,15 @@ static void computer_transform_guess(Ctx& C, const std::vector<P3>& source, cons
         asum++;
         std::vector<int> counts;
         ts.score2 = fine_verify(P, ts.T, C.sub1, C.sub2, C.keep_blobs ? &counts : nullptr);
-        score2_sum += ts.score2; score1_sum += ts.score;
         if (C.keep_blobs) { for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) topT.push_back(ts.T.m[a][b]); tops1.push_back(ts.score); tops2.push_back(ts.score2); topc.push_back(ts.centre); fvoff.push_back((int)fvc.size() / 5); for (int v : counts) fvc.push_back(v); }
       } else break;
     }
     if (C.keep_blobs) { fvoff.push_back((int)fvc.size() / 5); C.put_f32(std::string("top_T") + tg, topT); C.put_f32(std::string("top_s1") + tg, tops1); C.put_f32(std::string("top_s2") + tg, tops2); C.put_i32(std::string("top_centre") + tg, topc); C.put_i32(std::string("fv_counts") + tg, fvc); C.put_i32(std::string("fv_off") + tg, fvoff); }
   }
   C.put_i32("n_hyp", n_hyp); C.put_i32("n_centres", n_centres); C.put_i32("cluster_num", cluster_nums);
-  std::vector<HighScore> tmp3; float best_best = 0;
-  std::vector<float> type_best;
-  for (int i = 0; i < 3; i++) {
-    int asum = 0; float best_score = 0; M4f tb = identity4();
-    for (auto& ts : ctv[i]) {
-      if (asum < analyse_max) {
-        asum++;
-        float score = ts.score / score1_sum + ts.score2 / score2_sum;
-        if (score > best_score) { best_score = score; tb = ts.T; }
-      }
-    }
-    if (best_best < best_score) best_best = best_score;
-    M3f R; for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) R.m[a][b] = tb.m[a][b];
-    Quatf q = quat_from_matrix(R);
-    HighScore h; h.qt = QT{q.w, q.x, q.y, q.z, tb.m[0][3], tb.m[1][3], tb.m[2][3], false}; h.score = best_score;
-    tmp3.push_back(h);
-    type_best.push_back(best_score); for (int a = 0; a < 3; a++) for (int b = 0; b < 4; b++) type_best.push_back(tb.m[a][b]);
-  }
-  C.put_f32("type_best", type_best);
-  std::vector<HighScore> hs;
-  for (auto& h : tmp3) if (h.score > best_best * 0.8) { hs.push_back(h); score_sum += h.score; }
-  fuse_answer(best, hs, score_sum);
+  std::vector<std::vector<TScore>> cand(3);
+  for (int i = 0; i < 3; i++) { int asum = 0; for (auto& ts : ctv[i]) { if (asum < analyse_max) { asum++; cand[i].push_back(ts); } else break; } }
+  stage_fuse(C, cand, best);
 }
 
 // main(): FCCF.cpp:1646-1690 (argv order: SRC, TAR; pipeline called with (TAR, SRC), Q1)
@@ -1306,6 +1336,7 @@ int orc_set_param(void* c, const char* name, double v) {
 #undef SP
   if (n == "emulate_pcl_overflow") { p.emulate_pcl_overflow = (int)v; return 0; }
   if (n == "libm_float") { g_libm_float = (int)v; return 0; }   // process-wide (test switch)
+  if (n == "lm_sequential") { g_lm_sequential = (int)v; return 0; }   // process-wide (test switch)
   return -1;
 }
 // full program: src = argv[1], tar = argv[2]; T row-major 16 floats
@@ -1383,6 +1414,54 @@ float orc_quick_verify(void* c, float* T16, const float* planes1, int F1, const 
   if (npairs) *npairs = (int)pr.size() / 2;
   if (iters) *iters = it;
   return s;
+}
+static std::vector<FaceNode> to_faces(const float* planes, int F) {
+  std::vector<FaceNode> f(F);
+  for (int i = 0; i < F; i++) { const float* p = planes + 7 * i; f[i].cx = p[0]; f[i].cy = p[1]; f[i].cz = p[2]; f[i].nx = p[3]; f[i].ny = p[4]; f[i].nz = p[5]; f[i].size = p[6]; f[i].alloc = false; f[i].id = i; }
+  return f;
+}
+// select_base + match loop + computer_transform + matrix -> quaternion on two plane tables (F x 7: c, n, size) with their
+// roughness values; results as blobs base1/2, base_angle1/2, matches, n_hyp, hyp<t>, hyp_qt<t>
+int orc_hypotheses(void* c, const float* planes1, const double* theta1, int F1, const float* planes2, const double* theta2, int F2) {
+  Ctx& C = *(Ctx*)c; C.blobs.clear();
+  std::vector<FaceNode> f1 = to_faces(planes1, F1), f2 = to_faces(planes2, F2);
+  std::vector<double> th1(theta1, theta1 + F1), th2(theta2, theta2 + F2);
+  std::vector<std::vector<M4f>> tv(3);
+  stage_hypotheses(C, f1, th1, f2, th2, tv);
+  std::vector<int> n_hyp;
+  for (int i = 0; i < 3; i++) { char tg[8]; snprintf(tg, sizeof tg, "%d", i); std::vector<QT> qv; pool_to_qt(C, tg, tv[i], qv); n_hyp.push_back((int)tv[i].size()); }
+  C.put_i32("n_hyp", n_hyp);
+  return 0;
+}
+// cluster_num + transform_cluster of three pools given as (qw qx qy qz tx ty tz) rows, pools concatenated; results as
+// blobs centre<t>, n_centres, cluster_num, cluster_seed_sorted<t>, cluster_size_sorted<t>
+int orc_cluster(void* c, const float* qt7, const int* n_hyp3) {
+  Ctx& C = *(Ctx*)c; C.blobs.clear();
+  int tnum = n_hyp3[0] + n_hyp3[1] + n_hyp3[2];
+  std::vector<int> n_centres, cluster_nums; size_t off = 0;
+  for (int i = 0; i < 3; i++) {
+    char tg[8]; snprintf(tg, sizeof tg, "%d", i);
+    std::vector<QT> qv, fine;
+    for (int k = 0; k < n_hyp3[i]; k++) { const float* q = qt7 + 7 * (off + k); qv.push_back(QT{q[0], q[1], q[2], q[3], q[4], q[5], q[6], false}); }
+    off += n_hyp3[i];
+    cluster_nums.push_back(pool_cluster(C, tg, qv, tnum, fine)); n_centres.push_back((int)fine.size());
+  }
+  C.put_i32("n_centres", n_centres); C.put_i32("cluster_num", cluster_nums);
+  return 0;
+}
+// per-type best + 0.8 gate + fuse_answer on up to 3 x k fine-verified candidates (row-major 4x4, quick score s1, fine
+// score s2; n_top3[t] candidates of type t in rank order); blob type_best
+int orc_fuse(void* c, const float* top_T, const float* s1, const float* s2, const int* n_top3, int k, float* T16) {
+  Ctx& C = *(Ctx*)c; C.blobs.clear();
+  std::vector<std::vector<TScore>> cand(3);
+  for (int t = 0; t < 3; t++) for (int j = 0; j < n_top3[t]; j++) {
+    TScore ts; memcpy(ts.T.m, top_T + 16 * ((size_t)t * k + j), 64); ts.score = s1[t * k + j]; ts.score2 = s2[t * k + j]; ts.centre = j;
+    cand[t].push_back(ts);
+  }
+  M4f best = identity4();
+  stage_fuse(C, cand, best);
+  memcpy(T16, best.m, 64);
+  return 0;
 }
 // stdout of main() (FCCF.cpp:1667, 1687): default ostream float formatting + Eigen's default IOFormat
 // (precision = stream's, every column right-aligned to the widest coefficient, " " and "\n" separators)

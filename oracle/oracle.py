@@ -50,6 +50,9 @@ def lib():
         L.orc_bench_fine_verify.restype = C.c_double
         L.orc_quick_verify.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, C.c_int, ip, ip, ip]
         L.orc_quick_verify.restype = C.c_float
+        L.orc_hypotheses.argtypes = [C.c_void_p, fp, dp, C.c_int, fp, dp, C.c_int]
+        L.orc_cluster.argtypes = [C.c_void_p, fp, ip]
+        L.orc_fuse.argtypes = [C.c_void_p, fp, fp, fp, ip, C.c_int, fp]
         L.orc_blob_bytes.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_blob_bytes.restype = C.c_int64
         L.orc_blob_dtype.argtypes = [C.c_void_p, C.c_char_p]
@@ -192,6 +195,38 @@ class Oracle:
         iters = C.c_int(0)
         s = self.L.orc_quick_verify(self.h, _f(T), _f(p1), len(p1), _f(p2), len(p2), _i(pairs), C.byref(npairs), C.byref(iters))
         return float(s), T.reshape(4, 4), pairs[:npairs.value].copy(), iters.value
+
+
+def _stage_methods():
+    def hypotheses(self, planes1, theta1, planes2, theta2):
+        p1 = np.ascontiguousarray(planes1, np.float32).reshape(-1, 7)
+        p2 = np.ascontiguousarray(planes2, np.float32).reshape(-1, 7)
+        t1 = np.ascontiguousarray(theta1, np.float64)
+        t2 = np.ascontiguousarray(theta2, np.float64)
+        dp = C.POINTER(C.c_double)
+        self.L.orc_hypotheses(self.h, _f(p1), t1.ctypes.data_as(dp), len(p1), _f(p2), t2.ctypes.data_as(dp), len(p2))
+        return self.blob("n_hyp")
+
+    def cluster(self, qt7, n_hyp):
+        q = np.ascontiguousarray(qt7, np.float32).reshape(-1, 7)
+        nh = np.ascontiguousarray(n_hyp, np.int32)
+        self.L.orc_cluster(self.h, _f(q), _i(nh))
+        return self.blob("n_centres")
+
+    def fuse(self, top_T, s1, s2, n_top):
+        T = np.ascontiguousarray(top_T, np.float32)
+        k = T.shape[1]
+        a = np.ascontiguousarray(s1, np.float32).reshape(3, k)
+        b = np.ascontiguousarray(s2, np.float32).reshape(3, k)
+        nt = np.ascontiguousarray(n_top, np.int32)
+        out = np.zeros(16, np.float32)
+        self.L.orc_fuse(self.h, _f(T), _f(a), _f(b), _i(nt), k, _f(out))
+        return out.reshape(4, 4)
+
+    Oracle.hypotheses, Oracle.cluster, Oracle.fuse = hypotheses, cluster, fuse
+
+
+_stage_methods()
 
 
 def format_output(leaf, T):

@@ -358,3 +358,72 @@ def test_libm_switch_bounds_the_last_ulp_effect(oracle_mod):
     pa, pb = a.blob("pvox1"), b.blob("pvox1")
     assert np.abs(pa - pb).max() <= 2.5e-7 and (pa != pb).mean() < 0.05
     assert scenes.rotation_error_deg(Ta, Tb) <= 0.01 and scenes.translation_error(Ta, Tb) <= 1e-3
+
+
+def test_oracle_switches_do_not_move_the_result(oracle_mod):
+    """Two choices of the oracle were made so that the CUDA path can agree with it to the last bit: float libm calls
+    of pcl::eigen33 evaluated correctly rounded (instead of the platform's float libm), and every Levenberg-Marquardt
+    row sum taken in xor-butterfly order (instead of row order).  This measures what they are worth: with the
+    platform float libm (libm_float = 1) and / or plain row-order sums (lm_sequential = 1) every decision of the
+    pipeline stays the same and the final transform moves by far less than the 0.01 degree / 1 mm parity bar."""
+    from fccf_pcr_b200 import scenes
+
+    cases = [("indoor", 20000, 7, 0.1, {}), ("indoor", 50000, 1, 0.1, {}), ("indoor", 200000, 2, 0.2, {}),
+             ("indoor_rough", 200000, 5, 0.2, dict(third_plane_threshold=0.02, included_angle_same_threshold=30.0, third_plane_normal_threshold=15.0))]
+    worst = (0.0, 0.0)
+    try:
+        for kind, n, seed, leaf, prm in cases:
+            src, tar, _ = scenes.make_pair(kind, n, seed)
+            ref = oracle_mod.Oracle(**prm)
+            T0 = ref.register(src, tar, leaf)
+            keep = {nm: ref.blob(nm).copy() for nm in ["merge_label1", "merge_label2", "base1", "base2", "matches", "n_hyp", "n_centres",
+                                                       "top_centre0", "top_centre1", "top_centre2", "qv_pairs0", "qv_pairs2"]}
+            for libm, seq in ((1, 0), (0, 1), (1, 1)):
+                o = oracle_mod.Oracle(libm_float=libm, lm_sequential=seq, **prm)
+                T = o.register(src, tar, leaf)
+                for nm, v in keep.items():
+                    assert np.array_equal(o.blob(nm), v), (kind, seed, libm, seq, nm)
+                de, dt = scenes.rotation_error_deg(T, T0), scenes.translation_error(T, T0)
+                worst = (max(worst[0], de), max(worst[1], dt))
+                assert de <= 1e-3 and dt <= 1e-4, (kind, seed, libm, seq, de, dt)      # a tenth of the parity bar
+                for t in range(3):
+                    for Ta, Tb in zip(o.blob("top_T%d" % t).reshape(-1, 4, 4), ref.blob("top_T%d" % t).reshape(-1, 4, 4)):
+                        assert scenes.rotation_error_deg(Ta, Tb) <= 1e-3 and scenes.translation_error(Ta, Tb) <= 1e-4
+    finally:
+        oracle_mod.Oracle(libm_float=0, lm_sequential=0)      # the switches are process-wide
+    print("oracle switches: worst final-transform shift %.2e deg, %.2e m" % worst)
+
+
+def test_stage_functions_known_answers(orc):
+    """Hand-checkable answers of the stage entry points of the oracle (select_base, cluster bypass, fusion)."""
+    import math
+
+    def plane(n, c=(0, 0, 0), size=100):
+        return [*c, *n, size]
+
+    c20, s20 = math.cos(math.radians(20)), math.sin(math.radians(20))
+    planes = np.array([plane((1, 0, 0)), plane((0, 1, 0)), plane((c20, s20, 0)), plane((0, 0, 1))], np.float32)
+    theta = np.array([0.5, 3.0, 2.0, np.nan])
+    orc.hypotheses(planes, theta, np.zeros((0, 7), np.float32), np.zeros(0))
+    base = orc.blob("base1").reshape(-1, 3).tolist()
+    # (0,1) 90 deg smooth/rough -> type 2; (0,2) 20 deg: outside (30, 150); (0,3) 90 deg with a NaN roughness -> type 3 ("none");
+    # (1,2) 70 deg rough/smooth(2.0 <= 2) -> type 2; (1,3), (2,3) -> type 3
+    assert base == [[0, 1, 2], [0, 3, 3], [1, 2, 2], [1, 3, 3], [2, 3, 3]]
+    np.testing.assert_allclose(orc.blob("base_angle1"), [90, 90, 70, 90, 90], atol=1e-3)
+    # Q12: empty pool -> one identity centre; 10 hypotheses pass through untouched
+    ten = np.tile(np.array([1, 0, 0, 0, 0.1, 0.2, 0.3], np.float32), (10, 1)) + np.arange(10, dtype=np.float32)[:, None] * 0.01
+    nc = orc.cluster(np.concatenate([ten]), [0, 10, 0])
+    assert nc.tolist() == [1, 10, 1]
+    assert orc.blob("centre0").tolist() == [1, 0, 0, 0, 0, 0, 0] and np.array_equal(orc.blob("centre1").reshape(-1, 7), ten)
+    assert orc.blob("cluster_num").tolist() == [0, 200, 0]
+    # fusion of a single surviving type returns that hypothesis (rotation rebuilt from its x / y axes)
+    T = np.zeros((3, 1, 4, 4), np.float32)
+    a = math.radians(30)
+    T[0, 0] = [[math.cos(a), -math.sin(a), 0, 1.0], [math.sin(a), math.cos(a), 0, 2.0], [0, 0, 1, 3.0], [0, 0, 0, 1]]
+    out = orc.fuse(T, [[0.5], [0], [0]], [[0.25], [0], [0]], [1, 0, 0])
+    np.testing.assert_allclose(out, T[0, 0], atol=1e-6)
+    tb = orc.blob("type_best").reshape(3, 13)
+    assert tb[0, 0] == 2.0 and tb[1, 0] == 0.0            # 0.5/0.5 + 0.25/0.25; empty types score 0
+    # Q15: NaN fine scores -> nothing survives the gate -> zero rotation block
+    out = orc.fuse(T, [[0.5], [0], [0]], [[np.nan], [0], [0]], [1, 0, 0])
+    assert not np.any(np.nan_to_num(out[:3, :3]))

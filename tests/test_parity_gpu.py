@@ -55,6 +55,32 @@ def _check_inlier_counts(c, o):
             assert abs(s2g[k] - so) <= 1e-5 * abs(so) or (np.isnan(so) and np.isnan(s2g[k]))
 
 
+def _legitimately_absent(o, thr=10):
+    """Blobs the oracle only emits for pools that are clustered (more than cluster_number_threshold hypotheses,
+    FCCF.cpp:1043): for smaller pools there is no seed list and no size list."""
+    out = set()
+    for t, n in enumerate(o.blob("n_hyp")):
+        if n <= thr:
+            out |= {"cluster_seed_sorted%d" % t, "cluster_size_sorted%d" % t}
+    return out
+
+
+def _refined_agree(Tg, To, T0, planes1, planes2, pairs):
+    """The rule for a refined transform (replaces the former 90 % gates): GPU and oracle agree within the bar
+    (0.01 degree, 1 mm).  A pair that does not must be an ill-conditioned problem — smallest / largest eigenvalue
+    of J^T J at the float64 scipy.optimize.least_squares solution below 1e-9, i.e. the matched planes leave a
+    direction unconstrained — AND both results must be minimisers of it: cost within 1e-6 (relative, plus 1e-12)
+    of the independent solve.  Anything else fails."""
+    import lm_check
+
+    if scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3:
+        return True
+    rows = lm_check.problem(T0, planes1, planes2, pairs)
+    _, cs, ratio = lm_check.solve(T0, rows)
+    cg, co = lm_check.cost_of(Tg, T0, rows), lm_check.cost_of(To, T0, rows)
+    return ratio < 1e-9 and cg <= cs * (1 + 1e-6) + 1e-12 and co <= cs * (1 + 1e-6) + 1e-12
+
+
 def _rel_rows(a, b, width, groups):
     """max over rows of |a-b| / max(|b|) per group of columns (a vector's error relative to its norm)."""
     a = a.reshape(-1, width).astype(np.float64)
@@ -91,8 +117,10 @@ def test_integer_stages_bit_exact(ctx, runs, case):
     src, tar, Tgt, o, To, Tg = runs(case)
     assert ctx.timing.n_launches > 0
     names = set(o.blob_names())
+    absent_ok = _legitimately_absent(o)
     for name in INT_BLOBS + EXACT_FLOAT_BLOBS:
         if name not in names:
+            assert name in absent_ok, "the oracle does not emit %s (typo, or a stage that did not run?)" % name
             continue
         a, b = ctx.blob(name), o.blob(name)
         assert a.shape == b.shape, name
@@ -128,6 +156,8 @@ def test_hypotheses_clusters_and_scores(ctx, runs, case):
     src, tar, Tgt, o, To, Tg = runs(case)
     for t in range(3):
         assert _rel_rows(ctx.blob("hyp%d" % t), o.blob("hyp%d" % t), 12, [[0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11]]) <= 1e-4
+        # matrix -> quaternion of every hypothesis (FCCF.cpp:1439-1462, a11)
+        assert _rel_rows(ctx.blob("hyp_qt%d" % t), o.blob("hyp_qt%d" % t), 7, [[0, 1, 2, 3], [4, 5, 6]]) <= 1e-4
         assert _rel_rows(ctx.blob("centre%d" % t), o.blob("centre%d" % t), 7, [[0, 1, 2, 3], [4, 5, 6]]) <= 1e-4
         np.testing.assert_array_equal(ctx.blob("qv_score%d" % t), o.blob("qv_score%d" % t))      # plane-pair importance sums
         np.testing.assert_array_equal(ctx.blob("top_s1%d" % t), o.blob("top_s1%d" % t))
@@ -152,9 +182,22 @@ def test_hypotheses_clusters_and_scores(ctx, runs, case):
                 assert it_g[ci] in (-1, -2) and (it_g[ci] == -2) == (it_o[ci] >= 0)
 
 
+def _check_type_best(c, o):
+    """Per-type best of the fine-verified hypotheses and its normalised score (FCCF.cpp:1546-1596, a17): 3 rows of
+    (score, 3x4)."""
+    a, b = c.blob("type_best").reshape(3, 13), o.blob("type_best").reshape(3, 13)
+    assert np.array_equal(np.isnan(a[:, 0]), np.isnan(b[:, 0]))
+    np.testing.assert_allclose(np.nan_to_num(a[:, 0]), np.nan_to_num(b[:, 0]), rtol=5e-2, atol=1e-6)     # ratios of fine scores: see the fine-score bound
+    for ty in range(3):
+        Ta, Tb = np.eye(4), np.eye(4)
+        Ta[:3, :] = a[ty, 1:].reshape(3, 4); Tb[:3, :] = b[ty, 1:].reshape(3, 4)
+        assert scenes.rotation_error_deg(Ta, Tb) <= 0.01 and scenes.translation_error(Ta, Tb) <= 1e-3, ty
+
+
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%d-seed%d-leaf%g" % c)
 def test_final_transform(ctx, runs, case):
     src, tar, Tgt, o, To, Tg = runs(case)
+    _check_type_best(ctx, o)
     assert scenes.rotation_error_deg(Tg, To) <= 0.01          # degrees
     assert scenes.translation_error(Tg, To) <= 1e-3           # metres
     np.testing.assert_array_equal(Tg[3], [0, 0, 0, 1])
@@ -284,7 +327,7 @@ def test_quick_verify_stage(ctx, orc):
     o.register(src, tar, 0.1)
     p1 = o.blob("face_plane1").reshape(-1, 7)
     p2 = o.blob("face_plane2").reshape(-1, 7)
-    cen = o.blob("centre0").reshape(-1, 7)[:24]
+    cen = o.blob("centre0").reshape(-1, 7)          # EVERY centre of the pool, not a sample
     Ts = []
     for c in cen:
         T = np.eye(4, dtype=np.float32)
@@ -293,13 +336,12 @@ def test_quick_verify_stage(ctx, orc):
         Ts.append(T)
     Ts = np.stack(Ts)
     sc, Tr, npair, pairs, iters = ctx.quick_verify(Ts, p1, p2)
-    agree = 0
     for k in range(len(Ts)):
         so, To, po, io = o.quick_verify(Ts[k], p1, p2)
         assert sc[k] == np.float32(so)
         assert npair[k] == len(po) and np.array_equal(pairs[k, :npair[k]], po)       # pair lists bit-exact
-        agree += scenes.rotation_error_deg(Tr[k], To) <= 0.01 and scenes.translation_error(Tr[k], To) <= 1e-3
-    assert agree >= 0.9 * len(Ts)
+        assert (iters[k] >= 0) == (io >= 0)
+        assert _refined_agree(Tr[k], To, Ts[k], p1, p2, po), "refined hypothesis %d" % k
 
 
 def test_golden_fixture(ctx):
@@ -496,11 +538,20 @@ def test_exhaustive_scoring_mode(oracle_mod):
         assert len(sel) == min(int(nc[t]), 256)
         np.testing.assert_array_equal(sel, o.blob("top_centre%d" % t))
         np.testing.assert_array_equal(c.blob("top_s1%d" % t), o.blob("top_s1%d" % t))
+        # every refined centre: transforms within the bar (or shown ill-conditioned, see _refined_agree) ...
+        Ta, Tb = c.blob("top_T%d" % t).reshape(-1, 4, 4), o.blob("top_T%d" % t).reshape(-1, 4, 4)
+        cen = o.blob("centre%d" % t).reshape(-1, 7)
+        p1, p2 = o.blob("face_plane1").reshape(-1, 7), o.blob("face_plane2").reshape(-1, 7)
+        po, off = o.blob("qv_pairs%d" % t).reshape(-1, 2), o.blob("qv_pair_off%d" % t)
+        for k in range(len(Ta)):
+            ci = int(sel[k])
+            T0 = np.eye(4, dtype=np.float32); T0[:3, :3] = o.quat_to_matrix(cen[ci, :4]); T0[:3, 3] = cen[ci, 4:7]
+            assert _refined_agree(Ta[k], Tb[k], T0, p1, p2, po[off[ci]:off[ci + 1]]), "type %d centre %d" % (t, ci)
+        # ... and their fine scores within what the bar itself allows: 0.01 degree at 10 m plus 1 mm moves a point
+        # by < 3 mm, and the points that close to one of the three faces of a 0.5 m voxel are ~3 % of the cloud
         a, b = c.blob("top_s2%d" % t), o.blob("top_s2%d" % t)
-        # fine scores of every refined centre; ill-conditioned (wrong) hypotheses amplify last-ulp libm differences of the LM
-        close = np.isclose(a, b, rtol=1e-3, atol=1e-6)
-        assert close.mean() >= 0.9, "type %d: %d of %d fine scores agree" % (t, close.sum(), len(a))
-    _check_inlier_counts(c, o) if False else None
+        np.testing.assert_allclose(a, b, rtol=5e-2, atol=2e-4, err_msg="type %d fine scores" % t)
+    _check_inlier_counts(c, o)      # bit-exact per-voxel counts and scores with the oracle fed the GPU's own transforms
     assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
     assert scenes.rotation_error_deg(Tg, Tgt) < 1.0 and scenes.translation_error(Tg, Tgt) < 0.08
     c.close()
@@ -602,3 +653,45 @@ def test_voxelgrid_without_pcl_overflow_emulation(oracle_mod):
         Tg, To = c.register(src, tar, 0.1), o.register(src, tar, 0.1)
         assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
         c.close()
+
+
+RICH = ("indoor_rough", 200000, 5, 0.2)
+RICH_PRM = dict(third_plane_threshold=0.02, included_angle_same_threshold=30.0, third_plane_normal_threshold=15.0)
+
+
+def test_rich_200k_three_pools_14k_hypotheses(oracle_mod):
+    """BASELINE config 2 size with everything populated: every second surface of the room undulates, so that the
+    three roughness pools (smooth-smooth, rough-rough, mixed) are all non-empty, and widened matching thresholds
+    give H = 14 020 hypotheses (pools of 6268 / 296 / 7456: both clustering paths).  Same parameters on both
+    sides; every stage blob compared."""
+    import fccf_pcr_b200 as fccf
+
+    src, tar, Tgt = scenes.make_pair(*RICH[:3])
+    o = oracle_mod.Oracle(**RICH_PRM)
+    To = o.register(src, tar, RICH[3])
+    c = fccf.Context(0, **RICH_PRM)
+    Tg = c.register(src, tar, RICH[3])
+    nh = o.blob("n_hyp")
+    assert (nh > 0).all() and nh.sum() >= 10000, nh
+    names = set(o.blob_names())
+    absent_ok = _legitimately_absent(o)
+    for name in INT_BLOBS + EXACT_FLOAT_BLOBS:
+        if name not in names:
+            assert name in absent_ok, name
+            continue
+        a, b = c.blob(name), o.blob(name)
+        assert a.shape == b.shape, name
+        assert np.array_equal(a, b, equal_nan=(a.dtype.kind == "f")), "%s: %d of %d entries differ" % (name, int((a != b).sum()), a.size)
+    for t in range(3):
+        assert _rel_rows(c.blob("hyp%d" % t), o.blob("hyp%d" % t), 12, [[0, 1, 2, 4, 5, 6, 8, 9, 10], [3, 7, 11]]) <= 1e-4
+        assert _rel_rows(c.blob("hyp_qt%d" % t), o.blob("hyp_qt%d" % t), 7, [[0, 1, 2, 3], [4, 5, 6]]) <= 1e-4
+        assert _rel_rows(c.blob("centre%d" % t), o.blob("centre%d" % t), 7, [[0, 1, 2, 3], [4, 5, 6]]) <= 1e-4
+        np.testing.assert_array_equal(c.blob("qv_score%d" % t), o.blob("qv_score%d" % t))
+        np.testing.assert_array_equal(c.blob("top_s1%d" % t), o.blob("top_s1%d" % t))
+        for Ta, Tb in zip(c.blob("top_T%d" % t).reshape(-1, 4, 4), o.blob("top_T%d" % t).reshape(-1, 4, 4)):
+            assert scenes.rotation_error_deg(Ta, Tb) <= 0.01 and scenes.translation_error(Ta, Tb) <= 1e-3
+    _check_inlier_counts(c, o)
+    _check_type_best(c, o)
+    assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
+    assert scenes.rotation_error_deg(Tg, Tgt) < 1.0 and scenes.translation_error(Tg, Tgt) < 0.08
+    c.close()
