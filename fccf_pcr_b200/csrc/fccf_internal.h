@@ -38,7 +38,7 @@ struct VGState {
   int nbits;
   float inv;
   int n_out;                 // number of output points
-  int pad;
+  int pad;                   // generic path: number of cells left to the warp-per-cell centroid kernel (voxelgrid.cu: VG_BIG)
 };
 struct OctState {
   double mn[3], mx[3];

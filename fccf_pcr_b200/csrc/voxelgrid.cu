@@ -127,7 +127,9 @@ struct VGOut {
   float* out[2];
   long long* cell[2];
   int* cnt[2];
+  u32* big[2];               // cells of more than VG_BIG points, left to vg_centroid_big_kernel (count: st->pad)
 };
+#define VG_BIG 192
 
 // one thread per occupied cell: in-order float32 running sum (pcl::CentroidPoint<PointXYZ>)
 template <typename KT>
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(128) vg_centroid_kernel(const VGOut* __restric
   const u32* idx = A.idx[c];
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nseg; s += gridDim.x * blockDim.x) {
     const int b = A.seg_start[c][s], e = A.seg_start[c][s + 1];
+    if (e - b > VG_BIG) { A.big[c][atomicAdd(&st->pad, 1)] = (u32)s; continue; }     // a warp sums it (below)
     float sx = 0.f, sy = 0.f, sz = 0.f;
     // the sum is sequential (in index order, like pcl::CentroidPoint) but the gathers are not: eight points
     // of the cell are fetched at once before they are added
@@ -159,6 +162,60 @@ __global__ void __launch_bounds__(128) vg_centroid_kernel(const VGOut* __restric
   }
 }
 
+// Cells of many points (a coarse leaf on a dense cloud: 10M points in a few hundred cells, BASELINE config 5) would keep
+// ONE thread adding tens of thousands of gathered points.  Here a CTA takes such a cell: its 8 warps gather 8 x 32
+// points of it per step into one half of a double-buffered shared-memory tile set while lanes 0..2 of warp 0 add the
+// other half's x / y / z in order — one dependent float add per point, which is the floor pcl::CentroidPoint's
+// sequential sum allows (a 32k-point cell: ~0.15 ms instead of the 7 ms of one warp with one gather in flight).
+template <typename KT>
+__global__ void __launch_bounds__(256) vg_centroid_big_kernel(const VGOut* __restrict__ AB) {
+  const VGOut& A = AB[blockIdx.z];
+  const int c = blockIdx.y;
+  VGState* st = A.st[c];
+  const int nbig = st->pad;
+  if (nbig == 0) return;
+  const float* p = A.in[c] ? A.in[c] : A.call->raw[c];
+  const u32* idx = A.idx[c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float tile[2][8][96];
+  for (int k = blockIdx.x; k < nbig; k += gridDim.x) {
+    const int s = (int)A.big[c][k];
+    const int b = A.seg_start[c][s], e = A.seg_start[c][s + 1];
+    float acc = 0.f;
+    // first step
+    { const int q = b + warp * 32 + lane; if (q < e) { const float* r = p + 3 * (size_t)idx[q]; float* t = &tile[0][warp][3 * lane]; t[0] = r[0]; t[1] = r[1]; t[2] = r[2]; } }
+    __syncthreads();
+    int cur = 0;
+    for (int k0 = b; k0 < e; k0 += 256) {
+      // gather the next step's point of this thread (loads in flight while warp 0 adds)
+      const int q = k0 + 256 + warp * 32 + lane;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      if (q < e) { const float* r = p + 3 * (size_t)idx[q]; r0 = r[0]; r1 = r[1]; r2 = r[2]; }
+      if (warp == 0 && lane < 3) {
+        const int m = min(256, e - k0);
+        const float* t = &tile[cur][0][lane];
+        int j = 0;
+        for (; j + 8 <= m; j += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) v[u] = t[3 * (j + u)];
+#pragma unroll
+          for (int u = 0; u < 8; u++) acc += v[u];
+        }
+        for (; j < m; j++) acc += t[3 * j];
+      }
+      float* nt = &tile[cur ^ 1][warp][3 * lane];
+      nt[0] = r0; nt[1] = r1; nt[2] = r2;
+      __syncthreads();
+      cur ^= 1;
+    }
+    const float fn = (float)(e - b);
+    if (warp == 0 && lane < 3) A.out[c][3 * (size_t)s + lane] = acc / fn;
+    if (threadIdx.x == 0) { A.cell[c][s] = (long long)((const KT*)A.keys[c])[b]; A.cnt[c][s] = e - b; }
+    __syncthreads();
+  }
+}
+
 struct InitArgs { PipeState* st; };
 __global__ void init_state_kernel(const InitArgs* __restrict__ AB, const CallArgs* __restrict__ calls) {
   PipeState* st = AB[blockIdx.x].st;
@@ -169,7 +226,7 @@ __global__ void init_state_kernel(const InitArgs* __restrict__ AB, const CallArg
     const int n0 = call.n0, n1 = call.n1;
     for (int s = 0; s < 2; s++) for (int c = 0; c < 2; c++) {
       VGState& v = st->vg[s][c];
-      v.n_in = 0; v.n_finite = 0; v.n_out = 0; v.bail = 0; v.total = 0; v.nbits = 1;
+      v.n_in = 0; v.n_finite = 0; v.n_out = 0; v.bail = 0; v.total = 0; v.nbits = 1; v.pad = 0;
       for (int a = 0; a < 3; a++) { v.mn[a] = 0x7fffffff; v.mx[a] = (int)0x80000000; v.minb[a] = 0; v.div[a] = 1; }
     }
     st->vg[0][0].n_in = n0; st->vg[0][1].n_in = n1;
@@ -213,9 +270,10 @@ void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uin
       sj.j[c] = sg;
       O.in[c] = A.in[c]; O.keys[c] = cw.keyA; O.idx[c] = cw.idxA; O.seg_start[c] = cw.seg_start; O.st[c] = &st->vg[stage][c];
       O.out[c] = cw.vg_xyz[stage]; O.cell[c] = cw.vg_cell[stage]; O.cnt[c] = cw.vg_cnt[stage];
+      O.big[c] = cw.hist;            // the sort's histogram buffer is free by then: (cap / 2048 + 2) * 256 entries >= cap / VG_BIG
       if (cw.cap > cap) cap = cw.cap;
     }
-    for (int c = ncloud; c < 2; c++) { A.in[c] = A.in[0]; A.n_in[c] = A.n_in[0]; A.st[c] = A.st[0]; A.keys[c] = A.keys[0]; A.ticket[c] = A.ticket[0]; }
+    for (int c = ncloud; c < 2; c++) { O.big[c] = O.big[0]; A.in[c] = A.in[0]; A.n_in[c] = A.n_in[0]; A.st[c] = A.st[0]; A.keys[c] = A.keys[0]; A.ticket[c] = A.ticket[0]; }
     A.call = &st->call; O.call = &st->call; A.emulate = b.p.emulate_pcl_overflow;
   }
   const VGArgs* dA = b.tab->put(As.data(), G); const VGOut* dO = b.tab->put(Os.data(), G);
@@ -236,7 +294,10 @@ void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uin
   const dim3 gc(grid_x((cap + 127) / 128, G, ncloud, 16384), ncloud, G);
   if (kb == 4) vg_centroid_kernel<u32><<<gc, 128, 0, s>>>(dO);
   else vg_centroid_kernel<u64><<<gc, 128, 0, s>>>(dO);
-  if (launches) *launches += 1;
+  const dim3 gb(grid_x(148 * 2, G, ncloud, 4096), ncloud, G);
+  if (kb == 4) vg_centroid_big_kernel<u32><<<gb, 256, 0, s>>>(dO);
+  else vg_centroid_big_kernel<u64><<<gb, 256, 0, s>>>(dO);
+  if (launches) *launches += 2;
 }
 
 }  // namespace fccf

@@ -439,17 +439,28 @@ def test_full_size_outdoor_2M(oracle_mod):
     c.close()
 
 
-@pytest.mark.parametrize("leaf", [0.1, 0.5])
+_PAIR_10M = {}
+
+
+def _pair_10m():
+    if not _PAIR_10M:
+        _PAIR_10M["p"] = scenes.make_pair("indoor", 10_000_000, 5)
+    return _PAIR_10M["p"]
+
+
+@pytest.mark.parametrize("leaf", [0.05, 0.1, 0.2, 0.3, 0.5, 0.75, 1.0])
 def test_full_size_10M(leaf, oracle_mod):
-    """BASELINE config 5 shape: 10M + 10M points, two leaves of the sweep: size-independent properties, and
-    (the oracle's own cost here is the 10M-point sort, a few seconds) the integer stages against the oracle.
-    Leaf 0.5 with the reference's fixed 1 m plane voxels is the near-degenerate case Q14: a handful of planar
-    voxels, reproduced as it is."""
+    """BASELINE config 5: 10M + 10M points, every leaf of the sweep with the reference's default parameters:
+    size-independent properties, and (the oracle's own cost here is the 10M-point sort, a couple of seconds) the
+    integer stages against the oracle.  Leaf >= 0.5 with the reference's fixed 1 m plane voxels is the (near-)
+    degenerate regime Q14: a handful of planar voxels or none, reproduced as it is; there a few hundred cells hold
+    tens of thousands of points each (the warp-per-cell centroid kernel)."""
     import fccf_pcr_b200 as fccf
 
-    src, tar, Tgt = scenes.make_pair("indoor", 10_000_000, 5)
+    src, tar, Tgt = _pair_10m()
     c = fccf.Context(0)
-    _voxelgrid_properties(c, src, leaf)
+    if leaf in (0.1, 0.5, 1.0):
+        _voxelgrid_properties(c, src, leaf)
     T = c.register(src, tar, leaf)
     assert c.timing.n_launches > 0 and c.timing.h2d_bytes == 240_000_000
     assert np.array_equal(c.register(src, tar, leaf), T, equal_nan=True)
@@ -457,13 +468,11 @@ def test_full_size_10M(leaf, oracle_mod):
     assert int(c.blob("vg2_cnt1").sum()) == len(c.blob("vg1_cnt1"))
     o = oracle_mod.Oracle()
     To = o.register(src, tar, leaf)
-    for name in ["vg1_cell1", "vg1_cnt1", "vg2_cell2", "vg2_cnt2", "vox_key1", "vox_cnt2", "merge_label1", "merge_label2", "base1", "base2", "matches", "n_hyp", "n_centres"]:
+    for name in ["vg1_cell1", "vg1_cnt1", "vg1_xyz1", "vg1_xyz2", "vg2_cell2", "vg2_cnt2", "vox_key1", "vox_cnt2", "merge_label1", "merge_label2", "base1", "base2", "matches", "n_hyp", "n_centres"]:
         assert np.array_equal(c.blob(name), o.blob(name)), name
     assert np.array_equal(np.isnan(T), np.isnan(To))
     if not np.isnan(To).any():
         assert scenes.rotation_error_deg(T, To) <= 0.01 and scenes.translation_error(T, To) <= 1e-3
-    if leaf < 0.4:
-        assert scenes.rotation_error_deg(T, Tgt) < 1.0 and scenes.translation_error(T, Tgt) < 0.08
     c.close()
 
 
