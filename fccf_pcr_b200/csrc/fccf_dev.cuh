@@ -236,8 +236,8 @@ __device__ void warp_exchange_sort(K* key, int* perm, int n, Less less) {
 __device__ __forceinline__ unsigned ord_key(int v) { return (unsigned)v ^ 0x80000000u; }
 __device__ __forceinline__ unsigned ord_key(float f) { unsigned b = __float_as_uint(f + 0.0f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 template <typename K>
-__device__ void block_exchange_sort_passes(K* key, int* perm, int n, unsigned long long* s_scratch) {
-  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, warp = t >> 5, nw = nt >> 5;
+__device__ void block_exchange_sort_passes(K* key, int* perm, int n, unsigned long long* s_scratch, int nt_) {
+  const int t = threadIdx.x, nt = nt_, lane = t & 31, warp = t >> 5, nw = nt >> 5;
   unsigned long long* s_w = s_scratch;                 // [32] exclusive prefix max over warps
   unsigned long long* s_tot = s_scratch + 32;          // [1]  chunk maximum
   unsigned long long* s_carry = s_scratch + 33;        // [1]  running maximum (packed) ...
@@ -302,8 +302,9 @@ __device__ void block_exchange_sort_passes(K* key, int* perm, int n, unsigned lo
 // total order (ints, non-NaN floats).
 #define XS_B 4
 template <typename K>
-__device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long* s_scratch) {
-  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, warp = t >> 5, nw = nt >> 5;
+// nt_: threads of the block that call (all of them still alive; a block whose surplus warps have exited passes the rest)
+__device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long* s_scratch, int nt_ = 0) {
+  const int t = threadIdx.x, nt = nt_ > 0 ? nt_ : (int)blockDim.x, lane = t & 31, warp = t >> 5, nw = nt >> 5;
   if (n < 2) return;
   // P: number of keys above the minimum
   unsigned* s_u = (unsigned*)s_scratch;              // [32] + [1]
@@ -352,7 +353,7 @@ __device__ void block_exchange_sort(K* key, int* perm, int n, unsigned long long
     __syncthreads();
   }
   if (P > n - 1) P = n - 1;
-  if (P > 3 * nt) { block_exchange_sort_passes(key, perm, n, s_scratch); return; }
+  if (P > 3 * nt) { block_exchange_sort_passes(key, perm, n, s_scratch, nt); return; }
   if (P <= 0 && thr == mn) return;
   // passes owned by this thread: t, t + nt, t + 2 nt.  Only the warps that own a pass take part in the
   // step loop (named barrier 1 over nact threads); the rest wait at the closing block barrier.
