@@ -701,7 +701,7 @@ static int register_many(fccf_ctx* ctx, int n_pairs, const float* const* src, co
   std::vector<int> chunk;
   for (int rem = n_pairs; rem > 0;) {
     int c = std::min(nl, rem);
-    if (host_in && nl >= 16 && !getenv("FCCF_NO_TAPER")) c = std::min(nl, std::max(nl / 4, rem / 2));
+    if (host_in && nl >= 4 && !getenv("FCCF_NO_TAPER")) c = std::min(nl, std::max(nl / 4, rem / 2));
     if (c > rem) c = rem;
     chunk.push_back(c); rem -= c;
   }
