@@ -35,6 +35,7 @@ struct ClArgs {
 };
 
 __global__ void __launch_bounds__(256) cluster_prep_kernel(const ClArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ClArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int n = st->hyp_off[3];
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) cluster_prep_kernel(const ClArgs* __restr
 }
 
 __global__ void __launch_bounds__(256) cluster_xs_kernel(const ClArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ClArgs& A = AB[blockIdx.z];
   const int n = A.st->hyp_off[3];
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -127,6 +129,7 @@ __device__ void cl_emit_centre(const float* qt, const int* mem, int m, float* ou
 extern __shared__ __align__(16) unsigned char cl_dyn[];
 
 __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ClArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int ty = blockIdx.x;
@@ -489,12 +492,12 @@ void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches) {
   }
   const ClArgs* dA = b.tab->put(As.data(), G);
   const SortJobs* dab = b.tab->put(abs_.data(), G); const SortJobs* dba = b.tab->put(bas_.data(), G);
-  cluster_prep_kernel<<<dim3(grid_x((cap + 255) / 256, G), 1, G), 256, 0, s>>>(dA);
+  klaunch(cluster_prep_kernel, dim3(dim3(grid_x((cap + 255) / 256, G), 1, G)), dim3(256), 0, s, dA);
   if (launches) *launches += 1;
   // 34-bit keys: 6 passes of 6 bits (even pass count: result back in ckeyA / cidxA)
   launch_sort(s, dab, dba, 1, G, cap, 6, 8, launches);
-  cluster_xs_kernel<<<dim3(grid_x((cap + 255) / 256, G), 1, G), 256, 0, s>>>(dA);
-  cluster_kernel<<<dim3(3, 1, G), 1024, CL_SMEM_BYTES, s>>>(dA);
+  klaunch(cluster_xs_kernel, dim3(dim3(grid_x((cap + 255) / 256, G), 1, G)), dim3(256), 0, s, dA);
+  klaunch(cluster_kernel, dim3(dim3(3, 1, G)), dim3(1024), CL_SMEM_BYTES, s, dA);
   if (launches) *launches += 2;
 }
 

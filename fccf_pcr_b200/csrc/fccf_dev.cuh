@@ -197,11 +197,12 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 // Pass i moves the first maximum of the suffix to position i and shifts every strict
 // left-to-right record of the suffix to the next record's position.  Called by one full warp;
 // key[]/perm[] live in shared or global memory.  `less(a,b)` is the reference's comparison.
+// npass: only the first npass passes (positions [0, npass) are then final, the rest is a permutation of the tail)
 template <typename K, typename Less>
-__device__ void warp_exchange_sort(K* key, int* perm, int n, Less less) {
+__device__ void warp_exchange_sort(K* key, int* perm, int n, Less less, int npass = 0x7fffffff) {
   const unsigned full = 0xffffffffu;
   int lane = threadIdx.x & 31;
-  for (int i = 0; i + 1 < n; i++) {
+  for (int i = 0; i + 1 < n && i < npass; i++) {
     K cur = key[i]; int curp = perm[i];
     bool moved = false;
     for (int base = i + 1; base < n; base += 32) {

@@ -217,7 +217,34 @@ struct Batch {                // the lanes one batched launch sequence covers
   ArgTable* tab;
   fccf_params p;
   AngleCuts cuts;
+  // inside a stream capture: a second capture stream and an event pair for work that may run beside the main
+  // sequence (nullptr outside captures: everything is launched in order on the one stream)
+  cudaStream_t side = nullptr; cudaEvent_t side_fork = nullptr, side_join = nullptr;
 };
+
+
+// ---- launches -------------------------------------------------------------------------------------
+// Every kernel of the library starts with FCCF_PDL_ENTER(): it lets the grids that depend on it be scheduled at
+// once (griddepcontrol.launch_dependents) and then waits until everything it depends on has completed and is
+// visible (griddepcontrol.wait).  A launch made while `fccf_pdl_on()` holds carries the programmatic stream
+// serialization attribute, so inside a captured sequence the next kernel's CTAs are already resident, spinning in
+// the wait, when the previous grid drains: the ~2 us launch gap between dependent kernels of a registration
+// (60+ per pair) shrinks to the drain itself.  Both instructions are no-ops for ordinary launches.  The wait is
+// executed before ANY exit path, so completion stays transitive along the chain.
+#ifdef __CUDACC__
+#define FCCF_PDL_ENTER() do { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+bool& fccf_pdl_flag();
+inline bool fccf_pdl_on() { return fccf_pdl_flag(); }
+template <typename... KA, typename... A>
+inline cudaError_t klaunch(void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaStream_t s, A... a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = fccf_pdl_on() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, KA(a)...);
+}
+#endif
 
 // copies calls[lane] into every lane's state block and resets the per-registration counters
 void launch_init_state(cudaStream_t s, const Batch& b, const CallArgs* d_calls, uint64_t* launches);

@@ -140,6 +140,7 @@ __device__ int hyp_generate_warp(const FaceTable& f1, const FaceTable& f2, int i
 }
 
 __global__ void __launch_bounds__(256) base_pairs_kernel(const HypArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(256) base_pairs_kernel(const HypArgs* __restri
 // ---- match loop (FCCF.cpp:1415-1427): one thread per (pair of cloud 1, pair of cloud 2): descriptor test
 // (included angle within 5 degrees, same roughness type).  match_cnt: 0 / 1 = matched (counted later) ----
 __global__ void __launch_bounds__(128) match_test_kernel(const HypArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int B1 = st->base[0].B, B2 = st->base[1].B;
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(128) match_test_kernel(const HypArgs* __restri
 
 // ---- ordered list of the matched entries (one CTA) ----
 __global__ void __launch_bounds__(1024) match_compact_kernel(const HypArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(1024) match_compact_kernel(const HypArgs* __re
 
 // ---- hypotheses per match: one warp per matched entry ----
 __global__ void __launch_bounds__(128) hyp_count_kernel(const HypArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int lane = threadIdx.x & 31;
@@ -236,6 +240,7 @@ __global__ void __launch_bounds__(128) hyp_count_kernel(const HypArgs* __restric
 struct u3 { u32 a[3]; };
 __device__ __forceinline__ u32 sat_add(u32 x, u32 y, u32 lim) { const u32 s = x + y; return (s < x || s > lim) ? lim : s; }
 __global__ void __launch_bounds__(1024) match_scan_kernel(const HypArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -279,6 +284,7 @@ __global__ void __launch_bounds__(1024) match_scan_kernel(const HypArgs* __restr
 }
 
 __global__ void __launch_bounds__(128) emit_hyp_kernel(const HypArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int lane = threadIdx.x & 31;
@@ -307,12 +313,12 @@ void launch_hypotheses(cudaStream_t s, const Batch& b, uint64_t* launches) {
   }
   const HypArgs* dA = b.tab->put(As.data(), G);
   const int nbw = grid_x((FCCF_MAXMATCH + 3) / 4, G);     // warp-per-match kernels: 4 warps per CTA, strided over the list
-  base_pairs_kernel<<<dim3(1, 1, G), 256, 0, s>>>(dA);
-  match_test_kernel<<<dim3(grid_x((FCCF_MAXMATCH + 127) / 128, G), 1, G), 128, 0, s>>>(dA);
-  match_compact_kernel<<<dim3(1, 1, G), 1024, 0, s>>>(dA);
-  hyp_count_kernel<<<dim3(nbw, 1, G), 128, 0, s>>>(dA);
-  match_scan_kernel<<<dim3(1, 1, G), 1024, 0, s>>>(dA);
-  emit_hyp_kernel<<<dim3(nbw, 1, G), 128, 0, s>>>(dA);
+  klaunch(base_pairs_kernel, dim3(dim3(1, 1, G)), dim3(256), 0, s, dA);
+  klaunch(match_test_kernel, dim3(dim3(grid_x((FCCF_MAXMATCH + 127) / 128, G), 1, G)), dim3(128), 0, s, dA);
+  klaunch(match_compact_kernel, dim3(dim3(1, 1, G)), dim3(1024), 0, s, dA);
+  klaunch(hyp_count_kernel, dim3(dim3(nbw, 1, G)), dim3(128), 0, s, dA);
+  klaunch(match_scan_kernel, dim3(dim3(1, 1, G)), dim3(1024), 0, s, dA);
+  klaunch(emit_hyp_kernel, dim3(dim3(nbw, 1, G)), dim3(128), 0, s, dA);
   if (launches) *launches += 6;
 }
 

@@ -44,6 +44,7 @@ __device__ __forceinline__ unsigned sc_hash32(u32 k) { return k * 0x9E3779B1u; }
 
 // lattice origin: first insert into an empty pcl octree: box = p0 +- res/2, padded to depth 1
 __global__ void score_setup_kernel(const ScArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ScArgs& A = AB[blockIdx.z];
   ScoreState* ss = A.ws.ss;
   if (threadIdx.x != 0) return;
@@ -75,6 +76,7 @@ __device__ __forceinline__ bool sc_lattice(const ScoreState* ss, double res, flo
 
 // bounding box of the static lattice coordinates; the last block derives the compact key layout
 __global__ void __launch_bounds__(256) score_bbox_kernel(const ScArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ScArgs& A = AB[blockIdx.z];
   ScoreState* ss = A.ws.ss;
   const int n1 = ss->n1;
@@ -128,6 +130,7 @@ __device__ __forceinline__ u32 sc_compact(const ScoreState* ss, const int l[3]) 
 }
 
 __global__ void __launch_bounds__(256) score_keys_kernel(const ScArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ScArgs& A = AB[blockIdx.z];
   const ScoreState* ss = A.ws.ss;
   const int n = ss->n_keys;
@@ -164,6 +167,7 @@ __device__ __forceinline__ ScPlan sc_plan(const ScoreState* ss, int cap_hash) {
 
 // per occupied voxel (ascending key): key and static count; clears the hash and the dense table
 __global__ void __launch_bounds__(256) score_table_kernel(const ScArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ScArgs& A = AB[blockIdx.z];
   ScoreState* ss = A.ws.ss;
   const int nocc = ss->n_occ;
@@ -178,6 +182,7 @@ __global__ void __launch_bounds__(256) score_table_kernel(const ScArgs* __restri
   }
 }
 __global__ void __launch_bounds__(256) score_insert_kernel(const ScArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ScArgs& A = AB[blockIdx.z];
   const ScoreState* ss = A.ws.ss;
   const int nocc = ss->n_occ, cap = ss->cap_eff, mode = ss->mode;
@@ -244,6 +249,7 @@ extern __shared__ __align__(16) unsigned char sc_dyn[];
 // cloud 32 points at a time.  No block-wide synchronisation after the table load.
 template <bool POW2>
 __global__ void __launch_bounds__(SC_THREADS, 1) score_warp_kernel(const ScArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ScArgs& A = AB[blockIdx.z];
   const ScoreState* ss = A.ws.ss;
   const int mode = ss->mode;
@@ -332,6 +338,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_warp_kernel(const ScArgs*
 // counters live in the CTA's rows of t_cnt.
 template <bool POW2>
 __global__ void __launch_bounds__(SC_THREADS) score_kernel(const ScArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ScArgs& A = AB[blockIdx.z];
   const ScoreState* ss = A.ws.ss;
   if (ss->mode != 2) return;                      // the launcher issues both kernels; one of them runs
@@ -401,6 +408,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_kernel(const ScArgs* __restr
 // per-voxel rows (Lx, Ly, Lz, s, t) of ONE hypothesis, L relative to the voxel of the first static point
 template <bool POW2>
 __global__ void __launch_bounds__(SC_THREADS) score_dump_kernel(const ScArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const ScArgs& A = AB[blockIdx.z];
   const ScoreState* ss = A.ws.ss;
   const int t = threadIdx.x;
@@ -482,16 +490,16 @@ void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJo
   const SortJobs* dab = tab.put(abs_.data(), G); const SortJobs* dba = tab.put(bas_.data(), G); const SegJobs* dsj = tab.put(sjs.data(), G);
   int nb = (cap + 255) / 256; if (nb > 1184) nb = 1184;
   nb = grid_x(nb, G);
-  score_setup_kernel<<<dim3(1, 1, G), 32, 0, s>>>(dA);
-  score_bbox_kernel<<<dim3(nb, 1, G), 256, 0, s>>>(dA);
-  score_keys_kernel<<<dim3(nb, 1, G), 256, 0, s>>>(dA);
+  klaunch(score_setup_kernel, dim3(dim3(1, 1, G)), dim3(32), 0, s, dA);
+  klaunch(score_bbox_kernel, dim3(dim3(nb, 1, G)), dim3(256), 0, s, dA);
+  klaunch(score_keys_kernel, dim3(dim3(nb, 1, G)), dim3(256), 0, s, dA);
   if (launches) *launches += 3;
   launch_sort(s, dab, dba, 1, G, cap, 4, 4, launches);
   launch_segments(s, dsj, 1, G, cap, 4, launches);
   int nbh = (cap_hash + 255) / 256; if (nbh > 1184) nbh = 1184;
   nbh = grid_x(nbh, G);
-  score_table_kernel<<<dim3(nbh, 1, G), 256, 0, s>>>(dA);
-  score_insert_kernel<<<dim3(nb, 1, G), 256, 0, s>>>(dA);
+  klaunch(score_table_kernel, dim3(dim3(nbh, 1, G)), dim3(256), 0, s, dA);
+  klaunch(score_insert_kernel, dim3(dim3(nb, 1, G)), dim3(256), 0, s, dA);
   if (launches) *launches += 2;
 }
 
@@ -512,11 +520,11 @@ static void score_launch(cudaStream_t s, const std::vector<ScArgs>& As, ArgTable
   const ScArgs* dA = tab.put(As.data(), G);
   // which kernel does the work is a device-side fact (table plan); the other one exits at once
   if (is_pow2_res(As[0].res)) {
-    score_warp_kernel<true><<<dim3(nbw, 1, G), SC_THREADS, SC_DYN_BYTES, s>>>(dA);
-    score_kernel<true><<<dim3(nbg, 1, G), SC_THREADS, 0, s>>>(dA);
+    klaunch(score_warp_kernel<true>, dim3(dim3(nbw, 1, G)), dim3(SC_THREADS), SC_DYN_BYTES, s, dA);
+    klaunch(score_kernel<true>, dim3(dim3(nbg, 1, G)), dim3(SC_THREADS), 0, s, dA);
   } else {
-    score_warp_kernel<false><<<dim3(nbw, 1, G), SC_THREADS, SC_DYN_BYTES, s>>>(dA);
-    score_kernel<false><<<dim3(nbg, 1, G), SC_THREADS, 0, s>>>(dA);
+    klaunch(score_warp_kernel<false>, dim3(dim3(nbw, 1, G)), dim3(SC_THREADS), SC_DYN_BYTES, s, dA);
+    klaunch(score_kernel<false>, dim3(dim3(nbg, 1, G)), dim3(SC_THREADS), 0, s, dA);
   }
   if (launches) *launches += 2;
 }
@@ -532,8 +540,8 @@ void launch_score_dump(cudaStream_t s, const fccf_params& p, const float* d_T16,
   ScArgs A; fill_common(A, p, ws);
   A.T = d_T16; A.n_hyp = 1; A.s2 = d_s2; A.rows = d_rows; A.cap_rows = cap_rows; A.nrows = d_nrows;
   const ScArgs* dA = tab.put(&A, 1);
-  if (is_pow2_res(A.res)) score_dump_kernel<true><<<1, SC_THREADS, 0, s>>>(dA);
-  else score_dump_kernel<false><<<1, SC_THREADS, 0, s>>>(dA);
+  if (is_pow2_res(A.res)) klaunch(score_dump_kernel<true>, dim3(1), dim3(SC_THREADS), 0, s, dA);
+  else klaunch(score_dump_kernel<false>, dim3(1), dim3(SC_THREADS), 0, s, dA);
   if (launches) *launches += 1;
 }
 
@@ -549,6 +557,7 @@ __device__ __forceinline__ long long pack_score(float sc, long long gidx) {
   return ((long long)key << 32) | (long long)(0xffffffffll - gidx);
 }
 __global__ void __launch_bounds__(256) score_best_kernel(const float* __restrict__ scores, int n, long long index_base, long long* out) {
+  FCCF_PDL_ENTER();
   long long best = (long long)0x8000000000000000ull;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     long long p = pack_score(scores[i], index_base + i);
@@ -570,7 +579,7 @@ void launch_score_best(cudaStream_t s, const float* d_scores, int n, long long i
   cudaMemsetAsync((char*)d_out + 7, top, 1, s);
   if (n <= 0) return;
   int nb = (n + 255) / 256; if (nb > 592) nb = 592;
-  score_best_kernel<<<nb, 256, 0, s>>>(d_scores, n, index_base, d_out);
+  klaunch(score_best_kernel, dim3(nb), dim3(256), 0, s, d_scores, n, index_base, d_out);
   if (launches) *launches += 1;
 }
 
@@ -579,6 +588,7 @@ struct FuseArgs { PipeState* st; const float* top_T; const float* top_s1; const 
 
 // FCCF.cpp:1546-1606 + fuse_answer 1291-1368
 __global__ void fuse_kernel(const FuseArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const FuseArgs& A = AB[blockIdx.x];
   PipeState* st = A.st;
   float score_sum = 0.f, score1_sum = 0.f, score2_sum = 0.f;
@@ -623,7 +633,7 @@ __global__ void fuse_kernel(const FuseArgs* __restrict__ AB) {
 // per-type best + gate + fusion alone (stand-alone stage entry point fccf_fuse)
 void launch_fuse(cudaStream_t s, PipeState* st, const float* top_T, const float* top_s1, const float* top_s2, float fine_number, int topk, ArgTable& tab, uint64_t* launches) {
   FuseArgs F; F.st = st; F.top_T = top_T; F.top_s1 = top_s1; F.top_s2 = top_s2; F.fine_number = fine_number; F.topk = topk;
-  fuse_kernel<<<1, 1, 0, s>>>(tab.put(&F, 1));
+  klaunch(fuse_kernel, dim3(1), dim3(1), 0, s, tab.put(&F, 1));
   if (launches) *launches += 1;
 }
 
@@ -653,7 +663,7 @@ void launch_fine_verify_fuse(cudaStream_t s, const Batch& b, uint64_t* launches)
     FuseArgs& F = Fs[g]; F.st = st; F.top_T = h.top_T; F.top_s1 = h.top_s1; F.top_s2 = h.top_s2; F.fine_number = b.p.fine_verify_number; F.topk = fccf_topk(b.p);
   }
   score_launch(s, As, *b.tab, launches);
-  fuse_kernel<<<G, 1, 0, s>>>(b.tab->put(Fs.data(), G));
+  klaunch(fuse_kernel, dim3(G), dim3(1), 0, s, b.tab->put(Fs.data(), G));
   if (launches) *launches += 1;
 }
 

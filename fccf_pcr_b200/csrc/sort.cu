@@ -32,13 +32,50 @@ __device__ __forceinline__ int rs_bpp(int nbits, int np) {
   return b < 1 ? 1 : (b > 8 ? 8 : b);
 }
 
+// Jobs of up to RS_SMALL keys are sorted by ONE CTA in shared memory before the passes (bitonic network over
+// (key, original index): the same stable order), the result written where an even pass count leaves it (back
+// in kin / vin); the pass kernels of such a job exit at once.
+// A 1k-hypothesis pool costs one ~8 us launch instead of twelve dependent pass kernels.
+#define RS_SMALL 4096
+template <typename KT>
+__global__ void __launch_bounds__(1024) rs_small_kernel(const SortJobs* __restrict__ JB) {
+  FCCF_PDL_ENTER();
+  const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
+  const int n = *j.n;
+  const int t = threadIdx.x;
+  if (n > RS_SMALL) return;
+  __shared__ KT sk[RS_SMALL];
+  __shared__ unsigned short sv[RS_SMALL];
+  KT* kin = (KT*)j.kin;
+  int N = 2;
+  while (N < n) N <<= 1;
+  for (int i = t; i < N; i += 1024) { sk[i] = i < n ? kin[i] : (KT)~(KT)0; sv[i] = (unsigned short)i; }
+  __syncthreads();
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int q = t; q < (N >> 1); q += 1024) {
+        const int lo = ((q & ~(jj - 1)) << 1) | (q & (jj - 1)), hi = lo | jj;
+        const bool up = (lo & k) == 0;
+        const KT a = sk[lo], b = sk[hi];
+        const unsigned short ia = sv[lo], ib = sv[hi];
+        const bool gt = a > b || (a == b && ia > ib);
+        if (gt == up) { sk[lo] = b; sk[hi] = a; sv[lo] = ib; sv[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  u32* vin = const_cast<u32*>(j.vin);
+  for (int i = t; i < n; i += 1024) { kin[i] = sk[i]; vin[i] = (u32)sv[i]; }
+}
+
 template <typename KT>
 __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restrict__ JB, int pass, int np) {
+  FCCF_PDL_ENTER();
   const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
   const KT* __restrict__ kin = (const KT*)j.kin;
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
-  if (pass >= rs_active(*j.nbits, np)) return;
+  if (n <= RS_SMALL || pass >= rs_active(*j.nbits, np)) return;   // small jobs are sorted by rs_small_kernel
   const int t = threadIdx.x;
   __shared__ u32 h[256];
   __shared__ int s_last;
@@ -85,11 +122,12 @@ __global__ void __launch_bounds__(RS_T) rs_hist_kernel(const SortJobs* __restric
 
 template <typename KT>
 __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __restrict__ JB, int pass, int np, int identity) {
+  FCCF_PDL_ENTER();
   const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
   const KT* __restrict__ kin = (const KT*)j.kin; KT* __restrict__ kout = (KT*)j.kout;
   const int n = *j.n;
   const int nact = (n + RS_TILE - 1) / RS_TILE;
-  if (pass >= rs_active(*j.nbits, np)) return;
+  if (n <= RS_SMALL || pass >= rs_active(*j.nbits, np)) return;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   // Warp w owns the 256 consecutive keys [w * 256, (w + 1) * 256) of the tile, in 8 rounds of 32: the stable
   // order of the tile is (warp, round, lane), so ONE private counter row per warp, bumped round after round
@@ -168,14 +206,17 @@ __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __r
 
 void launch_sort(cudaStream_t s, const SortJobs* ab, const SortJobs* ba, int njobs, int G, int cap, int np, int key_bytes, uint64_t* launches) {
   dim3 grid(grid_x((cap + RS_TILE - 1) / RS_TILE, G, njobs), njobs, G);
+  if (key_bytes == 4) klaunch(rs_small_kernel<u32>, dim3(dim3(1, njobs, G)), dim3(1024), 0, s, ab);
+  else klaunch(rs_small_kernel<u64>, dim3(dim3(1, njobs, G)), dim3(1024), 0, s, ab);
+  if (launches) *launches += 1;
   for (int p = 0; p < np; p++) {
     const SortJobs* J = (p & 1) ? ba : ab;
     if (key_bytes == 4) {
-      rs_hist_kernel<u32><<<grid, RS_T, 0, s>>>(J, p, np);
-      rs_scatter_kernel<u32><<<grid, RS_T, 0, s>>>(J, p, np, p == 0 ? 1 : 0);
+      klaunch(rs_hist_kernel<u32>, dim3(grid), dim3(RS_T), 0, s, J, p, np);
+      klaunch(rs_scatter_kernel<u32>, dim3(grid), dim3(RS_T), 0, s, J, p, np, p == 0 ? 1 : 0);
     } else {
-      rs_hist_kernel<u64><<<grid, RS_T, 0, s>>>(J, p, np);
-      rs_scatter_kernel<u64><<<grid, RS_T, 0, s>>>(J, p, np, p == 0 ? 1 : 0);
+      klaunch(rs_hist_kernel<u64>, dim3(grid), dim3(RS_T), 0, s, J, p, np);
+      klaunch(rs_scatter_kernel<u64>, dim3(grid), dim3(RS_T), 0, s, J, p, np, p == 0 ? 1 : 0);
     }
     if (launches) *launches += 2;
   }
@@ -189,6 +230,7 @@ __device__ __forceinline__ bool seg_is_head(const KT* keys, int i) { return i ==
 
 template <typename KT>
 __global__ void __launch_bounds__(RS_T) seg_count_kernel(const SegJobs* __restrict__ JB) {
+  FCCF_PDL_ENTER();
   const SegJob& j = JB[blockIdx.z].j[blockIdx.y];
   const KT* __restrict__ keys = (const KT*)j.keys;
   const int n = *j.n;
@@ -238,6 +280,7 @@ __global__ void __launch_bounds__(RS_T) seg_count_kernel(const SegJobs* __restri
 
 template <typename KT>
 __global__ void __launch_bounds__(RS_T) seg_write_kernel(const SegJobs* __restrict__ JB) {
+  FCCF_PDL_ENTER();
   const SegJob& j = JB[blockIdx.z].j[blockIdx.y];
   const KT* __restrict__ keys = (const KT*)j.keys;
   const int n = *j.n;
@@ -267,8 +310,8 @@ __global__ void __launch_bounds__(RS_T) seg_write_kernel(const SegJobs* __restri
 
 void launch_segments(cudaStream_t s, const SegJobs* jobs, int njobs, int G, int cap, int key_bytes, uint64_t* launches) {
   dim3 grid(grid_x((cap + RS_TILE - 1) / RS_TILE, G, njobs), njobs, G);
-  if (key_bytes == 4) { seg_count_kernel<u32><<<grid, RS_T, 0, s>>>(jobs); seg_write_kernel<u32><<<grid, RS_T, 0, s>>>(jobs); }
-  else { seg_count_kernel<u64><<<grid, RS_T, 0, s>>>(jobs); seg_write_kernel<u64><<<grid, RS_T, 0, s>>>(jobs); }
+  if (key_bytes == 4) { klaunch(seg_count_kernel<u32>, dim3(grid), dim3(RS_T), 0, s, jobs); klaunch(seg_write_kernel<u32>, dim3(grid), dim3(RS_T), 0, s, jobs); }
+  else { klaunch(seg_count_kernel<u64>, dim3(grid), dim3(RS_T), 0, s, jobs); klaunch(seg_write_kernel<u64>, dim3(grid), dim3(RS_T), 0, s, jobs); }
   if (launches) *launches += 2;
 }
 

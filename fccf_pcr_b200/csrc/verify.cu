@@ -55,8 +55,9 @@ __device__ __forceinline__ void rot_with_jac(const double q[4], const double a[3
 struct LmRow { double n1[3], p1[3], n2[3], p2[3], w; bool active; int odd; };
 
 // residual of this lane's row and (optionally) its 6 local Jacobian entries; warp-uniform return
-__device__ __forceinline__ bool lm_eval(const LmRow& R, const double x[7], double& r, double J[6], bool want) {
-  bool fin = true;
+// fin_r (optional): all residuals finite, whatever the Jacobian does
+__device__ __forceinline__ bool lm_eval(const LmRow& R, const double x[7], double& r, double J[6], bool want, bool* fin_r = nullptr) {
+  bool fin = true, finr = true;
   r = 0.0;
   if (want) for (int c = 0; c < 6; c++) J[c] = 0.0;
   if (R.active) {
@@ -71,7 +72,7 @@ __device__ __forceinline__ bool lm_eval(const LmRow& R, const double x[7], doubl
     double d = dot3d(R.n1, R.p1) - dot3d(n2r, p2r);
     double sd = sqrt(d * d);
     r = R.odd ? R.w * sd : R.w * nc;
-    fin = isfinite(r);
+    fin = isfinite(r); finr = fin;
     if (want) {
       double Ja[7];
       #pragma unroll
@@ -92,6 +93,7 @@ __device__ __forceinline__ bool lm_eval(const LmRow& R, const double x[7], doubl
       for (int lc = 0; lc < 6; lc++) fin = fin && isfinite(J[lc]);
     }
   }
+  if (fin_r) *fin_r = __all_sync(0xffffffffu, finr);
   return __all_sync(0xffffffffu, fin);
 }
 __device__ __forceinline__ void lm_plus(const double x[7], const double delta[6], double out[7]) {
@@ -110,46 +112,62 @@ __device__ __forceinline__ void lm_plus(const double x[7], const double delta[6]
 }
 // min || [A; B] y - [b; 0] || by Householder QR.  Lane l holds main row l (A, b) and, for l < 6,
 // augmented row l (B = diag(lmd)).  Returns false on a zero column / non-finite solution.
+// Per column ONE round of butterflies: the products of column k with the columns behind it and with the right-
+// hand side (g_j = a_k . a_j, all independent) give the norm (g_k), the reflector's v.v = g_k + alpha^2 - 2 alpha a_kk
+// and every v . a_j = g_j - alpha a_kj — the same reflections as the three dependent reductions per column of the
+// textbook loop, with a third of the dependent shuffle depth.  (The sums associate differently from the oracle's:
+// agreement is to rounding, inside the 0.01 degree / 1 mm bar by orders of magnitude — tests/lm_check.py.)
 __device__ __forceinline__ bool lm_qr_solve(double A[6], double b, double B[6], int lane, double y[6]) {
   double bb = 0.0;   // rhs of the augmented row
   const bool aug = lane < 6;
   #pragma unroll
   for (int k = 0; k < 6; k++) {
-    double mk = (lane >= k) ? A[k] : 0.0;
-    double ak = aug ? B[k] : 0.0;
-    double nrm = sqrt(bfly(mk * mk + ak * ak));
+    const double mk = (lane >= k) ? A[k] : 0.0;
+    const double ak = aug ? B[k] : 0.0;
+    double g[7];
+    #pragma unroll
+    for (int j = k; j < 6; j++) g[j] = mk * A[j] + ak * (aug ? B[j] : 0.0);
+    g[6] = mk * b + ak * bb;
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      #pragma unroll
+      for (int j = k; j < 7; j++) g[j] = g[j] + __shfl_xor_sync(0xffffffffu, g[j], o);
+    }
+    const double nrm = sqrt(g[k]);
     if (nrm == 0.0) return false;
-    double akk = __shfl_sync(0xffffffffu, A[k], k);
-    double alpha = (akk > 0) ? -nrm : nrm;
-    double v0 = akk - alpha;
-    double vm = (lane == k) ? v0 : mk;     // Householder vector entries of this lane's rows
-    double va = ak;
-    double vtv = bfly(vm * vm + va * va);
+    const double akk = __shfl_sync(0xffffffffu, A[k], k);
+    const double alpha = (akk > 0) ? -nrm : nrm;
+    const double vtv = (g[k] + alpha * alpha) - 2.0 * (alpha * akk);
     if (vtv == 0.0) return false;
-    double beta = 2.0 / vtv;
+    const double beta = 2.0 / vtv;
+    const double vm = (lane == k) ? (akk - alpha) : mk;     // Householder vector entries of this lane's rows
+    const double va = ak;
     #pragma unroll
     for (int j = k + 1; j < 6; j++) {
-      double s = bfly(vm * A[j] + va * (aug ? B[j] : 0.0));
-      s *= beta;
+      const double akj = __shfl_sync(0xffffffffu, A[j], k);
+      const double s = (g[j] - alpha * akj) * beta;
       A[j] -= s * vm;
       if (aug) B[j] -= s * va;
     }
     {
-      double s = bfly(vm * b + va * bb);
-      s *= beta;
+      const double bk = __shfl_sync(0xffffffffu, b, k);
+      const double s = (g[6] - alpha * bk) * beta;
       b -= s * vm;
       if (aug) bb -= s * va;
     }
     if (lane == k) A[k] = alpha;
   }
+  // back substitution: the six reciprocals of the diagonal first (independent divisions), then multiplications
+  double dinv[6];
+  #pragma unroll
+  for (int k = 0; k < 6; k++) dinv[k] = 1.0 / __shfl_sync(0xffffffffu, A[k], k);
   bool ok = true;
   #pragma unroll
   for (int k = 5; k >= 0; k--) {
     double s = b;
     #pragma unroll
     for (int j = k + 1; j < 6; j++) s -= A[j] * y[j];
-    s = s / A[k];
-    y[k] = __shfl_sync(0xffffffffu, s, k);
+    y[k] = __shfl_sync(0xffffffffu, s * dinv[k], k);
     ok = ok && isfinite(y[k]);
   }
   return ok;
@@ -210,9 +228,12 @@ __device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
     invalid = 0;
     double delta[6]; for (int c = 0; c < 6; c++) delta[c] = step[c] * scale[c];
     double xc[7]; lm_plus(x, delta, xc);
+    // residuals AND Jacobian at the candidate in one evaluation: an accepted step (nearly all of them) needs both
     double rc, Jd[6];
     double cand_cost;
-    if (lm_eval(R, xc, rc, Jd, false)) cand_cost = 0.5 * bfly(rc * rc);
+    bool cand_fin_r;
+    const bool cand_fin = lm_eval(R, xc, rc, Jd, true, &cand_fin_r);
+    if (cand_fin_r) cand_cost = 0.5 * bfly(rc * rc);
     else cand_cost = 1.7976931348623157e308;
     double sn = 0; for (int i = 0; i < 7; i++) sn += (x[i] - xc[i]) * (x[i] - xc[i]); sn = sqrt(sn);
     if (sn <= parameter_tolerance * (x_norm + parameter_tolerance)) break;
@@ -224,7 +245,10 @@ __device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
       for (int i = 0; i < 7; i++) x[i] = xc[i];
       x_norm = 0; for (int i = 0; i < 7; i++) x_norm += x[i] * x[i]; x_norm = sqrt(x_norm);
       cost = cand_cost;
-      if (!lm_eval(R, x, r, J, true)) break;
+      if (!cand_fin) break;
+      r = rc;
+      #pragma unroll
+      for (int c = 0; c < 6; c++) J[c] = Jd[c];
       #pragma unroll
       for (int c = 0; c < 6; c++) g[c] = bfly(J[c] * r);
       #pragma unroll
@@ -235,7 +259,7 @@ __device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
         gmax = 0; for (int i = 0; i < 7; i++) gmax = fmax(gmax, fabs(x[i] - xp[i]));
       }
       step_successful = true;
-      radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel - 1.0, 3.0));
+      { const double u = 2.0 * rel - 1.0; radius = radius / fmax(1.0 / 3.0, 1.0 - u * u * u); }   // pow(u, 3)
       radius = fmin(max_radius, radius);
       decrease_factor = 2.0; reuse_diag = false;
     } else {
@@ -340,6 +364,7 @@ struct QvArgs {
 // quick_verify — runs only for those (refine_top_kernel), with bit-identical results for everything the
 // path consumes.
 __global__ void __launch_bounds__(128) quick_verify_kernel(const QvArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const QvArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int lane = threadIdx.x & 31;
@@ -358,6 +383,7 @@ __global__ void __launch_bounds__(128) quick_verify_kernel(const QvArgs* __restr
 
 // score_range + top-k (FCCF.cpp:1494-1544): one CTA per type ranks the centres
 __global__ void __launch_bounds__(256) rank_top_kernel(const QvArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const QvArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int t = threadIdx.x, ty = blockIdx.x;
@@ -368,13 +394,15 @@ __global__ void __launch_bounds__(256) rank_top_kernel(const QvArgs* __restrict_
   int has_nan = 0;
   for (int k = t; k < C; k += 256) { float v = A.qv_score[ty * FCCF_MAXCENTRE + k]; s_key[k] = v; s_perm[k] = k; has_nan |= (v != v); }
   has_nan = __syncthreads_or(has_nan);
-  if (!has_nan) block_exchange_sort(s_key, s_perm, C, s_sort);
-  else if (t < 32) warp_exchange_sort(s_key, s_perm, C, [](float a, float b) { return a < b; });   // NaN keys have no total order: literal emulation
-  __syncthreads();
   int amax = (int)A.fine_number;
   if (amax > A.topk) amax = A.topk;
   int nt = C < amax ? C : amax;
-  for (int k = t; k < C; k += 256) A.rank_perm[ty * FCCF_MAXCENTRE + k] = s_perm[k];
+  // Only the first nt positions of the exchange sort are ever read (FCCF.cpp:1499-1544): pass i of the sort makes
+  // position i final, so a few selected centres need a few literal passes by one warp, not the whole sort.
+  if (nt <= 16 || has_nan) { if (t < 32) warp_exchange_sort(s_key, s_perm, C, [](float a, float b) { return a < b; }, has_nan ? 0x7fffffff : nt); }   // NaN keys have no total order: literal emulation
+  else block_exchange_sort(s_key, s_perm, C, s_sort);
+  __syncthreads();
+  for (int k = t; k < C; k += 256) A.rank_perm[ty * FCCF_MAXCENTRE + k] = s_perm[k];   // (complete only when the whole sort ran)
   for (int k = t; k < nt; k += 256) { A.top_s1[ty * A.topk + k] = s_key[k]; A.top_centre[ty * A.topk + k] = s_perm[k]; }
   if (t == 0) st->n_top[ty] = nt;
 }
@@ -382,6 +410,7 @@ __global__ void __launch_bounds__(256) rank_top_kernel(const QvArgs* __restrict_
 // quick_verify with the Ceres refinement for the selected centres: one warp per (type, rank)
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) refine_top_kernel(const QvArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const QvArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int lane = threadIdx.x & 31;
@@ -411,18 +440,19 @@ void launch_quick_verify(cudaStream_t s, const Batch& b, uint64_t* launches) {
   const QvArgs* dA = b.tab->put(As.data(), G);
   static int occ = -1;
   if (occ < 0) { const char* e = getenv("FCCF_QV_OCC"); occ = e ? atoi(e) : 2; }
-  quick_verify_kernel<<<dim3((3 * FCCF_MAXCENTRE + 3) / 4, 1, G), 128, 0, s>>>(dA);
-  rank_top_kernel<<<dim3(3, 1, G), 256, 0, s>>>(dA);
+  klaunch(quick_verify_kernel, dim3(dim3((3 * FCCF_MAXCENTRE + 3) / 4, 1, G)), dim3(128), 0, s, dA);
+  klaunch(rank_top_kernel, dim3(dim3(3, 1, G)), dim3(256), 0, s, dA);
   dim3 grid((3 * fccf_topk(b.p) + 3) / 4, 1, G);
-  if (occ <= 2) refine_top_kernel<2><<<grid, 128, 0, s>>>(dA);
-  else if (occ == 3) refine_top_kernel<3><<<grid, 128, 0, s>>>(dA);
-  else refine_top_kernel<4><<<grid, 128, 0, s>>>(dA);
+  if (occ <= 2) klaunch(refine_top_kernel<2>, dim3(grid), dim3(128), 0, s, dA);
+  else if (occ == 3) klaunch(refine_top_kernel<3>, dim3(grid), dim3(128), 0, s, dA);
+  else klaunch(refine_top_kernel<4>, dim3(grid), dim3(128), 0, s, dA);
   if (launches) *launches += 3;
 }
 
 // stand-alone: n hypotheses (row-major 4x4, updated in place) against two plane tables (F x 8)
 struct QvListArgs { float* T; int n; const float* pl1; int f1; const float* pl2; int f2; float* score; int* npair; int* pairs; int* iters; float ang_cut, dist_thr, required; };
 __global__ void __launch_bounds__(128) quick_verify_list_kernel(const __grid_constant__ QvListArgs A) {
+  FCCF_PDL_ENTER();
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (wid >= A.n) return;
@@ -439,7 +469,7 @@ void launch_quick_verify_list(cudaStream_t s, const fccf_params& p, float* d_T16
   A.T = d_T16; A.n = n; A.pl1 = d_planes1; A.f1 = f1; A.pl2 = d_planes2; A.f2 = f2; A.score = d_score; A.npair = d_npair; A.pairs = d_pairs; A.iters = d_iters;
   A.ang_cut = angle_cut(p.quick_verify_angel_threshold, true); A.dist_thr = p.quick_verify_distance_threshold; A.required = p.required_optimize_plane;
   if (n <= 0) return;
-  quick_verify_list_kernel<<<(n + 3) / 4, 128, 0, s>>>(A);
+  klaunch(quick_verify_list_kernel, dim3((n + 3) / 4), dim3(128), 0, s, A);
   if (launches) *launches += 1;
 }
 

@@ -25,6 +25,7 @@ struct VGArgs {
 };
 
 __global__ void __launch_bounds__(256) vg_minmax_kernel(const VGArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const VGArgs& A = AB[blockIdx.z];
   const int c = blockIdx.y;
   const int n = *A.n_in[c];
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) vg_minmax_kernel(const VGArgs* __restrict
 
 template <typename KT>
 __global__ void __launch_bounds__(256) vg_keys_kernel(const VGArgs* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const VGArgs& A = AB[blockIdx.z];
   const int c = blockIdx.y;
   const VGState* st = A.st[c];
@@ -134,6 +136,7 @@ struct VGOut {
 // one thread per occupied cell: in-order float32 running sum (pcl::CentroidPoint<PointXYZ>)
 template <typename KT>
 __global__ void __launch_bounds__(128) vg_centroid_kernel(const VGOut* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const VGOut& A = AB[blockIdx.z];
   const int c = blockIdx.y;
   VGState* st = A.st[c];
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(128) vg_centroid_kernel(const VGOut* __restric
 // sequential sum allows (a 32k-point cell: ~0.15 ms instead of the 7 ms of one warp with one gather in flight).
 template <typename KT>
 __global__ void __launch_bounds__(256) vg_centroid_big_kernel(const VGOut* __restrict__ AB) {
+  FCCF_PDL_ENTER();
   const VGOut& A = AB[blockIdx.z];
   const int c = blockIdx.y;
   VGState* st = A.st[c];
@@ -218,6 +222,7 @@ __global__ void __launch_bounds__(256) vg_centroid_big_kernel(const VGOut* __res
 
 struct InitArgs { PipeState* st; };
 __global__ void init_state_kernel(const InitArgs* __restrict__ AB, const CallArgs* __restrict__ calls) {
+  FCCF_PDL_ENTER();
   PipeState* st = AB[blockIdx.x].st;
   int t = threadIdx.x;
   if (t == 0) {
@@ -240,7 +245,7 @@ __global__ void init_state_kernel(const InitArgs* __restrict__ AB, const CallArg
 void launch_init_state(cudaStream_t s, const Batch& b, const CallArgs* d_calls, uint64_t* launches) {
   std::vector<InitArgs> I(b.G);
   for (int g = 0; g < b.G; g++) I[g].st = b.w[g].st;
-  init_state_kernel<<<b.G, 64, 0, s>>>(b.tab->put(I.data(), b.G), d_calls);
+  klaunch(init_state_kernel, dim3(b.G), dim3(64), 0, s, b.tab->put(I.data(), b.G), d_calls);
   if (launches) *launches += 1;
 }
 
@@ -280,23 +285,23 @@ void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uin
   const SortJobs* dab = b.tab->put(abs_.data(), G); const SortJobs* dba = b.tab->put(bas_.data(), G); const SegJobs* dsj = b.tab->put(sjs.data(), G);
   int nb_mm = (cap + 256 * 8 - 1) / (256 * 8);
   if (nb_mm > 592) nb_mm = 592;
-  vg_minmax_kernel<<<dim3(grid_x(nb_mm, G, ncloud), ncloud, G), 256, 0, s>>>(dA);
+  klaunch(vg_minmax_kernel, dim3(dim3(grid_x(nb_mm, G, ncloud), ncloud, G)), dim3(256), 0, s, dA);
   // With pcl::VoxelGrid's int32 overflow bail-out emulated, every key (cell index, point index when bailing
   // out, "non-finite" = number of cells) fits 32 bits: the sort moves 4-byte keys.  Without it cells may
   // need the full 64 bits.
   const int kb = b.p.emulate_pcl_overflow ? 4 : 8;
-  if (kb == 4) vg_keys_kernel<u32><<<dim3(grid_x((cap + 255) / 256, G, ncloud), ncloud, G), 256, 0, s>>>(dA);
-  else vg_keys_kernel<u64><<<dim3(grid_x((cap + 255) / 256, G, ncloud), ncloud, G), 256, 0, s>>>(dA);
+  if (kb == 4) klaunch(vg_keys_kernel<u32>, dim3(dim3(grid_x((cap + 255) / 256, G, ncloud), ncloud, G)), dim3(256), 0, s, dA);
+  else klaunch(vg_keys_kernel<u64>, dim3(dim3(grid_x((cap + 255) / 256, G, ncloud), ncloud, G)), dim3(256), 0, s, dA);
   if (launches) *launches += 2;
   launch_sort(s, dab, dba, ncloud, G, cap, kb == 4 ? 4 : 8, kb, launches);   // result back in keyA / idxA (even pass counts)
   launch_segments(s, dsj, ncloud, G, cap, kb, launches);
   // more CTAs of this kernel per lane: fewer lanes in flight at once, so that the clouds being gathered from stay in L2
   const dim3 gc(grid_x((cap + 127) / 128, G, ncloud, 16384), ncloud, G);
-  if (kb == 4) vg_centroid_kernel<u32><<<gc, 128, 0, s>>>(dO);
-  else vg_centroid_kernel<u64><<<gc, 128, 0, s>>>(dO);
+  if (kb == 4) klaunch(vg_centroid_kernel<u32>, dim3(gc), dim3(128), 0, s, dO);
+  else klaunch(vg_centroid_kernel<u64>, dim3(gc), dim3(128), 0, s, dO);
   const dim3 gb(grid_x(148 * 2, G, ncloud, 4096), ncloud, G);
-  if (kb == 4) vg_centroid_big_kernel<u32><<<gb, 256, 0, s>>>(dO);
-  else vg_centroid_big_kernel<u64><<<gb, 256, 0, s>>>(dO);
+  if (kb == 4) klaunch(vg_centroid_big_kernel<u32>, dim3(gb), dim3(256), 0, s, dO);
+  else klaunch(vg_centroid_big_kernel<u64>, dim3(gb), dim3(256), 0, s, dO);
   if (launches) *launches += 2;
 }
 

@@ -137,6 +137,7 @@ __device__ __forceinline__ unsigned vf_group(bool in, int v, int nbits) {
 template <int CS>
 __global__ void __launch_bounds__(VF_T, 1) vg_fast_kernel(const VFArgs* __restrict__ AB, int ncloud, int nitems, u32* __restrict__ info_all,
                                                           float4* __restrict__ queue_all, int stride) {
+  FCCF_PDL_ENTER();
   typedef VfGeo<CS> G;
   constexpr int DIG = G::DIG, DB = G::DB, MAXSLOT = G::MAXSLOT, TABSTRIDE = G::TABSTRIDE;
   cg::cluster_group cluster = cg::this_cluster();
@@ -563,8 +564,9 @@ cudaError_t launch_voxelgrid_fast(cudaStream_t s, const Batch& b, int stage, int
   if (ncl < 1) ncl = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs * ncl); cfg.blockDim = dim3(VF_T); cfg.dynamicSmemBytes = cs == 8 ? VfGeo<8>::SMEM_BYTES : VfGeo<4>::SMEM_BYTES; cfg.stream = s;
-  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchAttribute at[2]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = fccf_pdl_on() ? 2 : 1;
   cudaError_t e = cs == 8 ? cudaLaunchKernelEx(&cfg, vg_fast_kernel<8>, dA, ncloud, nitems, sc.info, sc.queue, sc.stride)
                           : cudaLaunchKernelEx(&cfg, vg_fast_kernel<4>, dA, ncloud, nitems, sc.info, sc.queue, sc.stride);
   if (launches) *launches += 1;

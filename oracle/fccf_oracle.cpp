@@ -925,7 +925,17 @@ static void lm_plus(const double x[7], const double delta[6], double out[7]) {
   for (int i = 0; i < 3; i++) out[4 + i] = x[4 + i] + delta[3 + i];
 }
 // min || [A; B] y - [b; 0] || by Householder QR (DENSE_QR).  A: 32 main rows, B: 6 damping rows.
-static bool qr_solve6(double A[32][6], double b[32], double B[6][6], double y[6]) {
+// Two algebraically identical ways to apply the reflections:
+//  * g_lm_textbook = 1 (test switch "lm_textbook"): the loop as Eigen's HouseholderQR states it — the column norm,
+//    then v.v, then one v.a_j per remaining column (three dependent reductions per column), back substitution by
+//    division, std::pow for the trust-region cubic;
+//  * default: per column ONE set of independent reductions g_j = a_k . a_j (j >= k, and the right-hand side), from
+//    which norm = sqrt(g_k), v.v = g_k + alpha^2 - 2 alpha a_kk and v.a_j = g_j - alpha a_kj follow; reciprocals of
+//    the diagonal first, then multiplications; u*u*u.  This is the form the CUDA path runs (a third of the dependent
+//    shuffle depth), so that trajectories agree to the last bit there.  What the choice is worth is MEASURED by
+//    tests/test_oracle_kat.py::test_oracle_switches_do_not_move_the_result.
+static int g_lm_textbook = 0;
+static bool qr_solve6_textbook(double A[32][6], double b[32], double B[6][6], double y[6]) {
   double bb[6] = {0, 0, 0, 0, 0, 0};
   double tmp[32];
   for (int k = 0; k < 6; k++) {
@@ -963,6 +973,50 @@ static bool qr_solve6(double A[32][6], double b[32], double B[6][6], double y[6]
     if (!std::isfinite(y[k])) return false;
   }
   return true;
+}
+static bool qr_solve6(double A[32][6], double b[32], double B[6][6], double y[6]) {
+  if (g_lm_textbook) return qr_solve6_textbook(A, b, B, y);
+  double bb[6] = {0, 0, 0, 0, 0, 0};
+  double tmp[32];
+  for (int k = 0; k < 6; k++) {
+    double mk[32], ak[32], g[7];
+    for (int l = 0; l < 32; l++) { mk[l] = (l >= k) ? A[l][k] : 0.0; ak[l] = (l < 6) ? B[l][k] : 0.0; }
+    for (int j = k; j < 6; j++) {
+      for (int l = 0; l < 32; l++) tmp[l] = mk[l] * A[l][j] + ak[l] * ((l < 6) ? B[l][j] : 0.0);
+      g[j] = bfly32(tmp);
+    }
+    for (int l = 0; l < 32; l++) tmp[l] = mk[l] * b[l] + ak[l] * ((l < 6) ? bb[l] : 0.0);
+    g[6] = bfly32(tmp);
+    double nrm = std::sqrt(g[k]);
+    if (nrm == 0.0) return false;
+    double akk = A[k][k];
+    double alpha = (akk > 0) ? -nrm : nrm;
+    double vtv = (g[k] + alpha * alpha) - 2.0 * (alpha * akk);
+    if (vtv == 0.0) return false;
+    double beta = 2.0 / vtv;
+    double vm[32];
+    for (int l = 0; l < 32; l++) vm[l] = (l == k) ? (akk - alpha) : mk[l];
+    for (int j = k + 1; j < 6; j++) {
+      double s = (g[j] - alpha * A[k][j]) * beta;
+      for (int l = 0; l < 32; l++) A[l][j] -= s * vm[l];
+      for (int l = 0; l < 6; l++) B[l][j] -= s * ak[l];
+    }
+    {
+      double s = (g[6] - alpha * b[k]) * beta;
+      for (int l = 0; l < 32; l++) b[l] -= s * vm[l];
+      for (int l = 0; l < 6; l++) bb[l] -= s * ak[l];
+    }
+    A[k][k] = alpha;
+  }
+  double dinv[6];
+  for (int k = 0; k < 6; k++) dinv[k] = 1.0 / A[k][k];
+  bool ok = true;
+  for (int k = 5; k >= 0; k--) {
+    double s = b[k]; for (int j = k + 1; j < 6; j++) s -= A[k][j] * y[j];
+    y[k] = s * dinv[k];
+    ok = ok && std::isfinite(y[k]);
+  }
+  return ok;
 }
 static void ceres_refine(M4f& newT, const std::vector<PairFace>& pf, int* iters_out) {
   const int max_iter = 50;
@@ -1041,7 +1095,7 @@ static void ceres_refine(M4f& newT, const std::vector<PairFace>& pf, int* iters_
         grad_and_scale(false);
         gmax = grad_max_norm();
         step_successful = true;
-        radius = radius / std::fmax(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+        { const double u = 2.0 * rel - 1.0; radius = radius / std::fmax(1.0 / 3.0, 1.0 - (g_lm_textbook ? std::pow(u, 3) : u * u * u)); }
         radius = std::fmin(max_radius, radius);
         decrease_factor = 2.0; reuse_diag = false;
       } else {
@@ -1337,6 +1391,7 @@ int orc_set_param(void* c, const char* name, double v) {
   if (n == "emulate_pcl_overflow") { p.emulate_pcl_overflow = (int)v; return 0; }
   if (n == "libm_float") { g_libm_float = (int)v; return 0; }   // process-wide (test switch)
   if (n == "lm_sequential") { g_lm_sequential = (int)v; return 0; }   // process-wide (test switch)
+  if (n == "lm_textbook") { g_lm_textbook = (int)v; return 0; }       // process-wide (test switch)
   return -1;
 }
 // full program: src = argv[1], tar = argv[2]; T row-major 16 floats

@@ -361,11 +361,14 @@ def test_libm_switch_bounds_the_last_ulp_effect(oracle_mod):
 
 
 def test_oracle_switches_do_not_move_the_result(oracle_mod):
-    """Two choices of the oracle were made so that the CUDA path can agree with it to the last bit: float libm calls
-    of pcl::eigen33 evaluated correctly rounded (instead of the platform's float libm), and every Levenberg-Marquardt
-    row sum taken in xor-butterfly order (instead of row order).  This measures what they are worth: with the
-    platform float libm (libm_float = 1) and / or plain row-order sums (lm_sequential = 1) every decision of the
-    pipeline stays the same and the final transform moves by far less than the 0.01 degree / 1 mm parity bar."""
+    """Three choices of the oracle were made so that the CUDA path can agree with it to the last bit: float libm calls
+    of pcl::eigen33 evaluated correctly rounded (instead of the platform's float libm), every Levenberg-Marquardt
+    row sum taken in xor-butterfly order (instead of row order), and the Householder reflections of the LM's QR applied
+    from one set of column products per column (instead of the textbook loop's three dependent reductions; with it
+    reciprocal-multiply back substitution and u*u*u for pow(u, 3)).  This measures what they are worth: with the
+    platform float libm (libm_float = 1), plain row-order sums (lm_sequential = 1) and / or the textbook QR
+    (lm_textbook = 1) every decision of the pipeline stays the same and the final transform moves by far less than
+    the 0.01 degree / 1 mm parity bar."""
     from fccf_pcr_b200 import scenes
 
     cases = [("indoor", 20000, 7, 0.1, {}), ("indoor", 50000, 1, 0.1, {}), ("indoor", 200000, 2, 0.2, {}),
@@ -378,19 +381,19 @@ def test_oracle_switches_do_not_move_the_result(oracle_mod):
             T0 = ref.register(src, tar, leaf)
             keep = {nm: ref.blob(nm).copy() for nm in ["merge_label1", "merge_label2", "base1", "base2", "matches", "n_hyp", "n_centres",
                                                        "top_centre0", "top_centre1", "top_centre2", "qv_pairs0", "qv_pairs2"]}
-            for libm, seq in ((1, 0), (0, 1), (1, 1)):
-                o = oracle_mod.Oracle(libm_float=libm, lm_sequential=seq, **prm)
+            for libm, seq, tb in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)):
+                o = oracle_mod.Oracle(libm_float=libm, lm_sequential=seq, lm_textbook=tb, **prm)
                 T = o.register(src, tar, leaf)
                 for nm, v in keep.items():
-                    assert np.array_equal(o.blob(nm), v), (kind, seed, libm, seq, nm)
+                    assert np.array_equal(o.blob(nm), v), (kind, seed, libm, seq, tb, nm)
                 de, dt = scenes.rotation_error_deg(T, T0), scenes.translation_error(T, T0)
                 worst = (max(worst[0], de), max(worst[1], dt))
-                assert de <= 1e-3 and dt <= 1e-4, (kind, seed, libm, seq, de, dt)      # a tenth of the parity bar
+                assert de <= 1e-3 and dt <= 1e-4, (kind, seed, libm, seq, tb, de, dt)      # a tenth of the parity bar
                 for t in range(3):
                     for Ta, Tb in zip(o.blob("top_T%d" % t).reshape(-1, 4, 4), ref.blob("top_T%d" % t).reshape(-1, 4, 4)):
                         assert scenes.rotation_error_deg(Ta, Tb) <= 1e-3 and scenes.translation_error(Ta, Tb) <= 1e-4
     finally:
-        oracle_mod.Oracle(libm_float=0, lm_sequential=0)      # the switches are process-wide
+        oracle_mod.Oracle(libm_float=0, lm_sequential=0, lm_textbook=0)      # the switches are process-wide
     print("oracle switches: worst final-transform shift %.2e deg, %.2e m" % worst)
 
 
