@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) score_keys_kernel(const ScArgs* __restric
 //   mode  0: dense cell -> id table + per-warp 16-bit counters in shared memory
 //         1: hash + per-warp 16-bit counters in shared memory
 //         2: hash and 32-bit counters in global memory (score_kernel)
-struct ScPlan { int cap, mode, row_words, nocc_pad, tab_bytes; unsigned cells; };
+struct ScPlan { int cap, mode, row_words, nocc_pad, tab_bytes; unsigned cells; int fast, s2_off; };   // fast: 32-bit counters + the moving cloud staged as float4 at s2_off
 __device__ __forceinline__ ScPlan sc_plan(const ScoreState* ss, int cap_hash) {
   ScPlan P;
   const int nocc = ss->n_occ;
@@ -162,6 +162,13 @@ __device__ __forceinline__ ScPlan sc_plan(const ScoreState* ss, int cap_hash) {
   P.mode = 2; P.tab_bytes = 0;
   if (small && P.cells <= SC_DENSE_CELLS && fixed + ((2 * (size_t)P.cells + 15) & ~(size_t)15) <= SC_DYN_BYTES) { P.mode = 0; P.tab_bytes = (int)((2 * P.cells + 15) & ~15u); }
   else if (small && fixed + (size_t)6 * cap <= SC_DYN_BYTES) { P.mode = 1; P.tab_bytes = 6 * cap; }
+  // room for the fast sweep?  one 32-bit counter per voxel (no half-word select / shift in front of the atomic)
+  // and the moving cloud as float4 in shared memory (one LDS.128 per point instead of three strided loads)
+  P.fast = 0; P.s2_off = 0;
+  if (P.mode != 2) {
+    const size_t wide = (size_t)P.tab_bytes + (size_t)4 * P.nocc_pad + (size_t)SC_WARPS * 4 * P.nocc_pad;
+    if (wide + (size_t)16 * ss->n2 <= SC_DYN_BYTES) { P.fast = 1; P.s2_off = (int)wide; }
+  }
   return P;
 }
 
@@ -273,7 +280,71 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_warp_kernel(const ScArgs*
   const int shift = 32 - (31 - __clz(P.cap));
   const double rr = POW2 ? 1.0 / (double)A.res : (double)A.res;
   const float* __restrict__ s2 = A.s2;
-  const float inv_tot = 0.f; (void)inv_tot;
+  // ---- fast sweep: power-of-two lattice with 1/res >= 1 and room in shared memory (ScPlan::fast) ----
+  // The 1/res scale is folded into the transform rows and the box (exact: a power of two commutes with every
+  // rounding), the moving cloud is read as one float4 per point out of shared memory, and every voxel has a
+  // 32-bit counter.  Same counts, same summation order of the score.
+  if (POW2 && P.fast && A.res <= 1.0f) {
+    const float rf = 1.0f / A.res;
+    float4* s2v = (float4*)(sc_dyn + P.s2_off);
+    for (int i = t; i < n2; i += SC_THREADS) s2v[i] = make_float4(s2[3 * i], s2[3 * i + 1], s2[3 * i + 2], 0.f);
+    __syncthreads();
+    u32* roww = (u32*)(s_cnt + P.nocc_pad) + (size_t)warp * P.nocc_pad;
+    const float slo0 = lo0 * rf, slo1 = lo1 * rf, slo2 = lo2 * rf, shi0 = hi0 * rf, shi1 = hi1 * rf, shi2 = hi2 * rf;
+    const double sm0 = m0 * rr, sm1 = m1 * rr, sm2 = m2 * rr;
+    for (int h = blockIdx.x * SC_WARPS + warp; h < A.n_hyp; h += gridDim.x * SC_WARPS) {
+      if (A.n_top) { int ty = h / A.topk, kk = h - ty * A.topk; if (kk >= A.n_top[ty]) continue; }
+      const float4* Tp = (const float4*)(A.T + (size_t)h * 16);
+      float4 r0 = __ldg(Tp), r1 = __ldg(Tp + 1), r2 = __ldg(Tp + 2);
+      r0.x *= rf; r0.y *= rf; r0.z *= rf; r0.w *= rf; r1.x *= rf; r1.y *= rf; r1.z *= rf; r1.w *= rf; r2.x *= rf; r2.y *= rf; r2.z *= rf; r2.w *= rf;
+      for (int i = lane; i < P.nocc_pad; i += 32) roww[i] = 0u;
+      __syncwarp();
+#pragma unroll 4
+      for (int i = lane; i < n2; i += 32) {
+        const float4 p = s2v[i];
+        const float qx = p.x * r0.x + (p.y * r0.y + (p.z * r0.z + r0.w));
+        const float qy = p.x * r1.x + (p.y * r1.y + (p.z * r1.z + r1.w));
+        const float qz = p.x * r2.x + (p.y * r2.y + (p.z * r2.z + r2.w));
+        if (qx >= slo0 && qx < shi0 && qy >= slo1 && qy < shi1 && qz >= slo2 && qz < shi2) {
+          const u32 cx = (u32)(__double2loint(__dadd_rd((double)qx - sm0, 6755399441055744.0)) - l0);
+          const u32 cy = (u32)(__double2loint(__dadd_rd((double)qy - sm1, 6755399441055744.0)) - l1);
+          const u32 cz = (u32)(__double2loint(__dadd_rd((double)qz - sm2, 6755399441055744.0)) - l2);
+          if (cx < dx && cy < dy && cz < dz) {
+            const u32 key = (cx * dy + cy) * dz + cz;
+            u32 id = 0xffffu;
+            if (mode == 0) id = tab16[key];
+            else {
+              unsigned hh = (sc_hash32(key) >> shift) & mask;
+              while (true) {
+                u32 k = hkey[hh];
+                if (k == key) { id = hid16[hh]; break; }
+                if (k == SC_EMPTY32) break;
+                hh = (hh + 1) & mask;
+              }
+            }
+            if (id != 0xffffu) atomicAdd(&roww[id], 1u);
+          }
+        }
+      }
+      __syncwarp();
+      float part = 0.f;
+      for (int w = lane; w < P.row_words; w += 32) {      // the order of the half-word rows: voxels 2w, 2w+1 per step
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int tt = (int)roww[2 * w + e];
+          if (tt > 0) {
+            float fs = (float)s_cnt[2 * w + e], ft = (float)tt;
+            float mn = fs < ft ? fs : ft, mx = fs > ft ? fs : ft;
+            part = part + (fs + ft) * (mn / mx);
+          }
+        }
+      }
+      for (int o = 16; o; o >>= 1) part = part + __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) A.scores[h] = part / (float)(n1 + n2);
+      __syncwarp();
+    }
+    return;
+  }
   for (int h = blockIdx.x * SC_WARPS + warp; h < A.n_hyp; h += gridDim.x * SC_WARPS) {
     if (A.n_top) { int ty = h / A.topk, kk = h - ty * A.topk; if (kk >= A.n_top[ty]) continue; }
     const float4* Tp = (const float4*)(A.T + (size_t)h * 16);
