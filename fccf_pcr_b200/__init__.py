@@ -40,7 +40,7 @@ class Timing(C.Structure):
 
 
 EXPORTS = [
-    "fccf_default_params", "fccf_create", "fccf_destroy", "fccf_last_error", "fccf_set_params", "fccf_register",
+    "fccf_default_params", "fccf_create", "fccf_destroy", "fccf_last_error", "fccf_set_params", "fccf_set_stage_timing", "fccf_register",
     "fccf_register_device", "fccf_register_batch", "fccf_voxelgrid", "fccf_extract_planes", "fccf_score_hypotheses",
     "fccf_score_hypotheses_bench", "fccf_score_counts", "fccf_quick_verify", "fccf_debug_blob", "fccf_launch_count",
     "fccf_stream_handle", "fccf_score_best", "fccf_register_batch_device", "fccf_register_batch_multi", "fccf_score_sharded",
@@ -75,6 +75,7 @@ def lib():
         L.fccf_last_error.argtypes = [vp]
         L.fccf_last_error.restype = C.c_char_p
         L.fccf_set_params.argtypes = [vp, C.POINTER(Params)]
+        L.fccf_set_stage_timing.argtypes = [vp, C.c_int]
         L.fccf_register.argtypes = [vp, fp, C.c_size_t, fp, C.c_size_t, C.c_float, fp, C.POINTER(Timing)]
         L.fccf_register_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_float, fp, C.POINTER(Timing)]
         L.fccf_register_batch.argtypes = [vp, C.c_int, C.POINTER(fp), C.POINTER(C.c_size_t), C.POINTER(fp), C.POINTER(C.c_size_t), C.c_float, fp, C.POINTER(Timing)]
@@ -183,6 +184,10 @@ class Context:
             raise FccfError("fccf_create failed: no usable CUDA device (libfccf has no CPU fallback)")
         self.h = C.c_void_p(h)
         self.timing = Timing()
+
+    def set_stage_timing(self, on):
+        """Per-stage device times in timing.stage_ms[1..6] (six more event nodes per captured sequence)."""
+        self._check(self.L.fccf_set_stage_timing(self.h, 1 if on else 0))
 
     def close(self):
         if getattr(self, "h", None):

@@ -78,6 +78,7 @@ struct Group {
   bool busy = false, had_h2d = false;
   int G = 0;                     // lanes of the sequence in flight
   bool fast = false;             // the sequence in flight uses the cluster VoxelGrid (voxelgrid_fast.cu)
+  bool stage_timed = false;      // the sequence in flight records the per-stage events
   float leaf = 0.f;
   VgFastScratch vf;              // its per-cluster scratch (L2-resident)
   size_t last_h2d = 0;
@@ -99,6 +100,7 @@ struct fccf_ctx {
   float fast_miss_leaf = 0.f; int fast_miss_ttl = 0;
   uint64_t fast_runs = 0, fast_misses = 0;
   uint64_t params_epoch = 1;
+  bool stage_timing = false;     // per-stage timing events inside the captured sequences (fccf_set_stage_timing)
   int cap_hyp = 1 << 18;
   bool have_run = false;
   float leaf = 0.f;
@@ -351,6 +353,8 @@ fccf_ctx* fccf_create(int device, const fccf_params* params) {
   ctx->p = p0;
   if (ctx->p.batch_lanes > 0) ctx->max_lanes = ctx->p.batch_lanes > 1024 ? 1024 : ctx->p.batch_lanes;
   if (const char* e = getenv("FCCF_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
+  if (const char* e = getenv("FCCF_STAGE_EVENTS")) ctx->stage_timing = (e[0] == '1');
+  sort_init_attributes();
   score_init_attributes();
   cluster_init_attributes();
   ctx->vg_fast = vg_fast_init() > 0;
@@ -392,6 +396,11 @@ int fccf_set_params(fccf_ctx* ctx, const fccf_params* params) {
   int lanes = ctx->p.batch_lanes;
   ctx->p = *params; ctx->p.batch_lanes = lanes;   // the lane count is fixed at creation
   ctx->params_epoch++;                            // captured graphs hold the old values: re-capture lazily
+  return FCCF_OK;
+}
+int fccf_set_stage_timing(fccf_ctx* ctx, int on) {
+  if (!ctx) return FCCF_ERR_ARG;
+  if (ctx->stage_timing != (on != 0)) { ctx->stage_timing = (on != 0); ctx->params_epoch++; }   // the events are nodes of the captured sequences
   return FCCF_OK;
 }
 // library-level integers for tools (not part of include/fccf.h)
@@ -480,7 +489,8 @@ static int check_status(fccf_ctx* ctx, int st) {
 static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_t* launches, bool capturing, bool fast) {
   cudaStream_t s = g->stream;
   // inside a capture a plain cudaEventRecord is only a dependency; the External flag makes a timing node
-  auto rec = [&](cudaEvent_t e) { return capturing ? cudaEventRecordWithFlags(e, s, cudaEventRecordExternal) : cudaEventRecord(e, s); };
+  const bool stage_events = ctx->stage_timing;
+  auto rec = [&](cudaEvent_t e) { if (!stage_events && e != g->ev[2] && e != g->ev[3]) return cudaSuccess; return capturing ? cudaEventRecordWithFlags(e, s, cudaEventRecordExternal) : cudaEventRecord(e, s); };
   std::vector<Work> ws;
   Batch b = make_batch(ctx, g, G, ws, tab);
   if (capturing) { b.side = g->stream2; b.side_fork = g->fork2; b.side_join = g->join2; }
@@ -614,7 +624,7 @@ static int group_enqueue(fccf_ctx* ctx, Group* g, int G, int pair0, const float*
   for (int l = 0; l < G; l++) nmax = std::max(nmax, std::max(n_src[l], n_tar[l]));
   bool fast = ctx->vg_fast && g->vf.ncl > 0 && nmax <= (size_t)g->vf.stride && nmax <= (size_t)vg_fast_nmax();
   if (fast && ctx->fast_miss_ttl > 0 && leaf <= ctx->fast_miss_leaf) { fast = false; ctx->fast_miss_ttl--; }
-  g->fast = fast; g->leaf = leaf;
+  g->fast = fast; g->leaf = leaf; g->stage_timed = ctx->stage_timing;
   int rc = group_launch(ctx, g, G, fast);
   if (rc) return rc;
   g->busy = true;
@@ -660,9 +670,11 @@ static int group_finish(fccf_ctx* ctx, Group* g, float* T_out, fccf_timing* tm) 
     tm->n_launches += (int)(g->launches - g->l0);
     tm->h2d_bytes += (unsigned long long)g->last_h2d;
     tm->d2h_bytes += sizeof(PipeState) * (unsigned long long)g->G;
-    cudaEventElapsedTime(&v, g->ev[2], g->sev[0]); tm->stage_ms[1] += v;
-    for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&v, g->sev[k], g->sev[k + 1]); tm->stage_ms[2 + k] += v; }
-    cudaEventElapsedTime(&v, g->sev[4], g->ev[3]); tm->stage_ms[6] += v;
+    if (g->stage_timed) {
+      cudaEventElapsedTime(&v, g->ev[2], g->sev[0]); tm->stage_ms[1] += v;
+      for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&v, g->sev[k], g->sev[k + 1]); tm->stage_ms[2 + k] += v; }
+      cudaEventElapsedTime(&v, g->sev[4], g->ev[3]); tm->stage_ms[6] += v;
+    }
   }
   return worst;
 }

@@ -376,14 +376,18 @@ __global__ void __launch_bounds__(1024) cluster_kernel(const ClArgs* __restrict_
   if (t == 0) {
     int clusternum = key[0];
     int emitted = 0, special = 0;
+    const double half = cluster_num / 2.0;
+    int kn = key[0], pn = perm[0];                       // the next entry is fetched while this one is decided
     for (int ci = 0; ci < K; ci++) {
-      if (key[ci] >= clusternum) {
+      const int kc = kn, pc = pn;
+      if (ci + 1 < K) { kn = key[ci + 1]; pn = perm[ci + 1]; }
+      if (kc >= clusternum) {
         if (emitted >= FCCF_MAXCENTRE) { atomicOr(&st->status, ST_CENTRE_OVERFLOW); break; }
-        s_emit[emitted++] = perm[ci];
-        special |= (key[ci] == 0 || key[ci] > CL_WSCR);     // clusters the warp path below does not finish (empty / above CL_WSCR members)
+        s_emit[emitted++] = pc;
+        special |= (kc == 0 || kc > CL_WSCR);     // clusters the warp path below does not finish (empty / above CL_WSCR members)
         if (cluster_num >= 0 && emitted > cluster_num) break;
       } else {
-        if ((double)emitted < (cluster_num / 2.0)) { clusternum--; if (clusternum < 2) break; }
+        if ((double)emitted < half) { clusternum--; if (clusternum < 2) break; }
         else break;   // stop = true: nothing further is emitted
       }
     }

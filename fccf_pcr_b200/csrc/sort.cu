@@ -36,7 +36,9 @@ __device__ __forceinline__ int rs_bpp(int nbits, int np) {
 // (key, original index): the same stable order), the result written where an even pass count leaves it (back
 // in kin / vin); the pass kernels of such a job exit at once.
 // A 1k-hypothesis pool costs one ~8 us launch instead of twelve dependent pass kernels.
-#define RS_SMALL 4096
+#define RS_SMALL 4096       // (8192: the one-CTA network takes longer than four passes over all SMs; measured on 8k octree keys)
+extern __shared__ __align__(16) unsigned char rs_small_dyn[];
+template <typename KT> struct RsSmallBytes { static constexpr int value = RS_SMALL * (sizeof(KT) == 4 ? 8 : 10); };
 template <typename KT>
 __global__ void __launch_bounds__(1024) rs_small_kernel(const SortJobs* __restrict__ JB) {
   FCCF_PDL_ENTER();
@@ -44,28 +46,47 @@ __global__ void __launch_bounds__(1024) rs_small_kernel(const SortJobs* __restri
   const int n = *j.n;
   const int t = threadIdx.x;
   if (n > RS_SMALL) return;
-  __shared__ KT sk[RS_SMALL];
-  __shared__ unsigned short sv[RS_SMALL];
   KT* kin = (KT*)j.kin;
+  u32* vin = const_cast<u32*>(j.vin);
   int N = 2;
   while (N < n) N <<= 1;
-  for (int i = t; i < N; i += 1024) { sk[i] = i < n ? kin[i] : (KT)~(KT)0; sv[i] = (unsigned short)i; }
-  __syncthreads();
-  for (int k = 2; k <= N; k <<= 1) {
-    for (int jj = k >> 1; jj > 0; jj >>= 1) {
-      for (int q = t; q < (N >> 1); q += 1024) {
-        const int lo = ((q & ~(jj - 1)) << 1) | (q & (jj - 1)), hi = lo | jj;
-        const bool up = (lo & k) == 0;
-        const KT a = sk[lo], b = sk[hi];
-        const unsigned short ia = sv[lo], ib = sv[hi];
-        const bool gt = a > b || (a == b && ia > ib);
-        if (gt == up) { sk[lo] = b; sk[hi] = a; sv[lo] = ib; sv[hi] = ia; }
+  if (sizeof(KT) == 4) {
+    // 32-bit keys: one 64-bit word (key, index) per element, a single compare per exchange
+    u64* sk = (u64*)rs_small_dyn;
+    for (int i = t; i < N; i += 1024) sk[i] = i < n ? (((u64)kin[i] << 32) | (u64)(u32)i) : ~(u64)0;
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1) {
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int q = t; q < (N >> 1); q += 1024) {
+          const int lo = ((q & ~(jj - 1)) << 1) | (q & (jj - 1)), hi = lo | jj;
+          const bool up = (lo & k) == 0;
+          const u64 a = sk[lo], b = sk[hi];
+          if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
+    for (int i = t; i < n; i += 1024) { const u64 v = sk[i]; kin[i] = (KT)(v >> 32); vin[i] = (u32)v; }
+  } else {
+    KT* sk = (KT*)rs_small_dyn;
+    unsigned short* sv = (unsigned short*)(sk + RS_SMALL);
+    for (int i = t; i < N; i += 1024) { sk[i] = i < n ? kin[i] : (KT)~(KT)0; sv[i] = (unsigned short)i; }
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1) {
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int q = t; q < (N >> 1); q += 1024) {
+          const int lo = ((q & ~(jj - 1)) << 1) | (q & (jj - 1)), hi = lo | jj;
+          const bool up = (lo & k) == 0;
+          const KT a = sk[lo], b = sk[hi];
+          const unsigned short ia = sv[lo], ib = sv[hi];
+          const bool gt = a > b || (a == b && ia > ib);
+          if (gt == up) { sk[lo] = b; sk[hi] = a; sv[lo] = ib; sv[hi] = ia; }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = t; i < n; i += 1024) { kin[i] = sk[i]; vin[i] = (u32)sv[i]; }
   }
-  u32* vin = const_cast<u32*>(j.vin);
-  for (int i = t; i < n; i += 1024) { kin[i] = sk[i]; vin[i] = (u32)sv[i]; }
 }
 
 template <typename KT>
@@ -204,10 +225,14 @@ __global__ void __launch_bounds__(RS_T, 4) rs_scatter_kernel(const SortJobs* __r
   }
 }
 
+void sort_init_attributes() {
+  cudaFuncSetAttribute(rs_small_kernel<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, RsSmallBytes<u32>::value);
+  cudaFuncSetAttribute(rs_small_kernel<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, RsSmallBytes<u64>::value);
+}
 void launch_sort(cudaStream_t s, const SortJobs* ab, const SortJobs* ba, int njobs, int G, int cap, int np, int key_bytes, uint64_t* launches) {
   dim3 grid(grid_x((cap + RS_TILE - 1) / RS_TILE, G, njobs), njobs, G);
-  if (key_bytes == 4) klaunch(rs_small_kernel<u32>, dim3(dim3(1, njobs, G)), dim3(1024), 0, s, ab);
-  else klaunch(rs_small_kernel<u64>, dim3(dim3(1, njobs, G)), dim3(1024), 0, s, ab);
+  if (key_bytes == 4) klaunch(rs_small_kernel<u32>, dim3(dim3(1, njobs, G)), dim3(1024), (size_t)RsSmallBytes<u32>::value, s, ab);
+  else klaunch(rs_small_kernel<u64>, dim3(dim3(1, njobs, G)), dim3(1024), (size_t)RsSmallBytes<u64>::value, s, ab);
   if (launches) *launches += 1;
   for (int p = 0; p < np; p++) {
     const SortJobs* J = (p & 1) ? ba : ab;

@@ -57,7 +57,9 @@ typedef struct fccf_timing {
   int n_launches;     /* kernels launched for this registration */
   unsigned long long h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host */
   float stage_ms[8];  /* voxelgrid(main), voxelgrid(pipeline), planes, hypotheses, cluster, quick_verify, fine_verify+fuse;
-                         [7]: batch entry points only, host wall clock of the whole batch in ms */
+                         [1]..[6] are filled only while stage timing is on (fccf_set_stage_timing: six more event nodes
+                         in every captured sequence, ~27 us per registration); [7]: batch entry points only, host wall
+                         clock of the whole batch in ms */
 } fccf_timing;
 
 enum { FCCF_OK = 0, FCCF_ERR_CUDA = 1, FCCF_ERR_ARG = 2, FCCF_ERR_CAPACITY = 3, FCCF_ERR_NO_DEVICE = 4 };
@@ -71,6 +73,9 @@ fccf_ctx* fccf_create(int device, const fccf_params* params);
 void fccf_destroy(fccf_ctx* ctx);
 const char* fccf_last_error(const fccf_ctx* ctx);
 int fccf_set_params(fccf_ctx* ctx, const fccf_params* params);
+/* per-stage device times (fccf_timing.stage_ms[1..6]): off by default (the reference prints one clock() figure,
+ * FCCF.cpp:1682-1686); FCCF_STAGE_EVENTS=1 in the environment turns it on at fccf_create */
+int fccf_set_stage_timing(fccf_ctx* ctx, int on);
 
 /* replaces: main() from the loaded clouds on (FCCF.cpp:1667-1687): VoxelGrid(leaf) on each cloud,
  * then computer_transform_guess(cloud_tar, cloud_src, T) — note the reference's swapped argument

@@ -1,5 +1,6 @@
 """One batched registration sequence (G pairs in one group) for profiling: ncu launch lists of the batched kernels."""
 import os
+os.environ.setdefault("FCCF_STAGE_EVENTS", "1")      # stage_ms[1..6] wanted
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

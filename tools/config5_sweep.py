@@ -5,6 +5,7 @@ identically to the oracle).  Per leaf: stage times, kernel launches, stage-0 Vox
 and parity against the CPU oracle.  Writes profiles/r02_config5_sweep.json / .md.
     python tools/config5_sweep.py [points] [--no-oracle]"""
 import json, os, sys, time
+os.environ.setdefault("FCCF_STAGE_EVENTS", "1")      # stage_ms[1..6] wanted
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,5 +1,6 @@
 """One warm registration of the 2M + 2M outdoor pair of BASELINE config 3 (profiling target).  python tools/one_reg_outdoor.py [repeats] [points]"""
 import os, sys
+os.environ.setdefault("FCCF_STAGE_EVENTS", "1")      # stage_ms[1..6] wanted
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import fccf_pcr_b200 as fccf

@@ -1,5 +1,6 @@
 """Per-stage device times of one registration (fccf_timing.stage_ms), for profiling runs."""
 import os
+os.environ.setdefault("FCCF_STAGE_EVENTS", "1")      # stage_ms[1..6] wanted
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,5 +1,6 @@
 """Stage times of a device-resident batch (one group alone).  python tools/vg_batch_time.py [pairs]"""
 import os, sys
+os.environ.setdefault("FCCF_STAGE_EVENTS", "1")      # stage_ms[1..6] wanted
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

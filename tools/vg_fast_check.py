@@ -1,6 +1,7 @@
 """Cluster VoxelGrid (voxelgrid_fast.cu) against the generic kernels and the oracle, and its stage time.
 Run on a GPU box:  python tools/vg_fast_check.py [pairs]"""
 import os
+os.environ.setdefault("FCCF_STAGE_EVENTS", "1")      # stage_ms[1..6] wanted
 import sys
 import time
 
