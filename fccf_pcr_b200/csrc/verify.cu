@@ -75,11 +75,17 @@ __device__ __forceinline__ bool lm_eval(const LmRow& R, const double x[7], doubl
     fin = isfinite(r); finr = fin;
     if (want) {
       double Ja[7];
+      // even rows: w * (cv . (n1 x dn)) / nc, odd rows: w * (d * dd) / sd — numerator and denominator are selected per
+      // lane and ONE division runs for the whole warp (the same operations per lane as the two-sided branch)
+      const double den = R.odd ? sd : nc;
       #pragma unroll
       for (int col = 0; col < 4; col++) {
         double dn[3] = {Jn[0][col], Jn[1][col], Jn[2][col]}, dp[3] = {Jp[0][col], Jp[1][col], Jp[2][col]};
-        if (!R.odd) { double dc[3]; crossd(R.n1, dn, dc); Ja[col] = R.w * (dot3d(cv, dc) / nc); }
-        else { double dd = -(dot3d(dn, p2r) + dot3d(n2r, dp)); Ja[col] = R.w * (d * dd / sd); }
+        double dc[3]; crossd(R.n1, dn, dc);
+        const double ne = dot3d(cv, dc);
+        const double dd = -(dot3d(dn, p2r) + dot3d(n2r, dp));
+        const double no = d * dd;
+        Ja[col] = R.w * ((R.odd ? no : ne) / den);
       }
       #pragma unroll
       for (int col = 0; col < 3; col++) Ja[4 + col] = R.odd ? R.w * (d * (-n2r[col]) / sd) : 0.0;
@@ -158,16 +164,17 @@ __device__ __forceinline__ bool lm_qr_solve(double A[6], double b, double B[6], 
     if (lane == k) A[k] = alpha;
   }
   // back substitution: the six reciprocals of the diagonal first (independent divisions), then multiplications
-  double dinv[6];
+  double amine = A[0];             // row k's diagonal entry lives in lane k: its reciprocal is computed there, once
   #pragma unroll
-  for (int k = 0; k < 6; k++) dinv[k] = 1.0 / __shfl_sync(0xffffffffu, A[k], k);
+  for (int k = 1; k < 6; k++) if (lane == k) amine = A[k];
+  const double dinv = 1.0 / amine;
   bool ok = true;
   #pragma unroll
   for (int k = 5; k >= 0; k--) {
     double s = b;
     #pragma unroll
     for (int j = k + 1; j < 6; j++) s -= A[j] * y[j];
-    y[k] = __shfl_sync(0xffffffffu, s * dinv[k], k);
+    y[k] = __shfl_sync(0xffffffffu, s * dinv, k);
     ok = ok && isfinite(y[k]);
   }
   return ok;
@@ -207,8 +214,13 @@ __device__ int lm_refine_warp(const LmRow& R, int lane, double x[7]) {
     step_successful = false;
     if (!reuse_diag) for (int c = 0; c < 6; c++) diag[c] = fmin(fmax(bfly(J[c] * J[c]), min_diag), max_diag);
     double Aq[6], Bq[6], step[6];
+    // damping row c belongs to lane c: one division and one square root per lane, not six
+    double dmine = diag[0];
     #pragma unroll
-    for (int c = 0; c < 6; c++) { Aq[c] = J[c]; Bq[c] = (lane == c) ? sqrt(diag[c] / radius) : 0.0; }
+    for (int c = 1; c < 6; c++) if (lane == c) dmine = diag[c];
+    const double bmine = sqrt(dmine / radius);
+    #pragma unroll
+    for (int c = 0; c < 6; c++) { Aq[c] = J[c]; Bq[c] = (lane == c) ? bmine : 0.0; }
     bool solved = lm_qr_solve(Aq, r, Bq, lane, step);
     reuse_diag = true;
     bool valid = false; double model_change = 0;
