@@ -704,3 +704,23 @@ def test_rich_200k_three_pools_14k_hypotheses(oracle_mod):
     assert scenes.rotation_error_deg(Tg, To) <= 0.01 and scenes.translation_error(Tg, To) <= 1e-3
     assert scenes.rotation_error_deg(Tg, Tgt) < 1.0 and scenes.translation_error(Tg, Tgt) < 0.08
     c.close()
+
+
+def test_stage_timing_is_opt_in(ctx):
+    """fccf_set_stage_timing: the per-stage event nodes are left out of the captured sequence by default (stage_ms[1..6]
+    stay zero), switched on they report every stage, and the registration result does not depend on them."""
+    src, tar, _ = scenes.make_pair("indoor", 20000, 7)
+    T0 = ctx.register(src, tar, 0.1).copy()
+    st0 = np.array(list(ctx.timing.stage_ms))
+    if os.environ.get("FCCF_STAGE_EVENTS") != "1":
+        assert st0[0] > 0 and np.all(st0[1:7] == 0), st0
+    ctx.set_stage_timing(True)
+    try:
+        T1 = ctx.register(src, tar, 0.1).copy()
+        st1 = np.array(list(ctx.timing.stage_ms))
+        assert np.all(st1[:7] > 0), st1
+        assert abs(st1[:7].sum() - (ctx.timing.downsample_ms + ctx.timing.pipeline_ms)) < 0.05 * ctx.timing.total_ms
+    finally:
+        ctx.set_stage_timing(False)
+    T2 = ctx.register(src, tar, 0.1)
+    assert np.array_equal(T0, T1, equal_nan=True) and np.array_equal(T0, T2, equal_nan=True)

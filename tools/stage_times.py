@@ -32,8 +32,6 @@ def main():
     print("cluster_kernel(type 0) cycles: neighbour lists %d | seeding %d (%d rounds) | seeds+sizes %d | sort %d | walk %d | small centres %d | big centres %d" % (
         pr[9] - pr[0], pr[1] - pr[9], pr[8], pr[2] - pr[1], pr[3] - pr[2], pr[4] - pr[3], pr[5] - pr[4], pr[6] - pr[5]))
     print("grow_faces(cloud 1) cycles: stage1 %d | stage2 %d | range_face %d | select+theta %d" % (pr[17] - pr[16], pr[18] - pr[17], pr[19] - pr[18], pr[20] - pr[19]))
-    print("grow stage1 detail: test %d | barrier+first %d | chain %d | rounds %d accepts %d windows %d exact(lane 0) %d" % (tuple(pr[10:16]) + (pr[21],)))
-    print("grow stage1 seeds: %d, seed set-up %d cycles, pair rows %d cycles" % (pr[24], pr[22], pr[23]))
     print("n_hyp", ctx.blob("n_hyp"), "n_centres", ctx.blob("n_centres"), "P", len(ctx.blob("vg2_cnt1")), len(ctx.blob("vg2_cnt2")),
           "V", len(ctx.blob("vox_cnt1")), "Vp", len(ctx.blob("pvox1")) // 7, "S", len(ctx.blob("sub1")) // 3, len(ctx.blob("sub2")) // 3)
 
