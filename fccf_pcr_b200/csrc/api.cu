@@ -355,6 +355,7 @@ fccf_ctx* fccf_create(int device, const fccf_params* params) {
   if (const char* e = getenv("FCCF_NO_GRAPH")) ctx->use_graph = !(e[0] == '1');
   if (const char* e = getenv("FCCF_STAGE_EVENTS")) ctx->stage_timing = (e[0] == '1');
   sort_init_attributes();
+  planes_init_attributes();
   score_init_attributes();
   cluster_init_attributes();
   ctx->vg_fast = vg_fast_init() > 0;

@@ -252,6 +252,7 @@ void cluster_init_attributes();
 int cluster_nbl_ints();
 int cluster_deg_ints();
 void sort_init_attributes();
+void planes_init_attributes();
 void score_init_attributes();   // one-time function attributes (not allowed inside a stream capture)
 // VoxelGrid stage `stage` (0: on raw clouds, 1: on the stage-0 output) for both clouds
 void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uint64_t* launches);
