@@ -724,3 +724,41 @@ def test_stage_timing_is_opt_in(ctx):
         ctx.set_stage_timing(False)
     T2 = ctx.register(src, tar, 0.1)
     assert np.array_equal(T0, T1, equal_nan=True) and np.array_equal(T0, T2, equal_nan=True)
+
+
+def _tilted_patches(seed, nx=28, ny=28):
+    """One square patch per metre of a floor, each tilted by 0-7 degrees about a random in-plane axis (a third of them
+    between 4.6 and 5.4 degrees, around normal_vector_threshold1 = 5) and a fifth of them lifted by 4-13 cm (around
+    compare_plane's l / (k d + 1) at one metre): hundreds of accept / reject decisions of face growing and merging
+    land next to their thresholds, normals come out of the PCA with both signs (cosines near -1), and the 224 stage-1
+    faces merge down to ~25 — the cases the float filter in front of the exact tests, the pair matrices and the
+    symmetric first sweep of stage 2 have to get right."""
+    rng = np.random.default_rng(seed)
+    u, v = np.meshgrid(np.linspace(-0.42, 0.42, 9), np.linspace(-0.42, 0.42, 9))
+    loc = np.stack([u.ravel(), v.ravel(), np.zeros(u.size)], 1)
+    pts = []
+    for ix in range(nx):
+        for iy in range(ny):
+            tilt = math.radians(rng.uniform(0.0, 7.0) if (ix + iy) % 3 else rng.uniform(4.6, 5.4))
+            az = rng.uniform(0, 2 * math.pi)
+            ax = np.array([math.cos(az), math.sin(az), 0.0])
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            R = np.eye(3) + math.sin(tilt) * K + (1 - math.cos(tilt)) * (K @ K)
+            z = 0.5 + (rng.uniform(0.04, 0.13) if (ix * 7 + iy) % 5 == 0 else 0.0)
+            c = np.array([ix + 0.5 + rng.uniform(-0.05, 0.05), iy + 0.5 + rng.uniform(-0.05, 0.05), z])
+            pts.append(loc @ R.T + c + rng.normal(scale=2e-4, size=loc.shape))
+    xyz = np.concatenate(pts).astype(np.float32)
+    return xyz[rng.permutation(len(xyz))]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_face_growing_next_to_its_thresholds(ctx, orc, seed):
+    xyz = _tilted_patches(seed)
+    nf = ctx.extract_planes(xyz)
+    assert nf == orc.face_extract(xyz)
+    gl = orc.blob("grow_label1")
+    assert len(gl) > 1000 and gl.max() + 1 > 100 and len(np.unique(orc.blob("merge_label1"))) < (gl.max() + 1) // 3     # many faces, many merges
+    for name in ["vox_flag1", "grow_label1", "merge_label1", "face_id1", "face_nvox1", "face_vox1"]:
+        assert np.array_equal(ctx.blob(name), orc.blob(name)), name
+    assert _rel_rows(ctx.blob("face_plane1"), orc.blob("face_plane1"), 7, [[0, 1, 2], [3, 4, 5], [6]]) <= PLANE_TOL
+    np.testing.assert_allclose(ctx.blob("face_theta1"), orc.blob("face_theta1"), atol=0.02)
