@@ -192,30 +192,32 @@ __global__ void __launch_bounds__(128) match_test_kernel(const HypArgs* __restri
 }
 
 // ---- ordered list of the matched entries (one CTA) ----
+// Every thread owns a run of consecutive entries (at most 15: B1 x B2 <= FCCF_MAXMATCH): it counts its run, ONE block
+// scan places the runs, it writes its entries — two barriers for the whole list instead of three per 1024 entries.
 __global__ void __launch_bounds__(1024) match_compact_kernel(const HypArgs* __restrict__ AB) {
   FCCF_PDL_ENTER();
   const HypArgs& A = AB[blockIdx.z];
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   __shared__ int s_w[32];
-  __shared__ int s_run;
   const int NM = st->base[0].B * st->base[1].B;
-  if (t == 0) s_run = 0;
+  const int per = (NM + 1023) / 1024;
+  const int b0 = min(NM, t * per), b1 = min(NM, b0 + per);
+  int cnt = 0;
+  for (int k = b0; k < b1; k++) cnt += (A.match_cnt[k] != 0) ? 1 : 0;
+  int inc = cnt;
+  for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+  if (lane == 31) s_w[warp] = inc;
   __syncthreads();
-  for (int i0 = 0; i0 < NM; i0 += 1024) {
-    int idx = i0 + t;
-    bool m = idx < NM && A.match_cnt[idx] != 0;
-    unsigned bal = __ballot_sync(0xffffffffu, m);
-    if (lane == 0) s_w[warp] = __popc(bal);
-    __syncthreads();
-    int off = s_run;
-    for (int w2 = 0; w2 < warp; w2++) off += s_w[w2];
-    if (m) A.mlist[off + __popc(bal & ((1u << lane) - 1u))] = idx;
-    __syncthreads();
-    if (t == 0) { int tot = 0; for (int w2 = 0; w2 < 32; w2++) tot += s_w[w2]; s_run += tot; }
-    __syncthreads();
+  if (warp == 0) {
+    const int wv = s_w[lane]; int wi = wv;
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += y; }
+    s_w[lane] = wi - wv;
+    if (lane == 31) { st->n_match = NM; st->tickets[22] = wi; }     // tickets[22]: number of matched entries
   }
-  if (t == 0) { st->n_match = NM; st->tickets[22] = s_run; }     // tickets[22]: number of matched entries
+  __syncthreads();
+  int off = s_w[warp] + inc - cnt;
+  for (int k = b0; k < b1; k++) if (A.match_cnt[k] != 0) A.mlist[off++] = k;
 }
 
 // ---- hypotheses per match: one warp per matched entry ----
@@ -245,37 +247,45 @@ __global__ void __launch_bounds__(1024) match_scan_kernel(const HypArgs* __restr
   PipeState* st = A.st;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   __shared__ u32 s_w[3][32];
-  __shared__ u32 s_carry[3];
+  __shared__ u32 s_tot[3];
   const int B1 = st->base[0].B, B2 = st->base[1].B;
   const int NM = B1 * B2;
   const u32 lim = (u32)A.cap_hyp + 1u;
-  if (t < 3) s_carry[t] = 0;
-  __syncthreads();
-  for (int i0 = 0; i0 < NM; i0 += 1024) {
-    int idx = i0 + t;
-    u32 x[3] = {0u, 0u, 0u}; int ty = -1;
-    if (idx < NM) { int cnt = A.match_cnt[idx]; if (cnt > 0) { ty = st->base[0].type[idx / B2]; x[ty] = (u32)cnt; } }
-    u32 inc[3] = {x[0], x[1], x[2]};
+  // every thread owns a run of consecutive entries (at most 15); saturating sums are associative (min(lim, a + b) of
+  // non-negative counts), so the run totals go through one block scan per type and the run is walked once more
+  const int per = (NM + 1023) / 1024;
+  const int b0 = min(NM, t * per), b1 = min(NM, b0 + per);
+  u32 x[3] = {0u, 0u, 0u};
+  for (int k = b0; k < b1; k++) { const int cnt = A.match_cnt[k]; if (cnt > 0) { const int ty = st->base[0].type[k / B2]; x[ty] = sat_add(x[ty], (u32)cnt, lim); } }
+  u32 inc[3] = {x[0], x[1], x[2]};
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, inc[k], d); if (lane >= d) inc[k] = sat_add(inc[k], y, lim); }
-      if (lane == 31) s_w[k][warp] = inc[k];
-    }
-    __syncthreads();
-    if (warp < 3) {
-      u32 wv = s_w[warp][lane], wi = wv;
-      for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi = sat_add(wi, y, lim); }
-      u32 ex = __shfl_up_sync(0xffffffffu, wi, 1);
-      s_w[warp][lane] = lane ? ex : 0u;
-    }
-    __syncthreads();
-    if (ty >= 0) A.match_off[idx] = (int)sat_add(sat_add(s_carry[ty], s_w[ty][warp], lim), inc[ty] - x[ty], lim);
-    __syncthreads();
-    if (t == 1023) { for (int k = 0; k < 3; k++) s_carry[k] = sat_add(sat_add(s_carry[k], s_w[k][warp], lim), inc[k], lim); }
-    __syncthreads();
+  for (int k = 0; k < 3; k++) {
+    for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, inc[k], d); if (lane >= d) inc[k] = sat_add(inc[k], y, lim); }
+    if (lane == 31) s_w[k][warp] = inc[k];
+  }
+  __syncthreads();
+  if (warp < 3) {
+    u32 wv = s_w[warp][lane], wi = wv;
+    for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi = sat_add(wi, y, lim); }
+    u32 ex = __shfl_up_sync(0xffffffffu, wi, 1);
+    s_w[warp][lane] = lane ? ex : 0u;
+    if (lane == 31) s_tot[warp] = wi;
+  }
+  __syncthreads();
+  u32 run[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    // exclusive prefix of this thread's run: warps in front + lanes in front (inclusive scan of the lane in front)
+    u32 before = __shfl_up_sync(0xffffffffu, inc[k], 1);
+    if (lane == 0) before = 0u;
+    run[k] = sat_add(s_w[k][warp], before, lim);
+  }
+  for (int k = b0; k < b1; k++) {
+    const int cnt = A.match_cnt[k];
+    if (cnt > 0) { const int ty = st->base[0].type[k / B2]; A.match_off[k] = (int)run[ty]; run[ty] = sat_add(run[ty], (u32)cnt, lim); }
   }
   if (t == 0) {
-    u32 n0 = s_carry[0], n1 = s_carry[1], n2 = s_carry[2];
+    u32 n0 = s_tot[0], n1 = s_tot[1], n2 = s_tot[2];
     if ((unsigned long long)n0 + n1 + n2 > (unsigned long long)A.cap_hyp) { atomicOr(&st->status, ST_HYP_OVERFLOW); n0 = n1 = n2 = 0; }
     st->n_hyp[0] = (int)n0; st->n_hyp[1] = (int)n1; st->n_hyp[2] = (int)n2;
     st->hyp_off[0] = 0; st->hyp_off[1] = (int)n0; st->hyp_off[2] = (int)(n0 + n1); st->hyp_off[3] = (int)(n0 + n1 + n2);
