@@ -55,7 +55,7 @@ struct Lane {
   int pair = -1;
 };
 
-struct GraphRec { int G = 0; bool fast = false; cudaGraphExec_t exec = nullptr; int launches = 0; };
+struct GraphRec { int G = 0; bool fast = false, lean = false; cudaGraphExec_t exec = nullptr; int launches = 0; };
 
 // A group = the lanes that run as ONE batched launch sequence on one stream: every kernel of the
 // pipeline is launched once with grid.z = G and serves G independent registrations (most stages of one
@@ -79,6 +79,7 @@ struct Group {
   int G = 0;                     // lanes of the sequence in flight
   bool fast = false;             // the sequence in flight uses the cluster VoxelGrid (voxelgrid_fast.cu)
   bool stage_timed = false;      // the sequence in flight records the per-stage events
+  bool lean = false;             // the sequence in flight has no radix pass launches behind its hypothesis / fine-verify sorts
   float leaf = 0.f;
   VgFastScratch vf;              // its per-cluster scratch (L2-resident)
   size_t last_h2d = 0;
@@ -98,6 +99,9 @@ struct fccf_ctx {
   // through the generic kernels, and calls with a leaf <= the one that missed go generic directly for a while.
   bool vg_fast = false;
   float fast_miss_leaf = 0.f; int fast_miss_ttl = 0;
+  // Sequences without the radix-pass launches of the hypothesis / fine-verify sorts ("lean"): used once a registration
+  // has shown lists well inside the one-CTA sort, dropped for a while when one meets a longer list (ST_SORT_MISS: re-run)
+  bool lean_ok = false; int lean_ttl = 0;
   uint64_t fast_runs = 0, fast_misses = 0;
   uint64_t params_epoch = 1;
   bool stage_timing = false;     // per-stage timing events inside the captured sequences (fccf_set_stage_timing)
@@ -393,7 +397,7 @@ const char* fccf_last_error(const fccf_ctx* ctx) {
 int fccf_set_params(fccf_ctx* ctx, const fccf_params* params) {
   if (!ctx || !params) return FCCF_ERR_ARG;
   if (const char* why = params_problem(*params)) { ctx->err = std::string("bad parameter: ") + why; return FCCF_ERR_ARG; }
-  ctx->fast_miss_leaf = 0.f; ctx->fast_miss_ttl = 0;
+  ctx->fast_miss_leaf = 0.f; ctx->fast_miss_ttl = 0; ctx->lean_ok = false; ctx->lean_ttl = 0;
   int lanes = ctx->p.batch_lanes;
   ctx->p = *params; ctx->p.batch_lanes = lanes;   // the lane count is fixed at creation
   ctx->params_epoch++;                            // captured graphs hold the old values: re-capture lazily
@@ -473,7 +477,7 @@ static int set_single_call(fccf_ctx* ctx, int n0, int n1, float leaf) {
 }
 
 static int check_status(fccf_ctx* ctx, int st) {
-  st &= ~ST_VG_FAST_MISS;          // not an error (handled by the caller: generic re-run)
+  st &= ~(ST_VG_FAST_MISS | ST_SORT_MISS);          // not errors (handled by the caller: re-run of the full sequence)
   if (st == 0) return FCCF_OK;
   char b[256];
   snprintf(b, sizeof b, "device status 0x%x:%s%s%s%s%s", st, (st & ST_OCT_DEPTH) ? " octree deeper than the 32-bit Morton key" : "",
@@ -487,7 +491,7 @@ static int check_status(fccf_ctx* ctx, int st) {
 // blocks, in stream order on the group's stream.  All sizes are device-side and the per-call values
 // (point counts, leaf, raw-cloud pointers) are read from the group's call array, so the sequence is
 // identical for every call with the same G: it is captured into a CUDA graph once and replayed.
-static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_t* launches, bool capturing, bool fast) {
+static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_t* launches, bool capturing, bool fast, bool lean = false) {
   cudaStream_t s = g->stream;
   // inside a capture a plain cudaEventRecord is only a dependency; the External flag makes a timing node
   const bool stage_events = ctx->stage_timing;
@@ -495,6 +499,7 @@ static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_
   std::vector<Work> ws;
   Batch b = make_batch(ctx, g, G, ws, tab);
   if (capturing) { b.side = g->stream2; b.side_fork = g->fork2; b.side_join = g->join2; }
+  b.lean = lean;
   struct PdlScope { bool prev; PdlScope(bool on) : prev(fccf_pdl_flag()) { fccf_pdl_flag() = on; } ~PdlScope() { fccf_pdl_flag() = prev; } } pdl_scope(capturing && pdl_wanted(G));
   launch_init_state(s, b, g->d_calls, launches);
   if (fast) CK(launch_voxelgrid_fast(s, b, 0, 2, g->vf, launches));   // main(): FCCF.cpp:1668-1678, one cluster per cloud
@@ -529,19 +534,19 @@ static int group_pipeline(fccf_ctx* ctx, Group* g, int G, ArgTable* tab, uint64_
   return FCCF_OK;
 }
 
-static int group_graph(fccf_ctx* ctx, Group* g, int G, bool fast, GraphRec** out) {
+static int group_graph(fccf_ctx* ctx, Group* g, int G, bool fast, bool lean, GraphRec** out) {
   if (g->params_epoch != ctx->params_epoch) { CK(cudaStreamSynchronize(g->stream)); group_drop_graphs(g); g->params_epoch = ctx->params_epoch; }
-  for (GraphRec& r : g->graphs) if (r.G == G && r.fast == fast) { *out = &r; return FCCF_OK; }
+  for (GraphRec& r : g->graphs) if (r.G == G && r.fast == fast && r.lean == lean) { *out = &r; return FCCF_OK; }
   // room for one more capture?  (about 10 KB of argument blocks per lane)
   if (g->graphs.size() >= 8 || g->tab.off + (size_t)G * 12288 + 65536 > g->tab.cap) { CK(cudaStreamSynchronize(g->stream)); group_drop_graphs(g); }
   cudaStream_t s = g->stream;
-  GraphRec r; r.G = G; r.fast = fast;
+  GraphRec r; r.G = G; r.fast = fast; r.lean = lean;
   size_t off0 = g->tab.off;
   g->tab.immediate = false;
   cudaGraph_t graph = nullptr;
   uint64_t cnt = 0;
   CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-  int rc = group_pipeline(ctx, g, G, &g->tab, &cnt, true, fast);
+  int rc = group_pipeline(ctx, g, G, &g->tab, &cnt, true, fast, lean);
   cudaError_t e = cudaStreamEndCapture(s, &graph);
   if (rc != FCCF_OK || e != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
@@ -562,17 +567,17 @@ static int group_graph(fccf_ctx* ctx, Group* g, int G, bool fast, GraphRec** out
 }
 
 // The batched pipeline of the G lanes whose call blocks are in g->d_calls (graph replay, or plain launches).
-static int group_launch(fccf_ctx* ctx, Group* g, int G, bool fast) {
+static int group_launch(fccf_ctx* ctx, Group* g, int G, bool fast, bool lean) {
   cudaStream_t s = g->stream;
   if (ctx->use_graph) {
     GraphRec* r = nullptr;
-    int rc = group_graph(ctx, g, G, fast, &r);
+    int rc = group_graph(ctx, g, G, fast, lean, &r);
     if (rc) return rc;
     CK(cudaGraphLaunch(r->exec, s));
     g->launches += (uint64_t)r->launches;
   } else {
     g->tab.immediate = true; g->tab.off = 0; g->tab.overflow = false;
-    int rc = group_pipeline(ctx, g, G, &g->tab, &g->launches, false, fast);
+    int rc = group_pipeline(ctx, g, G, &g->tab, &g->launches, false, fast, lean);
     if (rc) return rc;
   }
   CK(cudaEventRecord(g->ev[4], s));
@@ -625,8 +630,9 @@ static int group_enqueue(fccf_ctx* ctx, Group* g, int G, int pair0, const float*
   for (int l = 0; l < G; l++) nmax = std::max(nmax, std::max(n_src[l], n_tar[l]));
   bool fast = ctx->vg_fast && g->vf.ncl > 0 && nmax <= (size_t)g->vf.stride && nmax <= (size_t)vg_fast_nmax();
   if (fast && ctx->fast_miss_ttl > 0 && leaf <= ctx->fast_miss_leaf) { fast = false; ctx->fast_miss_ttl--; }
-  g->fast = fast; g->leaf = leaf; g->stage_timed = ctx->stage_timing;
-  int rc = group_launch(ctx, g, G, fast);
+  const bool lean = ctx->lean_ok && ctx->use_graph;
+  g->fast = fast; g->leaf = leaf; g->stage_timed = ctx->stage_timing; g->lean = lean;
+  int rc = group_launch(ctx, g, G, fast, lean);
   if (rc) return rc;
   g->busy = true;
   return FCCF_OK;
@@ -638,20 +644,29 @@ static int group_finish(fccf_ctx* ctx, Group* g, float* T_out, fccf_timing* tm) 
   g->busy = false;                 // whatever happens below, the group is drained or abandoned
   CK(cudaStreamSynchronize(g->stream));
   CK(cudaGetLastError());
-  if (g->fast) {
-    ctx->fast_runs++;
-    bool miss = false;
-    for (int l = 0; l < g->G; l++) miss = miss || (g->lanes[l].h_st->status & ST_VG_FAST_MISS);
-    if (miss) {
-      // a cloud the cluster VoxelGrid could not hold: the same call blocks and raw clouds are still on the
-      // device, so the sequence is simply replayed through the generic kernels
-      ctx->fast_misses++;
-      ctx->fast_miss_leaf = std::max(ctx->fast_miss_leaf, g->leaf); ctx->fast_miss_ttl = 64;
-      g->fast = false;
-      int rc = group_launch(ctx, g, g->G, false);
+  {
+    // Two parts of a sequence are speculative: the cluster VoxelGrid (a cloud it cannot hold raises ST_VG_FAST_MISS) and
+    // the "lean" sorts without radix passes (a list beyond the one-CTA sort raises ST_SORT_MISS).  The call blocks and
+    // the raw clouds are still on the device, so a miss is answered by replaying the sequence without that part.
+    if (g->fast) ctx->fast_runs++;
+    bool vmiss = false, smiss = false;
+    for (int l = 0; l < g->G; l++) { const int stt = g->lanes[l].h_st->status; vmiss = vmiss || (stt & ST_VG_FAST_MISS); smiss = smiss || (stt & ST_SORT_MISS); }
+    vmiss = vmiss && g->fast; smiss = smiss && g->lean;
+    if (vmiss) { ctx->fast_misses++; ctx->fast_miss_leaf = std::max(ctx->fast_miss_leaf, g->leaf); ctx->fast_miss_ttl = 64; }
+    if (smiss) { ctx->lean_ok = false; ctx->lean_ttl = 64; }
+    if (vmiss || smiss) {
+      g->fast = g->fast && !vmiss; g->lean = g->lean && !smiss;
+      int rc = group_launch(ctx, g, g->G, g->fast, g->lean);
       if (rc) return rc;
       CK(cudaStreamSynchronize(g->stream));
       CK(cudaGetLastError());
+    }
+    // lean sequences from the next call on, once every lane's lists sit well inside the one-CTA sort
+    if (!smiss) {
+      int longest = 0;
+      for (int l = 0; l < g->G; l++) { const PipeState* hs = g->lanes[l].h_st; longest = std::max(longest, std::max(hs->hyp_off[3], hs->oct[0].S)); }
+      if (ctx->lean_ttl > 0) ctx->lean_ttl--;
+      else ctx->lean_ok = longest <= RS_SMALL - RS_SMALL / 16;
     }
   }
   int worst = FCCF_OK;

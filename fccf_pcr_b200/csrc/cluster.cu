@@ -490,7 +490,7 @@ void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches) {
     A.thr_n = b.p.cluster_number_threshold; A.ang_cut = b.cuts.cluster_lt; A.rad = b.p.cluster_distance_threshold; A.sel_num = b.p.seclct_cluster_number;
     A.nbits = &st->tickets[20]; A.cap_hyp = h.cap_hyp; A.nbl = h.c_nbl; A.deg = h.c_deg;
     if (h.cap_hyp > cap) cap = h.cap_hyp;
-    SortJob j; j.kin = h.ckeyA; j.kout = h.ckeyB; j.vin = h.cidxA; j.vout = h.cidxB; j.n = &st->hyp_off[3]; j.nbits = &st->tickets[20]; j.hist = h.chist; j.ticket = &st->tickets[21];
+    SortJob j; j.kin = h.ckeyA; j.kout = h.ckeyB; j.vin = h.cidxA; j.vout = h.cidxB; j.n = &st->hyp_off[3]; j.nbits = &st->tickets[20]; j.hist = h.chist; j.ticket = &st->tickets[21]; j.miss = &st->status;
     ab.j[0] = j; ab.j[1] = j; ab.j[2] = j;
     SortJob k = j; k.kin = h.ckeyB; k.kout = h.ckeyA; k.vin = h.cidxB; k.vout = h.cidxA; ba.j[0] = k; ba.j[1] = k; ba.j[2] = k;
   }
@@ -499,7 +499,7 @@ void launch_cluster(cudaStream_t s, const Batch& b, uint64_t* launches) {
   klaunch(cluster_prep_kernel, dim3(dim3(grid_x((cap + 255) / 256, G), 1, G)), dim3(256), 0, s, dA);
   if (launches) *launches += 1;
   // 34-bit keys: 6 passes of 6 bits (even pass count: result back in ckeyA / cidxA)
-  launch_sort(s, dab, dba, 1, G, cap, 6, 8, launches);
+  launch_sort(s, dab, dba, 1, G, cap, 6, 8, launches, b.lean);
   klaunch(cluster_xs_kernel, dim3(dim3(grid_x((cap + 255) / 256, G), 1, G)), dim3(256), 0, s, dA);
   klaunch(cluster_kernel, dim3(dim3(3, 1, G)), dim3(1024), CL_SMEM_BYTES, s, dA);
   if (launches) *launches += 2;

@@ -26,7 +26,9 @@ inline int fccf_topk(const fccf_params& p) { int k = (int)p.fine_verify_number; 
 
 // status bits written by kernels (checked by the host after the final synchronise)
 enum { ST_OCT_DEPTH = 1, ST_HYP_OVERFLOW = 2, ST_KEYBITS = 4, ST_CENTRE_OVERFLOW = 8, ST_HASH_FULL = 16, ST_CLUSTER_MEMBERS = 32,
-       ST_VG_FAST_MISS = 64 };   // not an error: the cluster VoxelGrid (voxelgrid_fast.cu) could not hold a cloud, the host re-runs the generic kernels
+       ST_VG_FAST_MISS = 64,     // not an error: the cluster VoxelGrid (voxelgrid_fast.cu) could not hold a cloud, the host re-runs the generic kernels
+       ST_SORT_MISS = 128 };     // not an error: a sequence captured without radix passes (small sorts only) met a longer list, the host re-runs the full one
+#define RS_SMALL 4096          // sort jobs of up to this many keys are done by one CTA in shared memory (sort.cu)
 
 struct VGState {
   int n_in, n_finite;
@@ -97,6 +99,7 @@ struct SortJob {
   const int* n; const int* nbits;
   u32* hist;     // [(nblocks_cap + 1) * 256]
   int* ticket;
+  int* miss;     // status word that takes ST_SORT_MISS when a pass-less launch meets a job beyond RS_SMALL (nullptr: none)
 };
 struct SortJobs { SortJob j[3]; };
 struct SegJob {
@@ -142,7 +145,8 @@ inline int grid_x(int nb_cap, int G, int njobs = 1, int budget = 4096) {
 // `np` passes of ceil(nbits/np) <= 8 bits.  Result ends in (kout,vout) of the last pass; the
 // launcher ping-pongs between the two buffer sets given in `a` and `b` (np even: result in a).
 // jobs_ab / jobs_ba: device tables of G entries.
-void launch_sort(cudaStream_t s, const SortJobs* jobs_ab, const SortJobs* jobs_ba, int njobs, int G, int cap, int np, int key_bytes, uint64_t* launches);
+// small_only: only the one-CTA sort is launched (sequences captured for lists known to be short; longer ones raise ST_SORT_MISS)
+void launch_sort(cudaStream_t s, const SortJobs* jobs_ab, const SortJobs* jobs_ba, int njobs, int G, int cap, int np, int key_bytes, uint64_t* launches, bool small_only = false);
 // segment heads of a sorted key array: seg_start[0..nseg], nseg
 void launch_segments(cudaStream_t s, const SegJobs* jobs, int njobs, int G, int cap, int key_bytes, uint64_t* launches);
 
@@ -220,6 +224,7 @@ struct Batch {                // the lanes one batched launch sequence covers
   // inside a stream capture: a second capture stream and an event pair for work that may run beside the main
   // sequence (nullptr outside captures: everything is launched in order on the one stream)
   cudaStream_t side = nullptr; cudaEvent_t side_fork = nullptr, side_join = nullptr;
+  bool lean = false;     // the hypothesis and fine-verify sorts are known to be short: no radix pass launches behind their small sort
 };
 
 
@@ -276,7 +281,7 @@ void launch_quick_verify_list(cudaStream_t s, const fccf_params& p, float* d_T16
                               const float* d_planes2, int f2, float* d_score, int* d_npair, int* d_pairs, int* d_iters, uint64_t* launches);
 // lattice + static hash of the static leftover cloud (n1/n2 are device-side counts), G lanes at once
 struct ScoreBuildJob { const float* s1; const int* n1; const int* n2; ScoreWS ws; };
-void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJob* jobs, int G, ArgTable& tab, uint64_t* launches);
+void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJob* jobs, int G, ArgTable& tab, uint64_t* launches, bool lean = false);
 // scores n_hyp hypotheses (row-major 4x4 each) -> d_scores
 void launch_score_list(cudaStream_t s, const fccf_params& p, const float* d_T16, int n_hyp, const float* d_s2, const ScoreWS& ws, float* d_scores, ArgTable& tab, uint64_t* launches);
 // packed (score, index) maximum of a device score list -> *d_out (8 bytes)

@@ -541,7 +541,7 @@ size_t score_ws_layout(ScoreWS* ws, char* base, int cap_points, int t_rows) {
   return off + 256;
 }
 
-void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJob* jobs, int G, ArgTable& tab, uint64_t* launches) {
+void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJob* jobs, int G, ArgTable& tab, uint64_t* launches, bool lean) {
   std::vector<ScArgs> As(G); std::vector<SortJobs> abs_(G), bas_(G); std::vector<SegJobs> sjs(G);
   int cap = 1, cap_hash = 1;
   for (int g = 0; g < G; g++) {
@@ -550,7 +550,7 @@ void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJo
     A.s1 = jobs[g].s1; A.n1p = jobs[g].n1; A.n2p = jobs[g].n2;
     if (ws.cap_points > cap) cap = ws.cap_points;
     if (ws.cap_hash > cap_hash) cap_hash = ws.cap_hash;
-    SortJob j; j.kin = ws.keyA; j.kout = ws.keyB; j.vin = ws.idxA; j.vout = ws.idxB; j.n = &ws.ss->n_keys; j.nbits = &ws.ss->nbits; j.hist = ws.hist; j.ticket = &ws.ss->tickets[1];
+    SortJob j; j.kin = ws.keyA; j.kout = ws.keyB; j.vin = ws.idxA; j.vout = ws.idxB; j.n = &ws.ss->n_keys; j.nbits = &ws.ss->nbits; j.hist = ws.hist; j.ticket = &ws.ss->tickets[1]; j.miss = ws.status;
     abs_[g].j[0] = j; abs_[g].j[1] = j; abs_[g].j[2] = j;
     SortJob k = j; k.kin = ws.keyB; k.kout = ws.keyA; k.vin = ws.idxB; k.vout = ws.idxA;
     bas_[g].j[0] = k; bas_[g].j[1] = k; bas_[g].j[2] = k;
@@ -565,7 +565,7 @@ void launch_score_build(cudaStream_t s, const fccf_params& p, const ScoreBuildJo
   klaunch(score_bbox_kernel, dim3(dim3(nb, 1, G)), dim3(256), 0, s, dA);
   klaunch(score_keys_kernel, dim3(dim3(nb, 1, G)), dim3(256), 0, s, dA);
   if (launches) *launches += 3;
-  launch_sort(s, dab, dba, 1, G, cap, 4, 4, launches);
+  launch_sort(s, dab, dba, 1, G, cap, 4, 4, launches, lean);
   launch_segments(s, dsj, 1, G, cap, 4, launches);
   int nbh = (cap_hash + 255) / 256; if (nbh > 1184) nbh = 1184;
   nbh = grid_x(nbh, G);
@@ -720,7 +720,7 @@ void launch_fine_verify_build(cudaStream_t s, const Batch& b, uint64_t* launches
     const Work& w = b.w[g]; PipeState* st = w.st;
     jobs[g].s1 = w.c[0].sub; jobs[g].n1 = &st->oct[0].S; jobs[g].n2 = &st->oct[1].S; jobs[g].ws = fv_ws(w);
   }
-  launch_score_build(s, b.p, jobs.data(), G, *b.tab, launches);
+  launch_score_build(s, b.p, jobs.data(), G, *b.tab, launches, b.lean);
 }
 
 void launch_fine_verify_fuse(cudaStream_t s, const Batch& b, uint64_t* launches) {

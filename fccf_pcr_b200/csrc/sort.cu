@@ -36,32 +36,49 @@ __device__ __forceinline__ int rs_bpp(int nbits, int np) {
 // (key, original index): the same stable order), the result written where an even pass count leaves it (back
 // in kin / vin); the pass kernels of such a job exit at once.
 // A 1k-hypothesis pool costs one ~8 us launch instead of twelve dependent pass kernels.
-#define RS_SMALL 4096       // (8192: the one-CTA network takes longer than four passes over all SMs; measured on 8k octree keys)
+// (RS_SMALL = 8192 was measured: the one-CTA network takes longer than four passes over all SMs on 8k octree keys)
 extern __shared__ __align__(16) unsigned char rs_small_dyn[];
 template <typename KT> struct RsSmallBytes { static constexpr int value = RS_SMALL * (sizeof(KT) == 4 ? 8 : 10); };
 template <typename KT>
-__global__ void __launch_bounds__(1024) rs_small_kernel(const SortJobs* __restrict__ JB) {
+__global__ void __launch_bounds__(1024) rs_small_kernel(const SortJobs* __restrict__ JB, int small_only) {
   FCCF_PDL_ENTER();
   const SortJob& j = JB[blockIdx.z].j[blockIdx.y];
   const int n = *j.n;
   const int t = threadIdx.x;
-  if (n > RS_SMALL) return;
+  if (n > RS_SMALL) { if (small_only && j.miss && t == 0) atomicOr(j.miss, ST_SORT_MISS); return; }
   KT* kin = (KT*)j.kin;
   u32* vin = const_cast<u32*>(j.vin);
   int N = 2;
   while (N < n) N <<= 1;
+  // Bitonic network: exchanges at distance >= 32 go through shared memory (one barrier each), the up to five exchanges at
+  // distances 16 .. 1 that end every merge step stay inside a warp and run on registers with shuffles (element i is
+  // handled by thread i mod 1024, so partners at distance < 32 sit in the same warp) — 28 barriers instead of 66 for 2048 keys.
   if (sizeof(KT) == 4) {
     // 32-bit keys: one 64-bit word (key, index) per element, a single compare per exchange
     u64* sk = (u64*)rs_small_dyn;
     for (int i = t; i < N; i += 1024) sk[i] = i < n ? (((u64)kin[i] << 32) | (u64)(u32)i) : ~(u64)0;
     __syncthreads();
     for (int k = 2; k <= N; k <<= 1) {
-      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      int jj = k >> 1;
+      for (; jj >= 32 || (N < 64 && jj > 0); jj >>= 1) {
         for (int q = t; q < (N >> 1); q += 1024) {
           const int lo = ((q & ~(jj - 1)) << 1) | (q & (jj - 1)), hi = lo | jj;
           const bool up = (lo & k) == 0;
           const u64 a = sk[lo], b = sk[hi];
           if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+        }
+        __syncthreads();
+      }
+      if (jj > 0) {
+        for (int i = t; i < N; i += 1024) {
+          u64 v = sk[i];
+          const bool up = (i & k) == 0;
+          for (int j2 = jj; j2 > 0; j2 >>= 1) {
+            const u64 o = __shfl_xor_sync(0xffffffffu, v, j2);
+            const bool keep_min = (((i & j2) == 0) == up);
+            v = keep_min ? (v < o ? v : o) : (v > o ? v : o);
+          }
+          sk[i] = v;
         }
         __syncthreads();
       }
@@ -73,7 +90,8 @@ __global__ void __launch_bounds__(1024) rs_small_kernel(const SortJobs* __restri
     for (int i = t; i < N; i += 1024) { sk[i] = i < n ? kin[i] : (KT)~(KT)0; sv[i] = (unsigned short)i; }
     __syncthreads();
     for (int k = 2; k <= N; k <<= 1) {
-      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      int jj = k >> 1;
+      for (; jj >= 32 || (N < 64 && jj > 0); jj >>= 1) {
         for (int q = t; q < (N >> 1); q += 1024) {
           const int lo = ((q & ~(jj - 1)) << 1) | (q & (jj - 1)), hi = lo | jj;
           const bool up = (lo & k) == 0;
@@ -81,6 +99,21 @@ __global__ void __launch_bounds__(1024) rs_small_kernel(const SortJobs* __restri
           const unsigned short ia = sv[lo], ib = sv[hi];
           const bool gt = a > b || (a == b && ia > ib);
           if (gt == up) { sk[lo] = b; sk[hi] = a; sv[lo] = ib; sv[hi] = ia; }
+        }
+        __syncthreads();
+      }
+      if (jj > 0) {
+        for (int i = t; i < N; i += 1024) {
+          KT v = sk[i]; u32 vi = sv[i];
+          const bool up = (i & k) == 0;
+          for (int j2 = jj; j2 > 0; j2 >>= 1) {
+            const KT o = __shfl_xor_sync(0xffffffffu, v, j2);
+            const u32 oi = __shfl_xor_sync(0xffffffffu, vi, j2);
+            const bool less = v < o || (v == o && vi < oi);
+            const bool keep_min = (((i & j2) == 0) == up);
+            if (keep_min != less) { v = o; vi = oi; }
+          }
+          sk[i] = v; sv[i] = (unsigned short)vi;
         }
         __syncthreads();
       }
@@ -229,11 +262,12 @@ void sort_init_attributes() {
   cudaFuncSetAttribute(rs_small_kernel<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, RsSmallBytes<u32>::value);
   cudaFuncSetAttribute(rs_small_kernel<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, RsSmallBytes<u64>::value);
 }
-void launch_sort(cudaStream_t s, const SortJobs* ab, const SortJobs* ba, int njobs, int G, int cap, int np, int key_bytes, uint64_t* launches) {
+void launch_sort(cudaStream_t s, const SortJobs* ab, const SortJobs* ba, int njobs, int G, int cap, int np, int key_bytes, uint64_t* launches, bool small_only) {
   dim3 grid(grid_x((cap + RS_TILE - 1) / RS_TILE, G, njobs), njobs, G);
-  if (key_bytes == 4) klaunch(rs_small_kernel<u32>, dim3(dim3(1, njobs, G)), dim3(1024), (size_t)RsSmallBytes<u32>::value, s, ab);
-  else klaunch(rs_small_kernel<u64>, dim3(dim3(1, njobs, G)), dim3(1024), (size_t)RsSmallBytes<u64>::value, s, ab);
+  if (key_bytes == 4) klaunch(rs_small_kernel<u32>, dim3(dim3(1, njobs, G)), dim3(1024), (size_t)RsSmallBytes<u32>::value, s, ab, small_only ? 1 : 0);
+  else klaunch(rs_small_kernel<u64>, dim3(dim3(1, njobs, G)), dim3(1024), (size_t)RsSmallBytes<u64>::value, s, ab, small_only ? 1 : 0);
   if (launches) *launches += 1;
+  if (small_only) return;
   for (int p = 0; p < np; p++) {
     const SortJobs* J = (p & 1) ? ba : ab;
     if (key_bytes == 4) {

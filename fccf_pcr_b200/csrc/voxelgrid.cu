@@ -266,7 +266,7 @@ void launch_voxelgrid(cudaStream_t s, const Batch& b, int stage, int ncloud, uin
       A.st[c] = &st->vg[stage][c];
       A.keys[c] = cw.keyA;
       A.ticket[c] = &st->tickets[0 + c];
-      SortJob j; j.kin = cw.keyA; j.kout = cw.keyB; j.vin = cw.idxA; j.vout = cw.idxB; j.n = &st->vg[stage][c].n_in; j.nbits = &st->vg[stage][c].nbits;
+      SortJob j; j.miss = nullptr; j.kin = cw.keyA; j.kout = cw.keyB; j.vin = cw.idxA; j.vout = cw.idxB; j.n = &st->vg[stage][c].n_in; j.nbits = &st->vg[stage][c].nbits;
       j.hist = cw.hist; j.ticket = &st->tickets[2 + c];
       ab.j[c] = j;
       SortJob k = j; k.kin = cw.keyB; k.kout = cw.keyA; k.vin = cw.idxB; k.vout = cw.idxA;
