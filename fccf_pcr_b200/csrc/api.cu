@@ -630,7 +630,8 @@ static int group_enqueue(fccf_ctx* ctx, Group* g, int G, int pair0, const float*
   for (int l = 0; l < G; l++) nmax = std::max(nmax, std::max(n_src[l], n_tar[l]));
   bool fast = ctx->vg_fast && g->vf.ncl > 0 && nmax <= (size_t)g->vf.stride && nmax <= (size_t)vg_fast_nmax();
   if (fast && ctx->fast_miss_ttl > 0 && leaf <= ctx->fast_miss_leaf) { fast = false; ctx->fast_miss_ttl--; }
-  const bool lean = ctx->lean_ok && ctx->use_graph;
+  static const bool no_lean = getenv("FCCF_NO_LEAN") && getenv("FCCF_NO_LEAN")[0] == '1';
+  const bool lean = ctx->lean_ok && ctx->use_graph && !no_lean;
   g->fast = fast; g->leaf = leaf; g->stage_timed = ctx->stage_timing; g->lean = lean;
   int rc = group_launch(ctx, g, G, fast, lean);
   if (rc) return rc;
@@ -649,18 +650,21 @@ static int group_finish(fccf_ctx* ctx, Group* g, float* T_out, fccf_timing* tm) 
     // the "lean" sorts without radix passes (a list beyond the one-CTA sort raises ST_SORT_MISS).  The call blocks and
     // the raw clouds are still on the device, so a miss is answered by replaying the sequence without that part.
     if (g->fast) ctx->fast_runs++;
-    bool vmiss = false, smiss = false;
-    for (int l = 0; l < g->G; l++) { const int stt = g->lanes[l].h_st->status; vmiss = vmiss || (stt & ST_VG_FAST_MISS); smiss = smiss || (stt & ST_SORT_MISS); }
-    vmiss = vmiss && g->fast; smiss = smiss && g->lean;
-    if (vmiss) { ctx->fast_misses++; ctx->fast_miss_leaf = std::max(ctx->fast_miss_leaf, g->leaf); ctx->fast_miss_ttl = 64; }
-    if (smiss) { ctx->lean_ok = false; ctx->lean_ttl = 64; }
-    if (vmiss || smiss) {
+    bool smiss_any = false;
+    for (int attempt = 0; attempt < 3; attempt++) {      // a replay can bring the other miss to light (clouds that the cluster VoxelGrid dropped have no lists)
+      bool vmiss = false, smiss = false;
+      for (int l = 0; l < g->G; l++) { const int stt = g->lanes[l].h_st->status; vmiss = vmiss || (stt & ST_VG_FAST_MISS); smiss = smiss || (stt & ST_SORT_MISS); }
+      vmiss = vmiss && g->fast; smiss = smiss && g->lean;
+      if (vmiss) { ctx->fast_misses++; ctx->fast_miss_leaf = std::max(ctx->fast_miss_leaf, g->leaf); ctx->fast_miss_ttl = 64; }
+      if (smiss) { ctx->lean_ok = false; ctx->lean_ttl = 64; smiss_any = true; }
+      if (!vmiss && !smiss) break;
       g->fast = g->fast && !vmiss; g->lean = g->lean && !smiss;
       int rc = group_launch(ctx, g, g->G, g->fast, g->lean);
       if (rc) return rc;
       CK(cudaStreamSynchronize(g->stream));
       CK(cudaGetLastError());
     }
+    const bool smiss = smiss_any;
     // lean sequences from the next call on, once every lane's lists sit well inside the one-CTA sort
     if (!smiss) {
       int longest = 0;

@@ -762,3 +762,40 @@ def test_face_growing_next_to_its_thresholds(ctx, orc, seed):
         assert np.array_equal(ctx.blob(name), orc.blob(name)), name
     assert _rel_rows(ctx.blob("face_plane1"), orc.blob("face_plane1"), 7, [[0, 1, 2], [3, 4, 5], [6]]) <= PLANE_TOL
     np.testing.assert_allclose(ctx.blob("face_theta1"), orc.blob("face_theta1"), atol=0.02)
+
+
+def test_lean_sequences_and_their_miss():
+    """Once a registration has shown hypothesis / fine-verify lists inside the one-CTA sort, the next sequences are
+    captured without the radix-pass launches behind those sorts; a pair whose lists are longer (here: 28k leftover
+    points for the fine-verify table) then raises ST_SORT_MISS and is replayed through the full sequence.  Both must
+    give exactly what a fresh context gives."""
+    import fccf_pcr_b200 as fccf
+
+    small, ls = scenes.make_pair("indoor", 20000, 7), 0.2
+    big, lb = scenes.make_pair("indoor", 50000, 1), 0.1
+    fresh = fccf.Context(0)
+    T_small = fresh.register(small[0], small[1], ls).copy()
+    full_launches = fresh.timing.n_launches
+    assert fresh.blob("n_hyp").sum() < 3000 and len(fresh.blob("sub1")) // 3 < 3000
+    fresh.close()
+    fresh = fccf.Context(0)
+    T_big = fresh.register(big[0], big[1], lb).copy()
+    assert len(fresh.blob("sub1")) // 3 > 4096
+    fresh.close()
+    c = fccf.Context(0)
+    c.register(small[0], small[1], ls)                        # full sequence; its lists are short
+    T1 = c.register(small[0], small[1], ls).copy()            # lean sequence
+    assert c.timing.n_launches < full_launches, (c.timing.n_launches, full_launches)
+    assert np.array_equal(T1, T_small, equal_nan=True)
+    T2 = c.register(big[0], big[1], lb).copy()                # lean sequence misses, full sequence replayed
+    assert np.array_equal(T2, T_big, equal_nan=True)
+    T3 = c.register(small[0], small[1], ls).copy()            # lean is off for a while: full sequence again
+    assert c.timing.n_launches >= full_launches
+    assert np.array_equal(T3, T_small, equal_nan=True)
+    # a batch with both kinds of pairs in one launch sequence, on a context that has lean sequences switched on
+    c2 = fccf.Context(0)
+    c2.register(small[0], small[1], lb)
+    Ts_lb = c2.register(small[0], small[1], lb).copy()
+    Tb = c2.register_batch([small[0], big[0], small[0]], [small[1], big[1], small[1]], lb)
+    assert np.array_equal(Tb[0], Ts_lb, equal_nan=True) and np.array_equal(Tb[1], T_big, equal_nan=True) and np.array_equal(Tb[2], Ts_lb, equal_nan=True)
+    c.close(); c2.close()
