@@ -1,5 +1,7 @@
 // fccf_internal.h — device workspace layout and kernel launchers of libfccf (not part of the ABI).
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -247,7 +249,9 @@ inline cudaError_t klaunch(void (*k)(KA...), dim3 g, dim3 b, size_t smem, cudaSt
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = fccf_pdl_on() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k, KA(a)...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, k, KA(a)...);
+  if (e != cudaSuccess && getenv("FCCF_DEBUG_LAUNCH")) fprintf(stderr, "libfccf: launch failed (%s): grid %u %u %u, block %u, dynamic smem %zu\n", cudaGetErrorString(e), g.x, g.y, g.z, b.x, smem);
+  return e;
 }
 #endif
 
