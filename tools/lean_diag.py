@@ -1,5 +1,7 @@
+"""Lean sequences and their miss path: launches and results of small / small / big / big registrations on one context
+against a fresh context (FCCF_NO_LEAN=1 for the comparison).  python tools/lean_diag.py"""
 import os, sys, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fccf_pcr_b200 as fccf
 from fccf_pcr_b200 import scenes
 small, ls = scenes.make_pair("indoor", 20000, 7), 0.2
