@@ -799,3 +799,26 @@ def test_lean_sequences_and_their_miss():
     Tb = c2.register_batch([small[0], big[0], small[0]], [small[1], big[1], small[1]], lb)
     assert np.array_equal(Tb[0], Ts_lb, equal_nan=True) and np.array_equal(Tb[1], T_big, equal_nan=True) and np.array_equal(Tb[2], Ts_lb, equal_nan=True)
     c.close(); c2.close()
+
+
+@pytest.mark.parametrize("res", [0.25, 1.0, 2.0, 0.3])
+def test_score_hypotheses_other_lattices(oracle_mod, res):
+    """The scoring sweep has three shared-memory forms: 1/res folded into the transform rows (power-of-two lattices with
+    1/res >= 1: 0.25, 0.5, 1.0), the unscaled power-of-two form (res = 2) and the division form (res = 0.3).  Scores
+    against fine_verify of the oracle run with the same voxel size, per-voxel counts bit-exact."""
+    import fccf_pcr_b200 as fccf
+
+    rng = np.random.default_rng(int(res * 100))
+    s1 = (rng.uniform(-1, 1, (4000, 3)) * [5, 4, 1.5]).astype(np.float32)
+    s2, _ = _moved(rng, s1, 3500, 0, 0)
+    Ts = np.stack([_moved(rng, s1, 1, rng.uniform(-8, 8), rng.uniform(-0.4, 0.4, 3))[1] for _ in range(24)])
+    o = oracle_mod.Oracle(fine_verify_voxel_size=res)
+    c = fccf.Context(0, fine_verify_voxel_size=res)
+    sc = c.score_hypotheses(Ts, s1, s2)
+    for k in range(len(Ts)):
+        so, rows = o.fine_verify(Ts[k], s1, s2)
+        assert abs(sc[k] - so) <= 1e-5 * max(so, 1e-3), (res, k, sc[k], so)
+        if k % 8 == 0:
+            rows = rows[np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))]
+            assert np.array_equal(c.score_counts(k), rows)
+    c.close()
